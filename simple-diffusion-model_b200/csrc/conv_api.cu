@@ -1,0 +1,159 @@
+// Host launchers (C-ABI) for the tcgen05 implicit-GEMM kernel: 3x3 conv (stride 1 / stride 2 on parity
+// planes), 4x4 stride-2 transposed conv (four output-parity GEMMs), and plain / batched NT GEMM.
+#include "host_util.h"
+#include "igemm.h"
+#include "sdm_b200.h"
+#include <cstring>
+
+namespace b2 {
+int launch_igemm_nt(int dtype, const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& p, int block_n, cudaStream_t st);
+}
+using namespace b2;
+
+static int pick_block_n(int cout, long long m_tiles, int groups) {
+    const int sms = device_sm_count();
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        if (cout < bn && i < 2) continue;
+        const long long tiles = m_tiles * ((cout + bn - 1) / bn) * groups;
+        if (tiles >= sms || i == 2) return bn;
+    }
+    return 64;
+}
+
+// Spatial box of <=128 output pixels: full rows first, then rows, then images.
+static void pick_box(int W, int H, int N, int* wb, int* hb, int* nb) {
+    *wb = W < 128 ? W : 128;
+    int rem = 128 / *wb;
+    *hb = H < rem ? H : rem;
+    rem /= *hb;
+    *nb = N < rem ? N : rem;
+    if (*nb < 1) *nb = 1;
+}
+
+extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
+                              const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
+                              const void* residual, long long ldr, float* gn_stats, int gn_groups, int dtype,
+                              void* stream) {
+    const int eb = dtype == 0 ? 2 : 4;
+    const int bk = 128 / eb;
+    if (Cin % bk != 0) return set_error("b2_conv2d_nhwc: Cin=%d must be a multiple of %d", Cin, bk);
+    if (Cout % 8 != 0) return set_error("b2_conv2d_nhwc: Cout=%d must be a multiple of 8", Cout);
+    if (mode < 0 || mode > 2) return set_error("b2_conv2d_nhwc: bad mode %d", mode);
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.W = W; p.H = H; p.N = N;
+    pick_box(W, H, N, &p.wb, &p.hb, &p.nb);
+    p.tiles_w = (W + p.wb - 1) / p.wb;
+    p.tiles_h = (H + p.hb - 1) / p.hb;
+    p.tiles_n = (N + p.nb - 1) / p.nb;
+    p.kb_per_tap = Cin / bk;
+    p.Cout = Cout;
+    p.out = y;
+    p.bias = bias;
+    p.alpha = 1.0f;
+    p.act = act;
+    p.residual = residual;
+    p.gn_stats = gn_stats;
+    p.cpg = gn_groups > 0 ? Cout / gn_groups : 0;
+    if (gn_stats && (p.cpg < 4 || (p.cpg & (p.cpg - 1)) != 0))
+        return set_error("b2_conv2d_nhwc: fused GroupNorm statistics need a power-of-two >=4 channels per group (got %d)", p.cpg);
+    int a_images = N;
+    if (mode == 0) {          // 3x3, stride 1, pad 1
+        p.groups = 1; p.taps = 9;
+        for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+            p.tap_dh[kh * 3 + kw] = kh - 1; p.tap_dw[kh * 3 + kw] = kw - 1; p.tap_dn[kh * 3 + kw] = 0;
+        }
+        p.oN = (long long)H * W * ldy; p.oH = (long long)W * ldy; p.oW = ldy;
+        p.rN = (long long)H * W * ldr; p.rH = (long long)W * ldr; p.rW = ldr;
+    } else if (mode == 1) {   // 3x3, stride 2, pad 1; x = parity planes [2][2][N][H][W][Cin], (H, W) = output size
+        p.groups = 1; p.taps = 9;
+        for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+            const int pr = (kh != 1), pc = (kw != 1);
+            p.tap_dh[kh * 3 + kw] = (kh == 0) ? -1 : 0;
+            p.tap_dw[kh * 3 + kw] = (kw == 0) ? -1 : 0;
+            p.tap_dn[kh * 3 + kw] = (pr * 2 + pc) * N;
+        }
+        a_images = 4 * N;
+        p.oN = (long long)H * W * ldy; p.oH = (long long)W * ldy; p.oW = ldy;
+        p.rN = (long long)H * W * ldr; p.rH = (long long)W * ldr; p.rW = ldr;
+    } else {                  // transposed 4x4, stride 2, pad 1; output 2H x 2W; group = output parity (a, b)
+        p.groups = 4; p.taps = 4;
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+            const int g = a * 2 + b;
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
+                const int t = g * 4 + i * 2 + j;
+                p.tap_dh[t] = (i == 0) ? 0 : (a == 0 ? -1 : 1);
+                p.tap_dw[t] = (j == 0) ? 0 : (b == 0 ? -1 : 1);
+                p.tap_dn[t] = 0;
+            }
+            p.goff[g] = ((long long)a * (2 * W) + b) * ldy;
+        }
+        p.oN = (long long)4 * H * W * ldy; p.oH = (long long)2 * (2 * W) * ldy; p.oW = 2 * ldy;
+        p.rN = (long long)4 * H * W * ldr; p.rH = (long long)2 * (2 * W) * ldr; p.rW = 2 * ldr;
+        if (residual) return set_error("b2_conv2d_nhwc: residual not supported for transposed conv");
+    }
+    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    const int bn = pick_block_n(Cout, m_tiles, p.groups);
+    p.n_tiles = (Cout + bn - 1) / bn;
+    p.b_mode = 0;
+
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)a_images};
+        uint64_t str[3] = {(uint64_t)ldx * eb, (uint64_t)W * ldx * eb, (uint64_t)H * W * ldx * eb};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
+        if (make_tmap_4d(&ta, x, eb, dims, str, box)) return 1;
+    }
+    {
+        const uint64_t ktot = (uint64_t)p.taps * Cin;
+        uint64_t dims[4] = {ktot, (uint64_t)Cout, (uint64_t)p.groups, 1};
+        uint64_t str[3] = {ktot * eb, ktot * Cout * eb, ktot * Cout * p.groups * eb};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)bn, 1, 1};
+        if (make_tmap_4d(&tb, wpacked, eb, dims, str, box)) return 1;
+    }
+    return launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream);
+}
+
+// C[b2][b1][m][n] = alpha * sum_k A[b2][b1][m][k] * B[b2][b1][n][k] (+ bias[n]) (act) (+ residual)
+// Strides are in elements. b1/b2 = 1 for a plain GEMM (then B is shared: its batch strides are ignored).
+extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long long a_s2, const void* B, long long ldb,
+                          long long b_s1, long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2,
+                          int M, int Ncols, int K, int batch1, int batch2, const float* bias, float alpha, int act,
+                          const void* residual, long long ldr, int out_fp32, int dtype, void* stream) {
+    const int eb = dtype == 0 ? 2 : 4;
+    const int bk = 128 / eb;
+    if (K % bk != 0) return set_error("b2_gemm_nt: K=%d must be a multiple of %d", K, bk);
+    if (residual && (batch1 != 1 || batch2 != 1)) return set_error("b2_gemm_nt: residual only for unbatched GEMM");
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.W = M; p.H = batch1; p.N = batch2;
+    p.wb = 128; p.hb = 1; p.nb = 1;
+    p.tiles_w = (M + 127) / 128; p.tiles_h = batch1; p.tiles_n = batch2;
+    p.groups = 1; p.taps = 1; p.kb_per_tap = K / bk;
+    p.Cout = Ncols;
+    p.out = C; p.oN = c_s2; p.oH = c_s1; p.oW = ldc;
+    p.residual = residual; p.rN = 0; p.rH = 0; p.rW = ldr;
+    p.bias = bias; p.alpha = alpha; p.act = act; p.out_fp32 = out_fp32;
+    const bool batched = (batch1 > 1 || batch2 > 1);
+    p.b_mode = batched ? 1 : 0;
+    const int bn = pick_block_n(Ncols, (long long)p.tiles_w * batch1 * batch2, 1);
+    p.n_tiles = (Ncols + bn - 1) / bn;
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch1, (uint64_t)batch2};
+        uint64_t str[3] = {(uint64_t)lda * eb, (uint64_t)(batch1 > 1 ? a_s1 : lda * M) * eb,
+                           (uint64_t)(batch2 > 1 ? a_s2 : lda * M * batch1) * eb};
+        uint32_t box[4] = {(uint32_t)bk, 128, 1, 1};
+        if (make_tmap_4d(&ta, A, eb, dims, str, box)) return 1;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)K, (uint64_t)Ncols, (uint64_t)batch1, (uint64_t)batch2};
+        uint64_t str[3] = {(uint64_t)ldb * eb, (uint64_t)(batch1 > 1 ? b_s1 : ldb * Ncols) * eb,
+                           (uint64_t)(batch2 > 1 ? b_s2 : ldb * Ncols * batch1) * eb};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)bn, 1, 1};
+        if (make_tmap_4d(&tb, B, eb, dims, str, box)) return 1;
+    }
+    return launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream);
+}

@@ -1,0 +1,72 @@
+#include "host_util.h"
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+namespace b2 {
+
+static thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+const char* last_error() { return g_err; }
+
+int device_sm_count() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (sms[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
+    }
+    return sms[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4],
+                 const uint64_t strides_bytes[3], const uint32_t box[4]) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("TMA base pointer not 16-byte aligned");
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < 3; ++i) {
+        gs[i] = strides_bytes[i];
+        if (gs[i] % 16 != 0) return set_error("TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+    }
+    if (box[0] * elem_bytes != 128) return set_error("TMA inner box must be 128 bytes");
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(out, dt, 4, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error("cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu box %u %u %u %u", (int)r,
+                         (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                         (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
+    return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,43 @@
+// Parameter blocks shared by the tcgen05 implicit-GEMM kernels and their host launchers.
+#pragma once
+#include <stdint.h>
+
+namespace b2 {
+
+constexpr int kMaxTaps = 16;   // 9 for 3x3, 4 groups x 4 taps for the 4x4/s2 transposed conv
+constexpr int kMaxGroups = 4;
+
+// C[pixel, cout] = sum_{tap, cin} A[pixel + tap offset, cin] * Bw[group][cout][tap*Cin + cin]
+// A is reached through a 4-D TMA map (cin | W | H | N); out-of-image taps are zero-filled by TMA.
+struct IgemmParams {
+    int W, H, N;                 // extents of A-map dims 1..3
+    int wb, hb, nb;              // A box over those dims (wb*hb*nb <= 128 rows of the MMA tile)
+    int tiles_w, tiles_h, tiles_n;
+    int n_tiles;                 // ceil(Cout / BLOCK_N)
+    int groups;                  // weight slabs (transposed-conv output parities), else 1
+    int taps;                    // taps per group
+    int kb_per_tap;              // 128-byte K blocks per tap (= Cin*sizeof(T)/128)
+    int b_mode;                  // 0: B batch coords = (group, 0); 1: = (h, n) of the A tile (batched GEMM)
+    int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dn[kMaxTaps];   // index: group*taps + tap
+    int Cout;                    // valid output columns
+    // output addressing (elements): out + n*oN + h*oH + w*oW + goff[group] + column
+    void* out;
+    long long oN, oH, oW;
+    long long goff[kMaxGroups];
+    int out_fp32;                // bf16 kernels only: write fp32 instead of bf16
+    const void* residual;        // optional, same dtype as out; rN/rH/rW addressing, no group offset
+    long long rN, rH, rW;
+    const float* bias;           // optional [Cout]
+    float alpha;                 // acc *= alpha before bias
+    int act;                     // 0 none, 1 swish
+    float* gn_stats;             // optional [N][Cout/cpg][2] (sum, sum of squares), accumulated atomically
+    int cpg;                     // channels per GroupNorm group
+};
+
+// C[m, n] (+)= sum_k A[k, m] * B[k + shift, n]  -- both operands MN-major ("TN" GEMM): weight
+// gradients (k = pixel), P.V in attention (k = key).
+struct GemmTnParams {
+    int dummy;
+};
+
+}  // namespace b2

@@ -1,0 +1,314 @@
+// tcgen05 implicit-GEMM ("NT": both operands K-major) for sm_100a.
+//
+// One persistent, warp-specialised kernel serves every dense contraction of the U-Net forward and
+// data-gradient paths (reference call sites: models/custom_layers.py:224 Conv2d 3x3, :196 Conv2d 3x3/s2,
+// :174 ConvTranspose2d 4x4/s2, :116/:119 attention Linear layers, :144 q.k^T):
+//   * A (activations, NHWC) arrives through a 4-D TMA map; a filter tap is just a shifted box, and the
+//     zero padding of the convolution is TMA's out-of-bounds fill -- no im2col buffer ever exists.
+//   * B (weights, [Cout][tap][Cin]) arrives through a second TMA map.
+//   * warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+//     (TMEM -> registers -> bias / Swish / GroupNorm partial sums / residual -> global).
+//   * accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "ptx.cuh"
+#include "igemm.h"
+#include "host_util.h"
+
+namespace b2 {
+
+template <int BLOCK_N, int STAGES>
+struct IgemmSmem {
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int B_BYTES = BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;   // +1024: manual alignment slack
+};
+
+struct TileCoord { int nt, w0, h0, n0, g; };
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+    TileCoord c;
+    c.nt = tile % p.n_tiles;  tile /= p.n_tiles;
+    c.w0 = (tile % p.tiles_w) * p.wb;  tile /= p.tiles_w;
+    c.h0 = (tile % p.tiles_h) * p.hb;  tile /= p.tiles_h;
+    c.n0 = (tile % p.tiles_n) * p.nb;  tile /= p.tiles_n;
+    c.g = tile;
+    return c;
+}
+
+template <int GS>
+__device__ __forceinline__ void gn_partial(const float (&v)[32], bool valid, bool uniform, int lane,
+                                           float* stats_row /* stats + n*G*2 */, int group0) {
+    constexpr int NG = 32 / GS;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        float s1 = 0.f, s2 = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < GS; ++i) { float x = v[g * GS + i]; s1 += x; s2 += x * x; }
+        }
+        if (uniform) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == 0) {
+                atomicAdd(stats_row + (group0 + g) * 2 + 0, s1);
+                atomicAdd(stats_row + (group0 + g) * 2 + 1, s2);
+            }
+        } else if (valid) {
+            atomicAdd(stats_row + (group0 + g) * 2 + 0, s1);
+            atomicAdd(stats_row + (group0 + g) * 2 + 1, s2);
+        }
+    }
+}
+
+template <typename T, int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ IgemmParams p) {
+    using S = IgemmSmem<BLOCK_N, STAGES>;
+    constexpr bool kTF32 = (sizeof(T) == 4);
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                 : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int k_iters = p.taps * p.kb_per_tap;
+    constexpr int BK_ELEMS = 128 / sizeof(T);
+    const uint32_t a_bytes = static_cast<uint32_t>(p.wb * p.hb * p.nb) * 128u;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile);
+                const int bb2 = p.b_mode ? tc.h0 : tc.g;
+                const int bb3 = p.b_mode ? tc.n0 : 0;
+                for (int t = 0; t < p.taps; ++t) {
+                    const int ti = tc.g * p.taps + t;
+                    const int aw = tc.w0 + p.tap_dw[ti], ah = tc.h0 + p.tap_dh[ti], an = tc.n0 + p.tap_dn[ti];
+                    for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                        uint8_t* b_dst = a_dst + S::A_BYTES;
+                        mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
+                        tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
+                        tma_load_4d(b_dst, &tmB, &full[s], (t * p.kb_per_tap + kb) * BK_ELEMS, tc.nt * BLOCK_N, bb2, bb3);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_ss<kTF32>(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const int w_in = row % p.wb;
+        const int h_in = (row / p.wb) % p.hb;
+        const int n_in = row / (p.wb * p.hb);
+        const int G = p.gn_stats ? (p.Cout / p.cpg) : 0;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile);
+            const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
+            const bool valid = (n_in < p.nb) && (w < p.W) && (h < p.H) && (n < p.N);
+            const long long o_off = n * p.oN + h * p.oH + w * p.oW + p.goff[tc.g];
+            const long long r_off = n * p.rN + h * p.rH + w * p.rW;
+            const int n_lane0 = __shfl_sync(0xffffffffu, n, 0);
+            const bool uniform = __all_sync(0xffffffffu, n == n_lane0 || !valid) && __shfl_sync(0xffffffffu, (int)valid, 0);
+
+            mbar_wait(&tfull[acc], acc_ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                const int col0 = tc.nt * BLOCK_N + ch * 32;
+                if (col0 >= p.Cout) break;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                tmem_ld_wait();
+                const int ncols = min(32, p.Cout - col0);
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(p.bias + col0 + i);
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = swishf(v[i]);
+                }
+                if (p.gn_stats && ncols == 32) {
+                    float* srow = p.gn_stats + static_cast<long long>(uniform ? n_lane0 : (valid ? n : 0)) * G * 2;
+                    const int cpg = p.cpg;
+                    if (cpg >= 32)      gn_partial<32>(v, valid, uniform, lane, srow, col0 / cpg);
+                    else if (cpg == 16) gn_partial<16>(v, valid, uniform, lane, srow, col0 / 16);
+                    else if (cpg == 8)  gn_partial<8>(v, valid, uniform, lane, srow, col0 / 8);
+                    else                gn_partial<4>(v, valid, uniform, lane, srow, col0 / 4);
+                }
+                if (valid) {
+                    const bool f32out = kTF32 || p.out_fp32;
+                    if (f32out) {
+                        float* o = reinterpret_cast<float*>(p.out) + o_off + col0;
+                        if (p.residual) {
+                            const float* rs = reinterpret_cast<const float*>(p.residual) + r_off + col0;
+                            if (ncols == 32) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float4 x = __ldg(reinterpret_cast<const float4*>(rs) + i);
+                                    v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += rs[i];
+                            }
+                        }
+                        if (ncols == 32) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = v[i];
+                        }
+                    } else {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_off + col0;
+                        if (p.residual) {
+                            const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0;
+                            if (ncols == 32) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    uint4 x = __ldg(reinterpret_cast<const uint4*>(rs) + i);
+                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        float2 f = __bfloat1622float2(h2[j]);
+                                        v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __bfloat162float(rs[i]);
+                            }
+                        }
+                        if (ncols == 32) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 x;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+                                reinterpret_cast<uint4*>(o)[i] = x;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = __float2bfloat16(v[i]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+template <typename T, int BLOCK_N, int STAGES>
+static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& p, int num_sms, cudaStream_t st) {
+    using S = IgemmSmem<BLOCK_N, STAGES>;
+    auto kern = igemm_nt_kernel<T, BLOCK_N, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return set_error("igemm_nt: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    kern<<<grid, 192, S::TOTAL, st>>>(a, b, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("igemm_nt launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_igemm_nt(int dtype /*0 bf16, 1 fp32(tf32)*/, const CUtensorMap& a, const CUtensorMap& b,
+                    const IgemmParams& p, int block_n, cudaStream_t st) {
+    const int sms = device_sm_count();
+    if (dtype == 0) {
+        if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4>(a, b, p, sms, st);
+        if (block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6>(a, b, p, sms, st);
+        if (block_n == 64)  return launch_cfg<__nv_bfloat16, 64, 8>(a, b, p, sms, st);
+    } else {
+        if (block_n == 256) return launch_cfg<float, 256, 4>(a, b, p, sms, st);
+        if (block_n == 128) return launch_cfg<float, 128, 6>(a, b, p, sms, st);
+        if (block_n == 64)  return launch_cfg<float, 64, 8>(a, b, p, sms, st);
+    }
+    return set_error("igemm_nt: unsupported block_n %d", block_n);
+}
+
+}  // namespace b2
