@@ -31,10 +31,12 @@ int b2_version(void);
  * mode 2: ConvTranspose2d 4x4 stride 2 pad 1   (custom_layers.py:174-179), (H, W) = INPUT size, y is 2H x 2W
  * wpacked: weights in kernel layout from b2_pack_conv_weight. act: 0 none, 1 Swish (custom_layers.py:18-20).
  * residual (optional, mode 0/1): added after the activation. gn_stats (optional): [N][gn_groups][2] fp32,
- * must be zeroed by the caller; receives per-(image, group) sum and sum of squares of the written values. */
+ * must be zeroed by the caller; receives per-(image, group) sum and sum of squares of the written values.
+ * out_mode 0: y is NHWC in `dtype`; out_mode 1 (mode 0 only): y is fp32 NCHW [N][Cout][H][W] -- the final
+ * layer writes the network output directly (models/U_Net.py:172); act 2 = tanh (image_recon, U_Net.py:126). */
 int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* wpacked,
                    const float* bias, int Cout, void* y, long long ldy, int act, const void* residual,
-                   long long ldr, float* gn_stats, int gn_groups, int dtype, void* stream);
+                   long long ldr, float* gn_stats, int gn_groups, int out_mode, int dtype, void* stream);
 
 /* C = alpha * A . B^T (+bias) (act) (+residual); A [M][K], B [Ncols][K] (nn.Linear weight layout,
  * custom_layers.py:116,119; q.k^T custom_layers.py:144).  batch1/batch2 > 1: batched with element strides
@@ -43,6 +45,60 @@ int b2_gemm_nt(const void* A, long long lda, long long a_s1, long long a_s2, con
                long long b_s1, long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2, int M,
                int Ncols, int K, int batch1, int batch2, const float* bias, float alpha, int act,
                const void* residual, long long ldr, int out_fp32, int dtype, void* stream);
+
+/* ---- memory-bound forward kernels ----------------------------------------------------------------------- */
+
+/* fp32 NCHW image -> NHWC `dtype` with channels zero-padded to Cpad (network input edge, U_Net.py:155). */
+int b2_nchw_to_nhwc_pad(const float* x, void* y, int N, int C, int H, int W, int Cpad, int dtype, void* stream);
+/* NHWC `dtype` (row stride ldx) -> fp32 NCHW (module-boundary edge of the standalone blocks). */
+int b2_nhwc_to_nchw(const void* x, long long ldx, float* y, int N, int C, int H, int W, int dtype, void* stream);
+/* planes[pr][pc][n][i][j][:] = x[n][2i+pr][2j+pc][:]; feeds b2_conv2d_nhwc mode 1 (custom_layers.py:196). */
+int b2_space_to_depth2(const void* x, long long ldx, void* planes, int N, int H, int W, int C, int dtype, void* stream);
+/* fp32 master weights -> kernel layout.  kind 0: Conv2d [Cout][Cin][3][3] -> [Cout][9][Cin_pad];
+ * kind 1: same weight -> data-gradient layout [Cin][9 flipped][Cout]; kind 2: ConvTranspose2d [Cin][Cout][4][4]
+ * -> [4 parities][Cout][4 taps][Cin]; kind 3: Linear [rows=Cout][cols=Cin] -> [rows][Cin_pad].
+ * dtype 1 rounds to TF32 (round-to-nearest) so the tensor core's truncation is exact. */
+int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int Cin_pad, int dtype, void* stream);
+/* out = s*(gamma*(y-mean)*rstd+beta) + s (+residual): GroupNorm x AdaGN (custom_layers.py:35-45) fused with the
+ * ResidualBlock add (custom_layers.py:282-287).  stats from b2_conv2d_nhwc; s = y_scale(emb) [B][C] with row
+ * stride s_bstride (0 broadcasts one embedding over the batch, as the samplers do). */
+int b2_adagn_apply(const void* y, long long ldy, const float* stats, const float* gamma, const float* beta,
+                   const float* s, long long s_bstride, const void* residual, long long ldr, void* out, long long ldo,
+                   int N, int HW, int C, int groups, float eps, int dtype, void* stream);
+/* P[b][i][j] = softmax over the QUERY index i of S[b][i][j] (custom_layers.py:147); S fp32, P `dtype`, row stride ldp. */
+int b2_softmax_query_axis(const float* S, void* P, int B, int Pq, int Pk, long long ldp, int dtype, void* stream);
+/* out[b1][b2][c][r] = in[b1][b2][r][c] (V^T for P.V, custom_layers.py:150). */
+int b2_transpose_batched(const void* in, long long ld_in, long long in_s1, long long in_s2, void* out, long long ld_out,
+                         long long out_s1, long long out_s2, int R, int Ccols, int B1, int B2, int dtype, void* stream);
+/* [sin(t f_k), cos(t f_k)] (custom_layers.py:84-90); t int64 [B]. */
+int b2_sinusoid_embedding(const long long* t, float* out, int B, int dim, void* stream);
+/* fp32 CUDA-core GEMM for the tiny embedding / AdaGN-scale linears (custom_layers.py:30,60-77):
+ * C (+)= op(A).op(B) (+bias)(Swish). ta: A stored [K][M]; tb 0: B stored [N][K], tb 1: B stored [K][N]. */
+int b2_small_gemm(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C, long long ldc,
+                  int M, int N, int K, const float* bias, int act, int accumulate, void* stream);
+
+/* ---- diffusion process (fp32 NCHW tensors) -------------------------------------------------------------- */
+
+/* Standard normals from Philox4x32-10 keyed on (seed, offset, global element index): sharded draws == unsharded. */
+int b2_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset, long long first_elem,
+                     void* stream);
+/* q(x_t|x_0) = sqrt(abar_t) img + sqrt(1-abar_t) eps (degraders.py:51-59 table gather when abar_table != NULL,
+ * degraders.py:70-82,96-104 cosine closed form otherwise); steps int64, 1 or N entries. */
+int b2_qsample(const float* img, const float* eps, float* out, const long long* steps, int steps_count,
+               const float* abar_table, int max_step, int N, long long per_image, void* stream);
+/* diffusion_sampling_algorithms.py:107-136: x0 = c_scale*(x - c_s*e); x' = c_an*x0 + c_dir*e + sigma*noise. */
+int b2_ddim_step(const float* x_t, const float* eps_hat, const float* noise, float* x_out, float* x0_out, long long n,
+                 float c_scale, float c_s, float c_an, float c_dir, float sigma, int last, void* stream);
+/* diffusion_sampling_algorithms.py:42-55: x' = scale1*(x - scale2*e) + sigma*z (z given | Philox | none). */
+int b2_ddpm_step(const float* x_t, const float* eps_hat, const float* z, float* out, long long n, float scale1,
+                 float scale2, float sigma, int use_philox, unsigned long long seed, unsigned long long offset,
+                 long long first_elem, void* stream);
+/* diffusion_sampling_algorithms.py:193-208: x' = x - (a_t x0 + b_t noise) + (a_n x0 + b_n noise). */
+int b2_cold_step(const float* x_t, const float* x0_hat, const float* noise, float* out, long long n, float a_t,
+                 float b_t, float a_n, float b_n, void* stream);
+/* loss = mean((pred-target)^2) (train_diffusion.py:350), grad (optional) = 2 (pred-target)/n * grad_scale. */
+int b2_mse_loss_grad(const float* pred, const float* target, float* grad, float* loss, long long n, float grad_scale,
+                     void* stream);
 
 #ifdef __cplusplus
 }

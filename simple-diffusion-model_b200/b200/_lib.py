@@ -1,0 +1,78 @@
+"""ctypes binding of libsdm_b200.so (C ABI declared in include/sdm_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a tensor is not on a CUDA device the
+call raises.  Build the library with `make` at the repo root (or `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsdm_b200.so")
+
+_P, _I, _L, _F, _U = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_ulonglong
+
+# name -> argument ctypes, in the order of include/sdm_b200.h
+SIGNATURES = {
+    "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
+    "b2_gemm_nt": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P, _F, _I, _P, _L, _I, _I, _P],
+    "b2_nchw_to_nhwc_pad": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b2_nhwc_to_nchw": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
+    "b2_space_to_depth2": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
+    "b2_pack_weight": [_I, _P, _P, _I, _I, _I, _I, _P],
+    "b2_adagn_apply": [_P, _L, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _P],
+    "b2_softmax_query_axis": [_P, _P, _I, _I, _I, _L, _I, _P],
+    "b2_transpose_batched": [_P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P],
+    "b2_sinusoid_embedding": [_P, _P, _I, _I, _P],
+    "b2_small_gemm": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _P, _I, _I, _P],
+    "b2_philox_normal": [_P, _L, _U, _U, _L, _P],
+    "b2_qsample": [_P, _P, _P, _P, _I, _P, _I, _I, _L, _P],
+    "b2_ddim_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
+    "b2_ddpm_step": [_P, _P, _P, _P, _L, _F, _F, _F, _I, _U, _U, _L, _P],
+    "b2_cold_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P],
+    "b2_mse_loss_grad": [_P, _P, _P, _P, _L, _F, _P],
+}
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the shared library once; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} not found: build the sm_100a extension first (`make`); there is no CPU fallback")
+        handle = ctypes.CDLL(LIB_PATH)
+        handle.b2_last_error.restype = ctypes.c_char_p
+        handle.b2_version.restype = _I
+        for name, args in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = args
+            fn.restype = _I
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        raise B200Error(f"{name}: {handle.b2_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise B200Error("sdm_b200 kernels need CUDA tensors: there is no CPU fallback")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,246 @@
+"""U-Net executor: walks the module tree of models/U_Net.py and issues the sm_100a kernels.
+
+Design (B200-first, not a translation of the reference's eager graph):
+  * activations live NHWC in the compute dtype (bf16, or fp32 for the TF32 parity mode); NCHW fp32 exists only at the
+    two network edges, and both edges are fused (input pad/transpose kernel; final conv epilogue writes NCHW fp32);
+  * every `torch.cat` of the reference (models/U_Net.py:168) is zero-copy: the down-sampler and the producer of `x`
+    write straight into the two channel halves of one pre-allocated buffer;
+  * Swish, bias, GroupNorm statistics and residual adds never run as separate passes: they are conv/GEMM epilogues or
+    the single AdaGN-apply pass;
+  * all 2 x (#res blocks) AdaGN scale vectors of a forward come from ONE small GEMM over a concatenated weight.
+Parameters stay fp32 in the reference's shapes (state_dict compatible); kernel-layout copies are cached here and
+refreshed when a parameter's version counter changes.
+"""
+import torch
+
+from . import ops
+from ._lib import B200Error, call, ptr, stream
+
+
+def _version_key(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class WeightCache:
+    def __init__(self):
+        self._packed = {}
+
+    def get(self, param, kind, code, cout, cin, cin_pad):
+        key = (id(param), kind, code, cin_pad)
+        ver = (param.data_ptr(), param._version)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.pack_weight(kind, param, cout, cin, cin_pad, code))
+            self._packed[key] = hit
+        return hit[1]
+
+    def clear(self):
+        self._packed.clear()
+
+
+class UNetEngine:
+    def __init__(self, net):
+        self.net = net
+        self.cache = WeightCache()
+        self._adagn_key = None
+        self._adagn_w = None
+        self._adagn_b = None
+        self._adagn_off = None
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _code(self):
+        return ops.TF32 if self.net.precision == "tf32" else ops.BF16
+
+    def _adagn_modules(self):
+        from models.custom_layers import AdaGN
+        return [m for m in self.net.modules() if isinstance(m, AdaGN)]
+
+    def _adagn_table(self):
+        """Concatenated y_scale weights of every AdaGN: one GEMM yields all scale vectors (custom_layers.py:38-42)."""
+        mods = self._adagn_modules()
+        params = [p for m in mods for p in (m.y_scale.weight, m.y_scale.bias)]
+        key = _version_key(params)
+        if key != self._adagn_key:
+            self._adagn_w = torch.cat([m.y_scale.weight.detach().float() for m in mods], dim=0).contiguous()
+            self._adagn_b = torch.cat([m.y_scale.bias.detach().float() for m in mods], dim=0).contiguous()
+            off, o = {}, 0
+            for m in mods:
+                off[id(m)] = o
+                o += m.y_scale.weight.shape[0]
+            self._adagn_off, self._adagn_total, self._adagn_key = off, o, key
+        return self._adagn_w, self._adagn_b, self._adagn_off, self._adagn_total
+
+    def _mlp(self, seq, x, b, dim_in, out, accumulate_last=False):
+        """Linear/Swish x3 + Linear on CUDA cores (tiny: custom_layers.py:59-77)."""
+        lins = [seq[0], seq[2], seq[4], seq[6]]
+        h = x
+        k = dim_in
+        for i, lin in enumerate(lins):
+            n = lin.weight.shape[0]
+            dst = out if i == 3 else torch.empty((b, n), dtype=torch.float32, device=x.device)
+            ops.small_gemm(h, lin.weight, b, n, k, k, lin.weight.shape[1], dst, n, bias=lin.bias, act=1 if i < 3 else 0,
+                           accumulate=(i == 3 and accumulate_last))
+            h, k = dst, n
+        return h
+
+    def embedding(self, t, cond):
+        ce = self.net.cond_emb
+        dim = ce.time_dim
+        t = t.to(torch.int64).contiguous()
+        bt = t.shape[0]
+        sin = torch.empty((bt, dim), dtype=torch.float32, device=t.device)
+        call("b2_sinusoid_embedding", ptr(t), ptr(sin), bt, dim, stream())
+        emb = torch.empty((bt, dim), dtype=torch.float32, device=t.device)
+        self._mlp(ce.time_layer, sin, bt, dim, emb)
+        if ce.cond_layer is not None:
+            if cond is None:
+                raise B200Error("this U_Net was built with cond_dim: `cond` is required")
+            c2 = cond.float().reshape(-1, cond.shape[-1]).contiguous()
+            bc = c2.shape[0]
+            if bc == bt:
+                # the last cond Linear accumulates straight into the time embedding (emb = time + cond, :96-97)
+                self._mlp(ce.cond_layer, c2, bc, c2.shape[1], emb, accumulate_last=True)
+            else:
+                cemb = torch.empty((bc, dim), dtype=torch.float32, device=t.device)
+                self._mlp(ce.cond_layer, c2, bc, c2.shape[1], cemb)
+                emb = emb + cemb              # batch-broadcast corner (t of shape [1] with batched labels)
+        return emb
+
+    # ------------------------------------------------------------------------------------------ layers
+    def conv_block(self, blk, x, ctx, out=None, residual=None, out_nchw=None, act_override=None):
+        """UNet_ConvBlock (custom_layers.py:240-245): conv + bias + Swish (+GN stats) then AdaGN apply (+residual)."""
+        conv = blk.conv_layer[0]
+        code = ops.code_of(x)
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        cin_pad = x.shape[3]
+        w = self.cache.get(conv.weight, 0, code, cout, cin, cin_pad)
+        act = 1 if blk.use_activation else 0
+        if act_override is not None:
+            act = act_override
+        has_gn = ctx["emb"] is not None and blk.adagn is not None
+        if not has_gn:
+            return ops.conv2d(0, x, w, conv.bias, cout, act=act, out=out, residual=residual, out_nchw_fp32=out_nchw)
+        n = x.shape[0]
+        groups = blk.adagn.group_norm.num_groups
+        stats = ctx["stats"][ctx["stats_i"]]
+        ctx["stats_i"] += 1
+        y = ops.conv2d(0, x, w, conv.bias, cout, act=act, gn_stats=stats, groups=groups)
+        off = ctx["adagn_off"][id(blk.adagn)]
+        s = ctx["s_all"][:, off:off + cout]
+        gn = blk.adagn.group_norm
+        return ops.adagn_apply(y, stats, gn.weight, gn.bias, s, ctx["s_bstride"], out=out, residual=residual,
+                               groups=groups, eps=gn.eps)
+
+    def residual_block(self, blk, x, ctx, out=None):
+        h = self.conv_block(blk.conv_block_1, x, ctx)
+        return self.conv_block(blk.conv_block_2, h, ctx, out=out, residual=x)
+
+    def attention(self, blk, x, out=None):
+        """AttentionBlock (custom_layers.py:127-163): softmax over the query axis, no norm, residual add."""
+        code = ops.code_of(x)
+        n, hh, ww, c = x.shape
+        ldx = x.stride(2)
+        p_len, heads, d = hh * ww, blk.heads, blk.d_k
+        dt, dev = x.dtype, x.device
+        kal = ops.K_ALIGN[code]
+        wp = self.cache.get(blk.projection.weight, 3, code, 3 * heads * d, c, c)
+        wo = self.cache.get(blk.output.weight, 3, code, c, heads * d, heads * d)
+        qkv = torch.empty((n * p_len, 3 * heads * d), dtype=dt, device=dev)
+        ops.gemm_nt(x, wp, n * p_len, 3 * heads * d, c, ldx, c, qkv, 3 * heads * d, bias=blk.projection.bias)
+        ldq = 3 * heads * d
+        # S[n][h][i][j] = scale * q_i . k_j
+        s_mat = torch.empty((n, heads, p_len, p_len), dtype=torch.float32, device=dev)
+        ops.gemm_nt(qkv, qkv[:, d:], p_len, p_len, d, ldq, ldq, s_mat, p_len, alpha=blk.scale, out_fp32=True,
+                    batch=(heads, n), a_strides=(3 * d, p_len * ldq), b_strides=(3 * d, p_len * ldq),
+                    c_strides=(p_len * p_len, heads * p_len * p_len))
+        ldp = ((p_len + 7) // 8) * 8
+        pm = torch.empty((n, heads, p_len, ldp), dtype=dt, device=dev)
+        call("b2_softmax_query_axis", ptr(s_mat), ptr(pm), n * heads, p_len, p_len, ldp, code, stream())
+        vt = torch.empty((n, heads, d, ldp), dtype=dt, device=dev)
+        call("b2_transpose_batched", ptr(qkv[:, 2 * d:]), ldq, 3 * d, p_len * ldq, ptr(vt), ldp, d * ldp, heads * d * ldp,
+             p_len, d, heads, n, code, stream())
+        o = torch.empty((n * p_len, heads * d), dtype=dt, device=dev)
+        ops.gemm_nt(pm, vt, p_len, d, p_len, ldp, ldp, o, heads * d, batch=(heads, n),
+                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(d * ldp, heads * d * ldp),
+                    c_strides=(d, p_len * heads * d))
+        if out is None:
+            out = torch.empty((n, hh, ww, c), dtype=dt, device=dev)
+        ops.gemm_nt(o, wo, n * p_len, c, heads * d, heads * d, heads * d, out, out.stride(2), bias=blk.output.bias,
+                    residual=x, ldr=ldx)
+        return out
+
+    def unet_block(self, blk, x, ctx, out):
+        """UNetBlock (custom_layers.py:336-341); `out` receives the sampler output (may be a channel slice)."""
+        from models.custom_layers import AttentionBlock, UpsampleBlock
+        for res, attn in zip(blk.res_layers, blk.attn_layers):
+            x = self.residual_block(res, x, ctx)
+            if isinstance(attn, AttentionBlock):
+                x = self.attention(attn, x)
+        code = ops.code_of(x)
+        conv = blk.out_layer.conv_layer[0]
+        if isinstance(blk.out_layer, UpsampleBlock):
+            cin, cout = conv.weight.shape[0], conv.weight.shape[1]
+            w = self.cache.get(conv.weight, 2, code, cout, cin, cin)
+            return ops.conv2d(2, x, w, conv.bias, cout, act=1, out=out)
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        w = self.cache.get(conv.weight, 0, code, cout, cin, cin)
+        planes = ops.space_to_depth2(x)
+        return ops.conv2d(1, planes, w, conv.bias, cout, act=1, out=out)
+
+    # ------------------------------------------------------------------------------------------ whole network
+    @torch.no_grad()
+    def forward(self, x, t=None, cond=None):
+        """models/U_Net.py:147-173.  x fp32 NCHW CUDA -> fp32 NCHW CUDA."""
+        net = self.net
+        if not x.is_cuda:
+            raise B200Error("U_Net.forward needs CUDA tensors: this build has no CPU path")
+        code = self._code()
+        n, cin, hgt, wid = x.shape
+        levels = len(net.down_layers)
+        if hgt % (1 << levels) or wid % (1 << levels):
+            raise B200Error(f"H and W must be divisible by 2**num_layers = {1 << levels}")
+        ctx = {"emb": None, "stats_i": 0}
+        if net.cond_emb is not None:
+            if t is None:
+                raise B200Error("timestep tensor `t` is required")
+            emb = self.embedding(t.to(x.device), cond.to(x.device) if cond is not None else None)
+            w_all, b_all, off, total = self._adagn_table()
+            be = emb.shape[0]
+            if be not in (1, n):
+                raise B200Error(f"embedding batch {be} does not broadcast over image batch {n}")
+            s_all = torch.empty((be, total), dtype=torch.float32, device=x.device)
+            ops.small_gemm(emb, w_all, be, total, emb.shape[1], emb.shape[1], w_all.shape[1], s_all, total, bias=b_all)
+            n_adagn = len(off)
+            max_groups = max(m.group_norm.num_groups for m in self._adagn_modules())
+            ctx.update(emb=emb, s_all=s_all, adagn_off=off, s_bstride=(total if be == n else 0),
+                       stats=torch.zeros((n_adagn, n, max_groups, 2), dtype=torch.float32, device=x.device))
+        cpad = ((cin + ops.K_ALIGN[code] - 1) // ops.K_ALIGN[code]) * ops.K_ALIGN[code]
+        h = ops.nchw_to_nhwc_pad(x, cpad, code)
+        h = self.conv_block(net.in_layer[0], h, ctx)
+        h = self.conv_block(net.in_layer[1], h, ctx)
+        cats = []
+        hh, ww = hgt, wid
+        for blk in net.down_layers:
+            cout = blk.out_layer.conv_layer[0].weight.shape[0]
+            hh, ww = hh // 2, ww // 2
+            cat = ops.new_act(n, hh, ww, 2 * cout, code, x.device)
+            h = self.unet_block(blk, h, ctx, out=cat[..., cout:])       # skip half of the future concat
+            cats.append(cat)
+        h = self.conv_block(net.middle_layer[0], h, ctx)
+        c_mid = cats[-1].shape[3] // 2
+        self.conv_block(net.middle_layer[1], h, ctx, out=cats[-1][..., :c_mid])
+        n_up = len(net.up_layers)
+        for i, blk in enumerate(net.up_layers):
+            cat = cats.pop()
+            cout = blk.out_layer.conv_layer[0].weight.shape[1]
+            if i + 1 < n_up:
+                dst = cats[-1][..., :cout]
+            else:
+                dst = None
+            h = self.unet_block(blk, cat, ctx, out=dst)
+        h = self.conv_block(net.out_layers[0], h, ctx)
+        last = net.out_layers[1]
+        c_out = last.conv_layer[0].weight.shape[0]
+        y = torch.empty((n, c_out, hgt, wid), dtype=torch.float32, device=x.device)
+        self.conv_block(last, h, ctx, out_nchw=y, act_override=(2 if net.image_recon else 0))
+        return y

@@ -1,0 +1,113 @@
+"""Thin Python wrappers over the C ABI.  Activations are torch CUDA tensors laid out NHWC ([N, H, W, C] with
+unit channel stride); a tensor may be a channel slice of a wider buffer -- the per-pixel stride is passed down as `ld`.
+dtype codes: 0 = bf16 storage / kind::f16 MMA, 1 = fp32 storage / kind::tf32 MMA."""
+import torch
+
+from ._lib import B200Error, call, ptr, stream
+
+BF16, TF32 = 0, 1
+TORCH_DTYPE = {BF16: torch.bfloat16, TF32: torch.float32}
+K_ALIGN = {BF16: 64, TF32: 32}          # channels per 128-byte K block
+
+
+def code_of(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return TF32
+    raise B200Error(f"unsupported activation dtype {t.dtype}")
+
+
+def _nhwc(t):
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise B200Error("expected an NHWC tensor with unit channel stride")
+    n, h, w, c = t.shape
+    ld = t.stride(2)
+    if (h > 1 and t.stride(1) != w * ld) or (n > 1 and t.stride(0) != h * w * ld):
+        raise B200Error("NHWC tensor must be dense in N, H, W (only the channel dim may be a slice)")
+    return n, h, w, c, ld
+
+
+def new_act(n, h, w, c, code, device):
+    return torch.empty((n, h, w, c), dtype=TORCH_DTYPE[code], device=device)
+
+
+def conv2d(mode, x, wpacked, bias, cout, act=0, out=None, residual=None, gn_stats=None, groups=32, out_nchw_fp32=None):
+    """mode 0: 3x3/s1; 1: 3x3/s2 (x = parity planes [4*N, H/2, W/2, C]); 2: transposed 4x4/s2."""
+    code = code_of(x)
+    n, h, w, cin, ldx = _nhwc(x)
+    if mode == 1:
+        n //= 4
+    oh, ow = (2 * h, 2 * w) if mode == 2 else (h, w)
+    if out_nchw_fp32 is not None:
+        y, ldy, out_mode = out_nchw_fp32, 0, 1
+    else:
+        if out is None:
+            out = new_act(n, oh, ow, cout, code, x.device)
+        y, out_mode = out, 0
+        ldy = _nhwc(out)[4]
+    ldr = _nhwc(residual)[4] if residual is not None else 0
+    call("b2_conv2d_nhwc", mode, ptr(x), n, h, w, cin, ldx, ptr(wpacked), ptr(bias), cout, ptr(y), ldy, act,
+         ptr(residual), ldr, ptr(gn_stats), groups if gn_stats is not None else 0, out_mode, code, stream())
+    return y
+
+
+def gemm_nt(a, b, m, ncols, k, lda, ldb, out, ldc, bias=None, alpha=1.0, act=0, residual=None, ldr=0, out_fp32=False,
+            batch=(1, 1), a_strides=(0, 0), b_strides=(0, 0), c_strides=(0, 0), code=None):
+    code = code_of(a) if code is None else code
+    call("b2_gemm_nt", ptr(a), lda, a_strides[0], a_strides[1], ptr(b), ldb, b_strides[0], b_strides[1], ptr(out), ldc,
+         c_strides[0], c_strides[1], m, ncols, k, batch[0], batch[1], ptr(bias), float(alpha), act, ptr(residual), ldr,
+         1 if out_fp32 else 0, code, stream())
+    return out
+
+
+def nchw_to_nhwc_pad(x, cpad, code):
+    n, c, h, w = x.shape
+    x = x.contiguous().float()
+    y = new_act(n, h, w, cpad, code, x.device)
+    call("b2_nchw_to_nhwc_pad", ptr(x), ptr(y), n, c, h, w, cpad, code, stream())
+    return y
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c, ld = _nhwc(x)
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    call("b2_nhwc_to_nchw", ptr(x), ld, ptr(y), n, c, h, w, code_of(x), stream())
+    return y
+
+
+def space_to_depth2(x):
+    n, h, w, c, ld = _nhwc(x)
+    planes = torch.empty((4 * n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+    call("b2_space_to_depth2", ptr(x), ld, ptr(planes), n, h, w, c, code_of(x), stream())
+    return planes
+
+
+def pack_weight(kind, w, cout, cin, cin_pad, code):
+    if kind == 0:
+        shape = (cout, 9 * cin_pad)
+    elif kind == 1:
+        shape = (cin, 9 * cout)
+    elif kind == 2:
+        shape = (4 * cout, 4 * cin)
+    else:
+        shape = (cout, cin_pad)
+    out = torch.empty(shape, dtype=TORCH_DTYPE[code], device=w.device)
+    call("b2_pack_weight", kind, ptr(w.detach().contiguous()), ptr(out), cout, cin, cin_pad, code, stream())
+    return out
+
+
+def adagn_apply(y, stats, gamma, beta, s, s_bstride, out=None, residual=None, groups=32, eps=1e-5):
+    n, h, w, c, ldy = _nhwc(y)
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=y.dtype, device=y.device)
+    ldo = _nhwc(out)[4]
+    ldr = _nhwc(residual)[4] if residual is not None else 0
+    call("b2_adagn_apply", ptr(y), ldy, ptr(stats), ptr(gamma), ptr(beta), ptr(s), s_bstride, ptr(residual), ldr, ptr(out),
+         ldo, n, h * w, c, groups, float(eps), code_of(y), stream())
+    return out
+
+
+def small_gemm(a, b, m, n, k, lda, ldb, out, ldc, ta=0, tb=0, bias=None, act=0, accumulate=False):
+    call("b2_small_gemm", ptr(a), lda, ta, ptr(b), ldb, tb, ptr(out), ldc, m, n, k, ptr(bias), act, 1 if accumulate else 0, stream())
+    return out

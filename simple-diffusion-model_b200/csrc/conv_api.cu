@@ -34,12 +34,12 @@ static void pick_box(int W, int H, int N, int* wb, int* hb, int* nb) {
 
 extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
                               const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
-                              const void* residual, long long ldr, float* gn_stats, int gn_groups, int dtype,
-                              void* stream) {
+                              const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
+                              int dtype, void* stream) {
     const int eb = dtype == 0 ? 2 : 4;
     const int bk = 128 / eb;
     if (Cin % bk != 0) return set_error("b2_conv2d_nhwc: Cin=%d must be a multiple of %d", Cin, bk);
-    if (Cout % 8 != 0) return set_error("b2_conv2d_nhwc: Cout=%d must be a multiple of 8", Cout);
+    if (out_mode != 0 && (mode != 0 || residual)) return set_error("b2_conv2d_nhwc: NCHW fp32 output only for the plain 3x3 conv");
     if (mode < 0 || mode > 2) return set_error("b2_conv2d_nhwc: bad mode %d", mode);
     IgemmParams p;
     memset(&p, 0, sizeof(p));
@@ -94,6 +94,20 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         p.rN = (long long)4 * H * W * ldr; p.rH = (long long)2 * (2 * W) * ldr; p.rW = 2 * ldr;
         if (residual) return set_error("b2_conv2d_nhwc: residual not supported for transposed conv");
     }
+    p.oC = 1;
+    if (out_mode == 1) {      // final layer: fp32 NCHW straight from the epilogue (ldy ignored)
+        p.oN = (long long)Cout * H * W; p.oH = W; p.oW = 1; p.oC = (long long)H * W;
+        p.out_fp32 = 1;
+    }
+    {
+        const int ov = (dtype == 1 || p.out_fp32) ? 4 : 8;    // elements per 16 bytes
+        const int oeb = 16 / ov;
+        bool ok = (p.oC == 1) && (ldy % ov == 0) && ((uintptr_t)y % 16 == 0);
+        for (int g = 0; g < p.groups; ++g) ok = ok && (p.goff[g] % ov == 0);
+        if (residual) ok = ok && (ldr % ov == 0) && ((uintptr_t)residual % 16 == 0);
+        (void)oeb;
+        p.vec_ok = ok ? 1 : 0;
+    }
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     const int bn = pick_block_n(Cout, m_tiles, p.groups);
     p.n_tiles = (Cout + bn - 1) / bn;
@@ -124,16 +138,22 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
                           const void* residual, long long ldr, int out_fp32, int dtype, void* stream) {
     const int eb = dtype == 0 ? 2 : 4;
     const int bk = 128 / eb;
-    if (K % bk != 0) return set_error("b2_gemm_nt: K=%d must be a multiple of %d", K, bk);
+    if ((lda * eb) % 16 || (ldb * eb) % 16) return set_error("b2_gemm_nt: lda/ldb rows must be 16-byte multiples");
     if (residual && (batch1 != 1 || batch2 != 1)) return set_error("b2_gemm_nt: residual only for unbatched GEMM");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.W = M; p.H = batch1; p.N = batch2;
     p.wb = 128; p.hb = 1; p.nb = 1;
     p.tiles_w = (M + 127) / 128; p.tiles_h = batch1; p.tiles_n = batch2;
-    p.groups = 1; p.taps = 1; p.kb_per_tap = K / bk;
+    p.groups = 1; p.taps = 1; p.kb_per_tap = (K + bk - 1) / bk;   // K tail is zero-filled by TMA
     p.Cout = Ncols;
-    p.out = C; p.oN = c_s2; p.oH = c_s1; p.oW = ldc;
+    p.out = C; p.oN = c_s2; p.oH = c_s1; p.oW = ldc; p.oC = 1;
+    {
+        const int ov = (dtype == 1 || out_fp32) ? 4 : 8;
+        bool ok = (ldc % ov == 0) && (c_s1 % ov == 0) && (c_s2 % ov == 0) && ((uintptr_t)C % 16 == 0);
+        if (residual) ok = ok && (ldr % ov == 0) && ((uintptr_t)residual % 16 == 0);
+        p.vec_ok = ok ? 1 : 0;
+    }
     p.residual = residual; p.rN = 0; p.rH = 0; p.rW = ldr;
     p.bias = bias; p.alpha = alpha; p.act = act; p.out_fp32 = out_fp32;
     const bool batched = (batch1 > 1 || batch2 > 1);

@@ -1,0 +1,378 @@
+// Memory-bound kernels of the forward path: layout edges, weight packing, GroupNorm x AdaGN apply (+residual),
+// query-axis softmax, batched transpose, sinusoidal embedding, small fp32 linear.  All are vectorised
+// (16-byte accesses where the layout allows) and sized in multiples of the SM count.
+#include "host_util.h"
+#include "ptx.cuh"
+#include "sdm_b200.h"
+
+using namespace b2;
+typedef __nv_bfloat16 bf16;
+
+#define LAUNCH_CHECK(name)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = cudaGetLastError();                                                      \
+        if (e_ != cudaSuccess) return set_error(name ": %s", cudaGetErrorString(e_));             \
+        return 0;                                                                                 \
+    } while (0)
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+
+// 16-byte vector of T <-> floats
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+template <typename T>
+__device__ __forceinline__ void load16(const T* p, float (&f)[Vec16<T>::N]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    if constexpr (sizeof(T) == 4) {
+        f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+    } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store16(T* p, const float (&f)[Vec16<T>::N]) {
+    uint4 u;
+    if constexpr (sizeof(T) == 4) {
+        u.x = __float_as_uint(f[0]); u.y = __float_as_uint(f[1]); u.z = __float_as_uint(f[2]); u.w = __float_as_uint(f[3]);
+    } else {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)device_sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------------ layout edges
+// x fp32 NCHW [N][C][H][W]  ->  y T NHWC [N][H][W][Cpad] (channels >= C zero-filled).
+template <typename T>
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int HW, int Cpad) {
+    const long long total = (long long)N * HW * (Cpad / 8);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % (Cpad / 8));
+        const long long pix = i / (Cpad / 8);
+        const int n = (int)(pix / HW), p = (int)(pix % HW);
+        T* o = y + pix * Cpad + cv * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            o[j] = from_f<T>(c < C ? __ldg(x + ((long long)n * C + c) * HW + p) : 0.f);
+        }
+    }
+}
+extern "C" int b2_nchw_to_nhwc_pad(const float* x, void* y, int N, int C, int H, int W, int Cpad, int dtype, void* stream) {
+    if (Cpad % 8) return set_error("b2_nchw_to_nhwc_pad: Cpad must be a multiple of 8");
+    const long long total = (long long)N * H * W * (Cpad / 8);
+    const int g = grid_for(total, 256);
+    if (dtype == 0) nchw_to_nhwc_pad_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, N, C, H * W, Cpad);
+    else nchw_to_nhwc_pad_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, N, C, H * W, Cpad);
+    LAUNCH_CHECK("b2_nchw_to_nhwc_pad");
+}
+
+// x T NHWC (ld) [N][H][W][C] -> y fp32 NCHW.
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ y, int N, int C, int HW) {
+    const long long total = (long long)N * C * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        const int c = (int)((i / HW) % C);
+        const int n = (int)(i / ((long long)HW * C));
+        y[i] = to_f<T>(x[((long long)n * HW + p) * ldx + c]);
+    }
+}
+extern "C" int b2_nhwc_to_nchw(const void* x, long long ldx, float* y, int N, int C, int H, int W, int dtype, void* stream) {
+    const int g = grid_for((long long)N * C * H * W, 256);
+    if (dtype == 0) nhwc_to_nchw_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, y, N, C, H * W);
+    else nhwc_to_nchw_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, y, N, C, H * W);
+    LAUNCH_CHECK("b2_nhwc_to_nchw");
+}
+
+// Parity planes for the stride-2 conv: planes[pr][pc][n][i][j][:] = x[n][2i+pr][2j+pc][:].
+template <typename T>
+__global__ void space_to_depth2_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ planes, int N, int H, int W, int C) {
+    constexpr int V = Vec16<T>::N;
+    const int cv = C / V, OH = H / 2, OW = W / 2;
+    const long long total = (long long)N * H * W * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv);
+        long long pix = i / cv;
+        const int w = (int)(pix % W); pix /= W;
+        const int h = (int)(pix % H);
+        const int n = (int)(pix / H);
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * ldx + c * V);
+        const int pl = (h & 1) * 2 + (w & 1);
+        T* o = planes + ((((long long)pl * N + n) * OH + (h >> 1)) * OW + (w >> 1)) * C + c * V;
+        *reinterpret_cast<uint4*>(o) = v;
+    }
+}
+extern "C" int b2_space_to_depth2(const void* x, long long ldx, void* planes, int N, int H, int W, int C, int dtype, void* stream) {
+    const int V = dtype == 0 ? 8 : 4;
+    if (C % V || ldx % V || (H & 1) || (W & 1)) return set_error("b2_space_to_depth2: C/ld must be vector aligned, H/W even");
+    const int g = grid_for((long long)N * H * W * (C / V), 256);
+    if (dtype == 0) space_to_depth2_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)planes, N, H, W, C);
+    else space_to_depth2_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, (float*)planes, N, H, W, C);
+    LAUNCH_CHECK("b2_space_to_depth2");
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+template <typename T> __device__ __forceinline__ T pack_val(float v);
+template <> __device__ __forceinline__ bf16 pack_val<bf16>(float v) { return __float2bfloat16(v); }
+template <> __device__ __forceinline__ float pack_val<float>(float v) { return round_tf32(v); }
+
+// kind 0: Conv2d weight [Cout][Cin][3][3] -> [Cout][9][Cin_pad]                     (forward layout)
+// kind 1: Conv2d weight [Cout][Cin][3][3] -> [Cin][9 flipped][Cout]                 (data-gradient layout, stride 1)
+// kind 2: ConvTranspose2d weight [Cin][Cout][4][4] -> [4 parities][Cout][4 taps][Cin]   (forward layout)
+// kind 3: plain cast [rows][cols] -> [rows][cols_pad]                                (Linear weights)
+template <typename T>
+__global__ void pack_weight_kernel(int kind, const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int Cin_pad) {
+    long long total;
+    if (kind == 0) total = (long long)Cout * 9 * Cin_pad;
+    else if (kind == 1) total = (long long)Cin * 9 * Cout;
+    else if (kind == 2) total = (long long)16 * Cout * Cin;
+    else total = (long long)Cout * Cin_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float v;
+        if (kind == 0) {
+            const int ci = (int)(i % Cin_pad); const int tap = (int)((i / Cin_pad) % 9); const int co = (int)(i / (9LL * Cin_pad));
+            v = ci < Cin ? __ldg(w + ((long long)co * Cin + ci) * 9 + tap) : 0.f;
+        } else if (kind == 1) {
+            const int co = (int)(i % Cout); const int tap = (int)((i / Cout) % 9); const int ci = (int)(i / (9LL * Cout));
+            v = __ldg(w + ((long long)co * Cin + ci) * 9 + (8 - tap));
+        } else if (kind == 2) {
+            const int ci = (int)(i % Cin); long long r = i / Cin;
+            const int t = (int)(r % 4); r /= 4;
+            const int co = (int)(r % Cout); const int g = (int)(r / Cout);
+            const int a = g >> 1, b = g & 1, ti = t >> 1, tj = t & 1;
+            const int kh = a == 0 ? (ti == 0 ? 1 : 3) : (ti == 0 ? 2 : 0);
+            const int kw = b == 0 ? (tj == 0 ? 1 : 3) : (tj == 0 ? 2 : 0);
+            v = __ldg(w + (((long long)ci * Cout + co) * 4 + kh) * 4 + kw);
+        } else {
+            const int c = (int)(i % Cin_pad); const int r = (int)(i / Cin_pad);
+            v = c < Cin ? __ldg(w + (long long)r * Cin + c) : 0.f;
+        }
+        out[i] = pack_val<T>(v);
+    }
+}
+extern "C" int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int Cin_pad, int dtype, void* stream) {
+    if (kind < 0 || kind > 3) return set_error("b2_pack_weight: bad kind");
+    const long long total = kind == 0 ? (long long)Cout * 9 * Cin_pad : kind == 1 ? (long long)Cin * 9 * Cout
+                          : kind == 2 ? (long long)16 * Cout * Cin : (long long)Cout * Cin_pad;
+    const int g = grid_for(total, 256);
+    if (dtype == 0) pack_weight_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (bf16*)out, Cout, Cin, Cin_pad);
+    else pack_weight_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (float*)out, Cout, Cin, Cin_pad);
+    LAUNCH_CHECK("b2_pack_weight");
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm x AdaGN apply
+// out = s * (gamma * (y - mean) * rstd + beta) + s  (+ residual)        [custom_layers.py:35-45, :282-287]
+// stats = per-(image, group) (sum, sum of squares) produced by the conv epilogue.  One CTA streams a slab of
+// pixels of one image; the per-channel affine (a, b) is folded once into shared memory.
+template <typename T>
+__global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const float* __restrict__ stats,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ s, long long s_bstride, const T* __restrict__ res, long long ldr,
+                                   T* __restrict__ out, long long ldo, int HW, int C, int groups, float eps, int slabs) {
+    extern __shared__ float sm[];
+    float* fa = sm;
+    float* fb = sm + C;
+    const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int cpg = C / groups;
+    const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float s1 = stats[((long long)n * groups + g) * 2], s2 = stats[((long long)n * groups + g) * 2 + 1];
+        const float mean = s1 * inv_cnt;
+        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float sc = s[(long long)n * s_bstride + c];
+        const float ga = gamma[c] * rstd;
+        fa[c] = sc * ga;
+        fb[c] = sc * (beta[c] - ga * mean) + sc;
+    }
+    __syncthreads();
+    constexpr int V = Vec16<T>::N;
+    const int cv = C / V;
+    const int p_per = (HW + slabs - 1) / slabs;
+    const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
+    const long long base = (long long)n * HW;
+    for (int i = threadIdx.x + p0 * cv; i < p1 * cv; i += blockDim.x) {
+        const int p = i / cv, c = (i % cv) * V;
+        float v[V];
+        load16<T>(y + (base + p) * ldy + c, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], fa[c + j], fb[c + j]);
+        if (res) {
+            float r[V];
+            load16<T>(res + (base + p) * ldr + c, r);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] += r[j];
+        }
+        store16<T>(out + (base + p) * ldo + c, v);
+    }
+}
+extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, const float* gamma, const float* beta,
+                              const float* s, long long s_bstride, const void* residual, long long ldr, void* out,
+                              long long ldo, int N, int HW, int C, int groups, float eps, int dtype, void* stream) {
+    const int V = dtype == 0 ? 8 : 4;
+    if (C % V || ldy % V || ldo % V || (residual && ldr % V)) return set_error("b2_adagn_apply: channel counts / strides must be 16-byte aligned");
+    if (C % groups) return set_error("b2_adagn_apply: C %% groups != 0");
+    const int sms = device_sm_count();
+    int slabs = (4 * sms + N - 1) / N;
+    const int max_slabs = (HW * (C / V) + 1023) / 1024;
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+    if (dtype == 0)
+        adagn_apply_kernel<bf16><<<N * slabs, 256, smem, (cudaStream_t)stream>>>((const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
+                                                                                   (const bf16*)residual, ldr, (bf16*)out, ldo, HW, C, groups, eps, slabs);
+    else
+        adagn_apply_kernel<float><<<N * slabs, 256, smem, (cudaStream_t)stream>>>((const float*)y, ldy, stats, gamma, beta, s, s_bstride,
+                                                                                    (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs);
+    LAUNCH_CHECK("b2_adagn_apply");
+}
+
+// ------------------------------------------------------------------------------------------------ attention helpers
+// Query-axis softmax (custom_layers.py:147): S[b][i][j] fp32 (already scaled) -> P[b][i][j] = exp(S - max_i) / sum_i.
+// One thread owns one key column j (coalesced across the warp), walking the query axis twice.
+template <typename T>
+__global__ void softmax_query_axis_kernel(const float* __restrict__ S, T* __restrict__ P, int B, int Pq, int Pk, long long ldp) {
+    const long long total = (long long)B * Pk;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % Pk);
+        const long long b = idx / Pk;
+        const float* col = S + b * Pq * Pk + j;
+        float m = -INFINITY, z = 0.f;
+        for (int i = 0; i < Pq; ++i) {
+            const float v = col[(long long)i * Pk];
+            const float mn = fmaxf(m, v);
+            z = z * __expf(m - mn) + __expf(v - mn);
+            m = mn;
+        }
+        const float inv = 1.0f / z;
+        T* o = P + b * Pq * ldp + j;
+        for (int i = 0; i < Pq; ++i) o[(long long)i * ldp] = from_f<T>(__expf(col[(long long)i * Pk] - m) * inv);
+    }
+}
+extern "C" int b2_softmax_query_axis(const float* S, void* P, int B, int Pq, int Pk, long long ldp, int dtype, void* stream) {
+    const int g = grid_for((long long)B * Pk, 128);
+    if (dtype == 0) softmax_query_axis_kernel<bf16><<<g, 128, 0, (cudaStream_t)stream>>>(S, (bf16*)P, B, Pq, Pk, ldp);
+    else softmax_query_axis_kernel<float><<<g, 128, 0, (cudaStream_t)stream>>>(S, (float*)P, B, Pq, Pk, ldp);
+    LAUNCH_CHECK("b2_softmax_query_axis");
+}
+
+// out[b1][b2][c][r] = in[b1][b2][r][c]   (32x32 smem tiles); in strides in elements.
+template <typename T>
+__global__ void transpose_batched_kernel(const T* __restrict__ in, long long ld_in, long long in_s1, long long in_s2,
+                                         T* __restrict__ out, long long ld_out, long long out_s1, long long out_s2,
+                                         int R, int Ccols, int B1) {
+    __shared__ T tile[32][33];
+    const int b = blockIdx.z, b1 = b % B1, b2 = b / B1;
+    const T* src = in + b1 * in_s1 + b2 * in_s2;
+    T* dst = out + b1 * out_s1 + b2 * out_s2;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < Ccols) tile[i][threadIdx.x] = src[(long long)r * ld_in + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < Ccols) dst[(long long)c * ld_out + r] = tile[threadIdx.x][i];
+    }
+}
+extern "C" int b2_transpose_batched(const void* in, long long ld_in, long long in_s1, long long in_s2, void* out, long long ld_out,
+                                    long long out_s1, long long out_s2, int R, int Ccols, int B1, int B2, int dtype, void* stream) {
+    dim3 grid((Ccols + 31) / 32, (R + 31) / 32, B1 * B2), block(32, 8);
+    if (grid.y > 65535 || grid.z > 65535) return set_error("b2_transpose_batched: grid too large");
+    if (dtype == 0) transpose_batched_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)in, ld_in, in_s1, in_s2, (bf16*)out, ld_out, out_s1, out_s2, R, Ccols, B1);
+    else transpose_batched_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, in_s1, in_s2, (float*)out, ld_out, out_s1, out_s2, R, Ccols, B1);
+    LAUNCH_CHECK("b2_transpose_batched");
+}
+
+// ------------------------------------------------------------------------------------------------ embedding + small linear
+// out[b][:] = [sin(t_b f_k), cos(t_b f_k)], f_k = exp(-k ln(1e4)/(half-1))        (custom_layers.py:84-90)
+__global__ void sinusoid_kernel(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, k = i % half;
+    const float f = expf((float)k * -(logf(10000.0f) / (float)(half - 1)));
+    const float a = (float)t[b] * f;
+    out[(long long)b * dim + k] = sinf(a);
+    out[(long long)b * dim + half + k] = cosf(a);
+}
+extern "C" int b2_sinusoid_embedding(const long long* t, float* out, int B, int dim, void* stream) {
+    if (dim < 4 || dim % 2) return set_error("b2_sinusoid_embedding: time_dim must be even and >= 4");
+    const int n = B * (dim / 2);
+    sinusoid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, out, B, dim);
+    LAUNCH_CHECK("b2_sinusoid_embedding");
+}
+
+// Small fp32 GEMM on CUDA cores for the embedding MLPs and the AdaGN scale vectors (M = batch, tiny):
+//   C[M][N] (+)= op(A) . op(B) (+ bias[N]) (Swish).  ta: A is [K][M]; tb == 0: B is [N][K] (Linear weight), tb == 1: B is [K][N].
+__global__ void small_gemm_kernel(const float* __restrict__ A, long long lda, int ta, const float* __restrict__ Bm, long long ldb, int tb,
+                                  float* __restrict__ C, long long ldc, int M, int N, int K, const float* __restrict__ bias, int act,
+                                  int accumulate) {
+    __shared__ float As[32][33], Bs[32][33];
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int i = ty; i < 32; i += 8) {
+            // As[i][tx] = A[m0+i][k0+tx]
+            const int m = m0 + i, k = k0 + tx;
+            float v = 0.f;
+            if (m < M && k < K) v = ta ? A[(long long)k * lda + m] : A[(long long)m * lda + k];
+            As[i][tx] = v;
+            const int n = n0 + i;
+            float w = 0.f;
+            if (n < N && k < K) w = tb ? Bm[(long long)k * ldb + n] : Bm[(long long)n * ldb + k];
+            Bs[i][tx] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+            const float b = Bs[tx][kk];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[ty + 8 * r][kk], b, acc[r]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx;
+    if (n < N) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int m = m0 + ty + 8 * r;
+            if (m < M) {
+                float v = acc[r] + (bias ? bias[n] : 0.f);
+                if (act == 1) v = swishf(v);
+                float* o = C + (long long)m * ldc + n;
+                *o = accumulate ? (*o + v) : v;
+            }
+        }
+    }
+}
+extern "C" int b2_small_gemm(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C, long long ldc,
+                             int M, int N, int K, const float* bias, int act, int accumulate, void* stream) {
+    dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
+    small_gemm_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, bias, act, accumulate);
+    LAUNCH_CHECK("b2_small_gemm");
+}

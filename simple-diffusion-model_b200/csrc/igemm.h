@@ -22,14 +22,15 @@ struct IgemmParams {
     int Cout;                    // valid output columns
     // output addressing (elements): out + n*oN + h*oH + w*oW + goff[group] + column
     void* out;
-    long long oN, oH, oW;
+    long long oN, oH, oW, oC;    // oC: column (channel) stride, 1 for NHWC, H*W for an NCHW result
+    int vec_ok;                  // 16-byte vector stores/loads allowed (oC == 1 and everything 16-byte aligned)
     long long goff[kMaxGroups];
     int out_fp32;                // bf16 kernels only: write fp32 instead of bf16
     const void* residual;        // optional, same dtype as out; rN/rH/rW addressing, no group offset
     long long rN, rH, rW;
     const float* bias;           // optional [Cout]
     float alpha;                 // acc *= alpha before bias
-    int act;                     // 0 none, 1 swish
+    int act;                     // 0 none, 1 swish, 2 tanh
     float* gn_stats;             // optional [N][Cout/cpg][2] (sum, sum of squares), accumulated atomically
     int cpg;                     // channels per GroupNorm group
 };

@@ -182,6 +182,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
                 tmem_ld_wait();
                 const int ncols = min(32, p.Cout - col0);
+                const bool vec = p.vec_ok && ncols == 32;
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
@@ -192,6 +193,9 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (p.act == 1) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = swishf(v[i]);
+                } else if (p.act == 2) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
                 }
                 if (p.gn_stats && ncols == 32) {
                     float* srow = p.gn_stats + static_cast<long long>(uniform ? n_lane0 : (valid ? n : 0)) * G * 2;
@@ -204,10 +208,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (valid) {
                     const bool f32out = kTF32 || p.out_fp32;
                     if (f32out) {
-                        float* o = reinterpret_cast<float*>(p.out) + o_off + col0;
+                        float* o = reinterpret_cast<float*>(p.out) + o_off + col0 * p.oC;
                         if (p.residual) {
                             const float* rs = reinterpret_cast<const float*>(p.residual) + r_off + col0;
-                            if (ncols == 32) {
+                            if (vec) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     float4 x = __ldg(reinterpret_cast<const float4*>(rs) + i);
@@ -218,19 +222,19 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += rs[i];
                             }
                         }
-                        if (ncols == 32) {
+                        if (vec) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = v[i];
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i * p.oC] = v[i];
                         }
                     } else {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_off + col0;
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_off + col0 * p.oC;
                         if (p.residual) {
                             const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0;
-                            if (ncols == 32) {
+                            if (vec) {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     uint4 x = __ldg(reinterpret_cast<const uint4*>(rs) + i);
@@ -246,7 +250,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __bfloat162float(rs[i]);
                             }
                         }
-                        if (ncols == 32) {
+                        if (vec) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 uint4 x;
@@ -257,7 +261,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = __float2bfloat16(v[i]);
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i * p.oC] = __float2bfloat16(v[i]);
                         }
                     }
                 }

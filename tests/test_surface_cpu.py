@@ -1,0 +1,72 @@
+"""CPU-side checks of the drop-in surface: parameter tree identical to the reference's (via the golden fixtures),
+constructor validation, and that the C-ABI library exports every symbol include/sdm_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_cond", "gpu_small", "gpu_cond", "default64"])
+def test_state_dict_matches_reference(name):
+    from models.U_Net import U_Net
+    fx = load_golden(f"unet_{name}.pt")
+    net = U_Net(**fx["kwargs"])
+    own = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert own == {k: tuple(v) for k, v in fx["shapes"].items()}
+    assert list(net.state_dict().keys()) == list(fx["shapes"].keys())      # same registration order too
+
+
+def test_ctor_validation_matches_reference():
+    from models.U_Net import U_Net
+    with pytest.raises(TypeError):
+        U_Net(num_layers=2.0)
+    with pytest.raises(TypeError):
+        U_Net(attn_layers=(1, 2))
+    with pytest.raises(ValueError):
+        U_Net(num_layers=0)
+    with pytest.raises(ValueError):
+        U_Net(num_layers=2, attn_layers=[2])
+    with pytest.raises(ValueError):
+        U_Net(num_layers=2, attn_layers=[0.5])
+
+
+def test_no_cpu_fallback():
+    from b200 import B200Error
+    from models.U_Net import U_Net
+    net = U_Net(num_resnet_blocks=1, num_layers=1, attn_layers=[], min_channel=128, max_channel=128)
+    with pytest.raises(B200Error):
+        with torch.no_grad():
+            net(torch.zeros(1, 3, 8, 8), torch.tensor([5]))
+
+
+def test_custom_load_state_dict_skips_mismatches(capsys):
+    from models.U_Net import U_Net
+    net = U_Net(num_resnet_blocks=1, num_layers=1, attn_layers=[], min_channel=128, max_channel=128)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    key = "in_layer.0.conv_layer.0.bias"
+    sd[key] = torch.full_like(sd[key], 0.25)
+    sd["bogus.weight"] = torch.zeros(3)
+    sd["in_layer.1.conv_layer.0.bias"] = torch.zeros(7)
+    net.custom_load_state_dict(sd)
+    out = capsys.readouterr().out
+    assert "No Layer found: bogus.weight" in out and "Skipped: in_layer.1.conv_layer.0.bias" in out
+    assert torch.all(net.state_dict()[key] == 0.25)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from b200._lib import LIB_PATH, SIGNATURES
+    header = open(os.path.join(ROOT, "include", "sdm_b200.h")).read()
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert os.path.exists(LIB_PATH), "build the library first: make"
+    handle = ctypes.CDLL(LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(handle, sym), f"{sym} declared in include/sdm_b200.h but not exported"
+    # the ctypes table covers exactly the compute entry points
+    assert set(SIGNATURES) == declared - {"b2_last_error", "b2_version"}
+    handle.b2_version.restype = ctypes.c_int
+    assert handle.b2_version() >= 100

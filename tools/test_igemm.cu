@@ -91,7 +91,7 @@ static void test_conv(int mode, int dtype, int N, int H, int W, int Cin, int Cou
     }
     const int kH = mode == 1 ? OH : H, kW = mode == 1 ? OW : W;
     B2(b2_conv2d_nhwc(mode, xin, N, kH, kW, Cin, Cin, wp.d, d_bias, Cout, y.d, Cout, act, use_res ? res.d : nullptr, Cout,
-                      d_stats, use_gn ? G : 0, dtype, nullptr));
+                      d_stats, use_gn ? G : 0, 0, dtype, nullptr));
     CK(cudaDeviceSynchronize());
     y.download();
     // reference
@@ -174,10 +174,10 @@ static void perf_conv(int dtype, int N, int H, int W, int C, int iters) {
     CK(cudaMalloc(&w, (size_t)C * 9 * C * eb)); CK(cudaMalloc(&bias, C * 4));
     CK(cudaMemset(x, 0, (size_t)N * H * W * C * eb)); CK(cudaMemset(w, 0, (size_t)C * 9 * C * eb)); CK(cudaMemset(bias, 0, C * 4));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) B2(b2_conv2d_nhwc(0, x, N, H, W, C, C, w, bias, C, y, C, 1, nullptr, 0, nullptr, 0, dtype, nullptr));
+    for (int i = 0; i < 3; ++i) B2(b2_conv2d_nhwc(0, x, N, H, W, C, C, w, bias, C, y, C, 1, nullptr, 0, nullptr, 0, 0, dtype, nullptr));
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) B2(b2_conv2d_nhwc(0, x, N, H, W, C, C, w, bias, C, y, C, 1, nullptr, 0, nullptr, 0, dtype, nullptr));
+    for (int i = 0; i < iters; ++i) B2(b2_conv2d_nhwc(0, x, N, H, W, C, C, w, bias, C, y, C, 1, nullptr, 0, nullptr, 0, 0, dtype, nullptr));
     cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
     double fl = 2.0 * N * H * W * (double)C * C * 9;
