@@ -19,7 +19,7 @@ template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
-template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float from_f<float>(float v) { return round_tf32(v); }   // fp32 activations feed kind::tf32 MMAs
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
 
 // 16-byte vector of T <-> floats
@@ -39,7 +39,8 @@ template <typename T>
 __device__ __forceinline__ void store16(T* p, const float (&f)[Vec16<T>::N]) {
     uint4 u;
     if constexpr (sizeof(T) == 4) {
-        u.x = __float_as_uint(f[0]); u.y = __float_as_uint(f[1]); u.z = __float_as_uint(f[2]); u.w = __float_as_uint(f[3]);
+        u.x = __float_as_uint(round_tf32(f[0])); u.y = __float_as_uint(round_tf32(f[1]));
+        u.z = __float_as_uint(round_tf32(f[2])); u.w = __float_as_uint(round_tf32(f[3]));
     } else {
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
@@ -128,11 +129,6 @@ extern "C" int b2_space_to_depth2(const void* x, long long ldx, void* planes, in
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-__device__ __forceinline__ float round_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
 template <typename T> __device__ __forceinline__ T pack_val(float v);
 template <> __device__ __forceinline__ bf16 pack_val<bf16>(float v) { return __float2bfloat16(v); }
 template <> __device__ __forceinline__ float pack_val<float>(float v) { return round_tf32(v); }

@@ -222,6 +222,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += rs[i];
                             }
                         }
+                        if (kTF32 && !p.out_fp32) {   // feeds the next kind::tf32 MMA: round to nearest, don't truncate
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+                        }
                         if (vec) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)

@@ -122,6 +122,13 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint
     return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Round-to-nearest fp32 -> tf32 (kind::tf32 MMA truncates its operands; pre-rounding makes that exact and unbiased).
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
 
 }  // namespace b2

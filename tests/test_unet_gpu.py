@@ -8,7 +8,7 @@ from oracle.weights import synth_state_dict
 pytestmark = pytest.mark.gpu
 
 # fp32-accumulate parity mode (TF32 operands): the north-star bound.  bf16 storage + bf16 operands: stated tolerance.
-TOL = {"tf32": 1e-3, "bf16": 2e-2}
+TOL = {"tf32": 1e-3, "bf16": 1e-2}
 
 
 def _build(fx, precision):
