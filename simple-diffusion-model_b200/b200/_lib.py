@@ -58,9 +58,24 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0          # kernels launched through the C ABI since import (bench.py reports the delta as gpu_launches)
+_HOOK = None          # optional (name, args) -> context manager, used by bench.py to time one kernel family with CUDA events
+
+
+def set_launch_hook(hook):
+    global _HOOK
+    _HOOK = hook
+
+
 def call(name, *args):
+    global LAUNCHES
     handle = lib()
-    rc = getattr(handle, name)(*args)
+    LAUNCHES += 1
+    if _HOOK is not None:
+        with _HOOK(name, args):
+            rc = getattr(handle, name)(*args)
+    else:
+        rc = getattr(handle, name)(*args)
     if rc != 0:
         raise B200Error(f"{name}: {handle.b2_last_error().decode()}")
 
