@@ -77,11 +77,12 @@ def test_ddpm_update_matches_oracle_with_injected_noise(sched):
     x = torch.randn((2, 3, 8, 8), generator=g)
     e = torch.randn((2, 3, 8, 8), generator=g)
     z = torch.randn((2, 3, 8, 8), generator=g)
+    xd, ed, zd = x.cuda(), e.cuda(), z.cuda()
     for step in (1000, 500, 2, 1):
         beta, alpha, abar = deg.host_params(step)
-        out = torch.empty_like(x, device="cuda")
-        zz = z.cuda() if step > 1 else None
-        call("b2_ddpm_step", ptr(x.cuda()), ptr(e.cuda()), ptr(zz), ptr(out), x.numel(), float(1 / alpha ** 0.5),
+        out = torch.empty_like(xd)
+        zz = zd if step > 1 else None
+        call("b2_ddpm_step", ptr(xd), ptr(ed), ptr(zz), ptr(out), x.numel(), float(1 / alpha ** 0.5),
              float((1 - alpha) / (1 - abar) ** 0.5), float(beta ** 0.5), 0, 0, 0, 0, stream())
         want = orc.ddpm_update(osched, x, e, step, z if step > 1 else 0)
         assert rel_l2(out.cpu(), want) < 1e-5
