@@ -21,7 +21,8 @@ struct IgemmSmem {
     static constexpr int B_BYTES = BLOCK_N * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;   // +1024: manual alignment slack
+    static constexpr int BIAS_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;        // [2 accumulator stages][BLOCK_N] fp32
+    static constexpr int TOTAL = BIAS_OFF + 2 * BLOCK_N * 4 + 1024;             // +1024: manual alignment slack
 };
 
 struct TileCoord { int nt, w0, h0, n0, g; };
@@ -36,36 +37,56 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
     return c;
 }
 
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int kThreads = 64 + kEpiWarps * 32;
+
+// Per-(image, group) sum / sum-of-squares of one 32-column chunk.  Each lane owns one pixel; the NV = 2*32/GS partial
+// values are reduced over the 32 lanes with a reduce-scatter butterfly (NV-1+log2(32/NV) shuffles instead of 5*NV),
+// after which NV distinct lanes issue one atomicAdd each.
 template <int GS>
 __device__ __forceinline__ void gn_partial(const float (&v)[32], bool valid, bool uniform, int lane,
                                            float* stats_row /* stats + n*G*2 */, int group0) {
     constexpr int NG = 32 / GS;
+    constexpr int NV = 2 * NG;
+    float a[NV];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         float s1 = 0.f, s2 = 0.f;
-        if (valid) {
 #pragma unroll
-            for (int i = 0; i < GS; ++i) { float x = v[g * GS + i]; s1 += x; s2 += x * x; }
-        }
-        if (uniform) {
+        for (int i = 0; i < GS; ++i) { const float x = v[g * GS + i]; s1 += x; s2 = fmaf(x, x, s2); }
+        a[2 * g] = valid ? s1 : 0.f;
+        a[2 * g + 1] = valid ? s2 : 0.f;
+    }
+    if (uniform) {
+        int cnt = NV;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            if (cnt > 1) {
+                const bool hi = (lane & o) != 0;
+                const int half = cnt / 2;
+#pragma unroll
+                for (int i = 0; i < NV / 2; ++i) {
+                    if (i < half) {
+                        const float keep = hi ? a[i + half] : a[i];
+                        const float send = hi ? a[i] : a[i + half];
+                        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+                cnt = half;
+            } else {
+                a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
             }
-            if (lane == 0) {
-                atomicAdd(stats_row + (group0 + g) * 2 + 0, s1);
-                atomicAdd(stats_row + (group0 + g) * 2 + 1, s2);
-            }
-        } else if (valid) {
-            atomicAdd(stats_row + (group0 + g) * 2 + 0, s1);
-            atomicAdd(stats_row + (group0 + g) * 2 + 1, s2);
         }
+        constexpr int LANES_PER_VAL = 32 / NV;
+        if ((lane & (LANES_PER_VAL - 1)) == 0) atomicAdd(stats_row + group0 * 2 + lane / LANES_PER_VAL, a[0]);
+    } else if (valid) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) atomicAdd(stats_row + group0 * 2 + i, a[i]);
     }
 }
 
 template <typename T, int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ IgemmParams p) {
     using S = IgemmSmem<BLOCK_N, STAGES>;
@@ -81,6 +102,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_s = reinterpret_cast<float*>(smem + S::BIAS_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -89,7 +111,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_holder);
@@ -155,13 +177,16 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 2..9)
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;          // which interleaved set of 32-column chunks this warp owns
+        const int epi_tid = threadIdx.x - 64;
         const int row = q * 32 + lane;
         const int w_in = row % p.wb;
         const int h_in = (row / p.wb) % p.hb;
         const int n_in = row / (p.wb * p.hb);
         const int G = p.gn_stats ? (p.Cout / p.cpg) : 0;
+        const bool f32out = kTF32 || p.out_fp32;
         int acc = 0; uint32_t acc_ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const TileCoord tc = decode_tile(p, tile);
@@ -171,11 +196,18 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const long long r_off = n * p.rN + h * p.rH + w * p.rW;
             const int n_lane0 = __shfl_sync(0xffffffffu, n, 0);
             const bool uniform = __all_sync(0xffffffffu, n == n_lane0 || !valid) && __shfl_sync(0xffffffffu, (int)valid, 0);
+            // stage this tile's bias slice once (all epilogue warps), then meet at a named barrier
+            float* bs = bias_s + acc * BLOCK_N;
+            if (epi_tid < BLOCK_N) {
+                const int c = tc.nt * BLOCK_N + epi_tid;
+                bs[epi_tid] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+            for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
                 const int col0 = tc.nt * BLOCK_N + ch * 32;
                 if (col0 >= p.Cout) break;
                 uint32_t r[32];
@@ -184,11 +216,14 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int ncols = min(32, p.Cout - col0);
                 const bool vec = p.vec_ok && ncols == 32;
                 float v[32];
+                const float4* b4 = reinterpret_cast<const float4*>(bs + ch * 32);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-                if (p.bias) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(p.bias + col0 + i);
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = b4[i];
+                    v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), p.alpha, b.x);
+                    v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), p.alpha, b.y);
+                    v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), p.alpha, b.z);
+                    v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), p.alpha, b.w);
                 }
                 if (p.act == 1) {
 #pragma unroll
@@ -206,7 +241,6 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     else                gn_partial<4>(v, valid, uniform, lane, srow, col0 / 4);
                 }
                 if (valid) {
-                    const bool f32out = kTF32 || p.out_fp32;
                     if (f32out) {
                         float* o = reinterpret_cast<float*>(p.out) + o_off + col0 * p.oC;
                         if (p.residual) {
@@ -298,7 +332,7 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmPar
     }
     const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    kern<<<grid, 192, S::TOTAL, st>>>(a, b, p);
+    kern<<<grid, kThreads, S::TOTAL, st>>>(a, b, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("igemm_nt launch: %s", cudaGetErrorString(e));
     return 0;

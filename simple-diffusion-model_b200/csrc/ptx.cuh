@@ -129,6 +129,6 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(u);
 }
 
-__device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float swishf(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace b2
