@@ -46,6 +46,20 @@ int b2_gemm_nt(const void* A, long long lda, long long a_s1, long long a_s2, con
                int Ncols, int K, int batch1, int batch2, const float* bias, float alpha, int act,
                const void* residual, long long ldr, int out_fp32, int dtype, void* stream);
 
+/* ---- gradients of the dense contractions (tcgen05 "TN" GEMM: contraction over pixel / sequence rows) -------- */
+
+/* Weight gradient of b2_conv2d_nhwc's three modes (autograd's convolution_backward in the reference), accumulated
+ * with fp32 atomics into a ZEROED buffer in kernel layout: mode 0/1 [Cout][9][Cin], mode 2 [4][Cout][4][Cin].
+ * x: forward input (mode 1: its parity planes); dz: gradient w.r.t. the conv pre-activation output
+ * (mode 2: [N][2H][2W][Cout]); (H, W) as in b2_conv2d_nhwc. */
+int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* dz, int Cout,
+                    long long lddz, float* grad_packed, int dtype, void* stream);
+/* C (+)= alpha * A^T . B with A [K][M], B [K][Ncols] (rows = contraction index), optionally batched.
+ * out_mode 0: fp32 atomic accumulate (Linear weight grads); out_mode 1: store in `dtype` (attention dV, dK). */
+int b2_gemm_tn(const void* A, long long lda, long long a_s1, long long a_s2, const void* B, long long ldb,
+               long long b_s1, long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2, int M,
+               int Ncols, int K, int batch1, int batch2, float alpha, int out_mode, int dtype, void* stream);
+
 /* ---- memory-bound forward kernels ----------------------------------------------------------------------- */
 
 /* fp32 NCHW image -> NHWC `dtype` with channels zero-padded to Cpad (network input edge, U_Net.py:155). */

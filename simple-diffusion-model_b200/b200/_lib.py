@@ -17,6 +17,8 @@ _P, _I, _L, _F, _U = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_
 SIGNATURES = {
     "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
     "b2_gemm_nt": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P, _F, _I, _P, _L, _I, _I, _P],
+    "b2_conv2d_wgrad": [_I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _I, _P],
+    "b2_gemm_tn": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "b2_nchw_to_nhwc_pad": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b2_nhwc_to_nchw": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
     "b2_space_to_depth2": [_P, _L, _P, _I, _I, _I, _I, _I, _P],

@@ -177,3 +177,169 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
     }
     return launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream);
 }
+
+// ================================================================================================ TN GEMM launchers
+namespace b2 {
+int launch_gemm_tn(int dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int block_n, cudaStream_t st);
+}
+
+// K box of <= 64 pixel rows whose row count is a multiple of the MMA K (16 bf16 / 8 tf32); boxes may overhang the
+// tensor (TMA zero-fills), which is what makes tiny images and short sequences legal.
+static int pick_kbox(int W, int H, int N, int batch_mode, int kmult, int* wb, int* hb, int* nb) {
+    if (batch_mode) {
+        int w = W < 64 ? W : 64;
+        w = ((w + kmult - 1) / kmult) * kmult;
+        *wb = w; *hb = 1; *nb = 1;
+        return 0;
+    }
+    for (int w = (W < 64 ? W : 64); w >= 1; --w) {
+        if (W % w) continue;
+        for (int h = (H < 64 / w ? H : 64 / w); h >= 1; --h) {
+            if (H % h) continue;
+            int n = 64 / (w * h);
+            if (n > N) n = N;
+            if (h < H) n = 1;                       // images may only be batched once whole images fit
+            while (n >= 1 && (w * h * n) % kmult) --n;
+            if (n >= 1) { *wb = w; *hb = h; *nb = n; return 0; }
+            // round the image count UP instead (overhang is zero-filled)
+            if (h == H) {
+                n = 1;
+                while ((w * h * n) % kmult) ++n;
+                if (w * h * n <= 64) { *wb = w; *hb = h; *nb = n; return 0; }
+            }
+        }
+    }
+    return set_error("gemm_tn: cannot tile a %dx%d image into K boxes of a multiple of %d rows", W, H, kmult);
+}
+
+static int tn_block_n(int ncols, int dtype) {
+    if (dtype == 0) return ncols >= 256 ? 256 : (ncols >= 128 ? 128 : 64);
+    return ncols >= 128 ? 128 : (ncols >= 64 ? 64 : 32);
+}
+
+static void tn_pick_splits(GemmTnParams* p, int batches) {
+    const int sms = device_sm_count();
+    const long long base = (long long)p->m_tiles * p->n_tiles * p->taps * batches;
+    const int k_boxes = p->kt_w * p->kt_h * p->kt_n;
+    int splits = 1;
+    if (p->out_mode == 0 && base < 2LL * sms) {
+        splits = (int)((2LL * sms + base - 1) / base);
+        const int cap = k_boxes / 4 > 1 ? k_boxes / 4 : 1;
+        if (splits > cap) splits = cap;
+    }
+    p->splits = splits < 1 ? 1 : splits;
+}
+
+// Weight gradient of the three convolution flavours, accumulated (fp32 atomics) into a zero-initialised buffer in
+// KERNEL layout: mode 0/1 -> [Cout][9][Cin], mode 2 -> [4 parities][Cout][4][Cin]  (b2_unpack_weight_grad maps
+// it back to the parameter's layout).  x: the forward input (mode 1: its parity planes), dz: gradient w.r.t. the
+// conv's pre-activation output.  (H, W): forward A-operand extents, as in b2_conv2d_nhwc.
+extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* dz,
+                               int Cout, long long lddz, float* grad_packed, int dtype, void* stream) {
+    const int eb = dtype == 0 ? 2 : 4;
+    const int kmult = dtype == 0 ? 16 : 8;
+    if (mode < 0 || mode > 2) return set_error("b2_conv2d_wgrad: bad mode %d", mode);
+    if ((ldx * eb) % 16 || (lddz * eb) % 16) return set_error("b2_conv2d_wgrad: channel strides must be 16-byte multiples");
+    GemmTnParams p;
+    memset(&p, 0, sizeof(p));
+    p.W = W; p.H = H; p.N = N;
+    if (pick_kbox(W, H, N, 0, kmult, &p.wb, &p.hb, &p.nb)) return 1;
+    p.kt_w = (W + p.wb - 1) / p.wb; p.kt_h = (H + p.hb - 1) / p.hb; p.kt_n = (N + p.nb - 1) / p.nb;
+    p.batch_mode = 0;
+    p.M = Cout; p.Ncols = Cin;
+    p.m_tiles = (Cout + 127) / 128;
+    const int bn = tn_block_n(Cin, dtype);
+    p.n_tiles = (Cin + bn - 1) / bn;
+    p.out_mode = 0; p.alpha = 1.0f;
+    p.tap_stride = Cin;
+    const int slab = 128 / eb;
+    int b_images = N;
+    const int n_groups = mode == 2 ? 4 : 1;
+    if (mode == 0 || mode == 1) {
+        p.taps = 9; p.ldc = 9LL * Cin;
+        for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+            const int t = kh * 3 + kw;
+            if (mode == 0) { p.tap_dh[t] = kh - 1; p.tap_dw[t] = kw - 1; p.tap_dn[t] = 0; }
+            else {
+                const int pr = (kh != 1), pc = (kw != 1);
+                p.tap_dh[t] = (kh == 0) ? -1 : 0; p.tap_dw[t] = (kw == 0) ? -1 : 0; p.tap_dn[t] = (pr * 2 + pc) * N;
+            }
+        }
+        if (mode == 1) b_images = 4 * N;
+    } else {
+        p.taps = 4; p.ldc = 4LL * Cin;
+    }
+    tn_pick_splits(&p, 1);
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)b_images};
+        uint64_t str[3] = {(uint64_t)ldx * eb, (uint64_t)W * ldx * eb, (uint64_t)H * W * ldx * eb};
+        uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
+        if (make_tmap_4d(&tb, x, eb, dims, str, box, dtype == 1)) return 1;
+    }
+    for (int g = 0; g < n_groups; ++g) {
+        const char* dz_base = (const char*)dz;
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)lddz * eb, (uint64_t)W * lddz * eb, (uint64_t)H * W * lddz * eb};
+        GemmTnParams pg = p;
+        pg.out = grad_packed;
+        if (mode == 2) {       // dz is [N][2H][2W][Cout]; parity (a, b) is the strided view dz[:, a::2, b::2, :]
+            const int a = g >> 1, b = g & 1;
+            dz_base += ((long long)a * (2 * W) + b) * lddz * eb;
+            str[0] = (uint64_t)2 * lddz * eb; str[1] = (uint64_t)2 * (2 * W) * lddz * eb; str[2] = (uint64_t)4 * H * W * lddz * eb;
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
+                const int t = i * 2 + j;
+                pg.tap_dh[t] = (i == 0) ? 0 : (a == 0 ? -1 : 1);
+                pg.tap_dw[t] = (j == 0) ? 0 : (b == 0 ? -1 : 1);
+                pg.tap_dn[t] = 0;
+            }
+            pg.out = grad_packed + (long long)g * Cout * 4 * Cin;
+        }
+        uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
+        if (make_tmap_4d(&ta, dz_base, eb, dims, str, box, dtype == 1)) return 1;
+        if (launch_gemm_tn(dtype, ta, tb, pg, bn, (cudaStream_t)stream)) return 1;
+    }
+    return 0;
+}
+
+// C[b2][b1][m][n] (+)= alpha * sum_k A[b2][b1][k][m] * B[b2][b1][k][n]; A [K][M] (row stride lda), B [K][Ncols].
+// out_mode 0: fp32 atomic accumulate into C (Linear weight gradients: dW = dY^T X, k = row);
+// out_mode 1: store in `dtype` (attention dV = P^T dO, dK = dS^T Q; batched over head / image).
+extern "C" int b2_gemm_tn(const void* A, long long lda, long long a_s1, long long a_s2, const void* B, long long ldb,
+                          long long b_s1, long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2, int M,
+                          int Ncols, int K, int batch1, int batch2, float alpha, int out_mode, int dtype, void* stream) {
+    const int eb = dtype == 0 ? 2 : 4;
+    const int kmult = dtype == 0 ? 16 : 8;
+    if ((lda * eb) % 16 || (ldb * eb) % 16) return set_error("b2_gemm_tn: lda/ldb rows must be 16-byte multiples");
+    GemmTnParams p;
+    memset(&p, 0, sizeof(p));
+    p.W = K; p.H = batch1; p.N = batch2;
+    if (pick_kbox(K, 1, 1, 1, kmult, &p.wb, &p.hb, &p.nb)) return 1;
+    p.kt_w = (K + p.wb - 1) / p.wb; p.kt_h = 1; p.kt_n = 1;
+    p.batch_mode = 1;
+    p.M = M; p.Ncols = Ncols;
+    p.m_tiles = (M + 127) / 128;
+    const int bn = tn_block_n(Ncols, dtype);
+    p.n_tiles = (Ncols + bn - 1) / bn;
+    p.taps = 1;
+    p.out = C; p.ldc = ldc; p.tap_stride = 0; p.c_s1 = c_s1; p.c_s2 = c_s2;
+    p.out_mode = out_mode; p.alpha = alpha;
+    tn_pick_splits(&p, batch1 * batch2);
+    const int slab = 128 / eb;
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[4] = {(uint64_t)M, (uint64_t)K, (uint64_t)batch1, (uint64_t)batch2};
+        uint64_t str[3] = {(uint64_t)lda * eb, (uint64_t)(batch1 > 1 ? a_s1 : lda * K) * eb,
+                           (uint64_t)(batch2 > 1 ? a_s2 : lda * K * batch1) * eb};
+        uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, 1, 1};
+        if (make_tmap_4d(&ta, A, eb, dims, str, box, dtype == 1)) return 1;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Ncols, (uint64_t)K, (uint64_t)batch1, (uint64_t)batch2};
+        uint64_t str[3] = {(uint64_t)ldb * eb, (uint64_t)(batch1 > 1 ? b_s1 : ldb * K) * eb,
+                           (uint64_t)(batch2 > 1 ? b_s2 : ldb * K * batch1) * eb};
+        uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, 1, 1};
+        if (make_tmap_4d(&tb, B, eb, dims, str, box, dtype == 1)) return 1;
+    }
+    return launch_gemm_tn(dtype, ta, tb, p, bn, (cudaStream_t)stream);
+}

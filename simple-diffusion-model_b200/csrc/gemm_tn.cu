@@ -1,0 +1,256 @@
+// tcgen05 "TN" GEMM for sm_100a: C[m][n] (+)= alpha * sum_k A[k][m] * B[k][n], both operands MN-major in shared
+// memory (the contraction index is the row index of both global tensors).  This is the shape of every weight
+// gradient of the U-Net (k = pixel: dW[cout][tap][cin] = sum_p dz[p][cout] * x[p + tap][cin], the reference's
+// convolution_backward / addmm backward) and of the attention products contracted over the sequence axis
+// (dV = P^T dO, dK = dS^T Q; reference models/custom_layers.py:144-150 under autograd).
+//   * operands arrive through 4-D TMA maps (channel | W | H | N); a filter tap is a shifted box with TMA zero fill,
+//     so the im2col matrix of the weight gradient never exists;
+//   * split-K over pixel boxes with fp32 vector atomics straight into the (flat) gradient buffer;
+//   * same warp roles / TMEM double buffering as igemm_nt.cu.
+#include "ptx.cuh"
+#include "igemm.h"
+#include "host_util.h"
+
+namespace b2 {
+
+constexpr int kTnEpiWarps = 8;
+constexpr int kTnThreads = 64 + kTnEpiWarps * 32;
+constexpr int kTnBK = 64;     // pixel rows per pipeline stage
+
+template <int BLOCK_N, int STAGES>
+struct TnSmem {
+    static constexpr int A_BYTES = 2 * kTnBK * 128;                 // two 64-wide M slabs
+    static constexpr int B_BYTES = (BLOCK_N / 64) * kTnBK * 128;    // BLOCK_N/64 slabs (bf16) -- see slab() for fp32
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+struct TnWork { int mt, nt_in_tap, tap, split, bh, bn; };
+
+__device__ __forceinline__ TnWork tn_decode(const GemmTnParams& p, int item) {
+    TnWork w;
+    w.split = item % p.splits;  item /= p.splits;
+    w.mt = item % p.m_tiles;    item /= p.m_tiles;
+    w.nt_in_tap = item % p.n_tiles;  item /= p.n_tiles;
+    w.tap = item % p.taps;      item /= p.taps;
+    if (p.batch_mode) { w.bh = item % p.H; w.bn = item / p.H; } else { w.bh = 0; w.bn = 0; }
+    return w;
+}
+
+// T = bf16: 64 elements per 128-byte slab row; T = float (tf32): 32 elements per slab row.
+template <typename T, int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kTnThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ GemmTnParams p) {
+    constexpr bool kTF32 = (sizeof(T) == 4);
+    constexpr int SLAB = 128 / sizeof(T);                 // MN elements per slab
+    constexpr int A_SLABS = 128 / SLAB;
+    constexpr int B_SLABS = BLOCK_N / SLAB;
+    constexpr int SLAB_BYTES = kTnBK * 128;
+    constexpr int A_BYTES = A_SLABS * SLAB_BYTES;
+    constexpr int B_BYTES = B_SLABS * SLAB_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int UMMA_K = 32 / sizeof(T);                // 16 (bf16) / 8 (tf32)
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kTnEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int batches = p.batch_mode ? p.H * p.N : 1;
+    const int total_items = p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
+    const int k_boxes = p.kt_w * p.kt_h * p.kt_n;
+    const uint32_t box_rows = static_cast<uint32_t>(p.wb * p.hb * p.nb);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const TnWork wk = tn_decode(p, item);
+                const int kb0 = (int)(((long long)k_boxes * wk.split) / p.splits);
+                const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    int r = kb;
+                    const int w0 = (r % p.kt_w) * p.wb;  r /= p.kt_w;
+                    int h0 = (r % p.kt_h) * p.hb;  r /= p.kt_h;
+                    int n0 = r * p.nb;
+                    if (p.batch_mode) { h0 = wk.bh; n0 = wk.bn; }
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + A_BYTES;
+                    mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
+#pragma unroll
+                    for (int sl = 0; sl < A_SLABS; ++sl)
+                        tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
+                    const int bw = w0 + p.tap_dw[wk.tap];
+                    const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
+                    const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
+#pragma unroll
+                    for (int sl = 0; sl < B_SLABS; ++sl)
+                        tma_load_4d(b_dst + sl * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + sl * SLAB, bw, bh, bn);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 1, 1);
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            const int k_steps = (int)(box_rows + UMMA_K - 1) / UMMA_K;      // rows beyond the box are never touched
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const TnWork wk = tn_decode(p, item);
+                const int kb0 = (int)(((long long)k_boxes * wk.split) / p.splits);
+                const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
+                mbar_wait(&tempty[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+                    for (int k = 0; k < k_steps; ++k) {
+                        // bf16: 8-row atoms (1024 B) of 16-byte chunks; tf32: 4-row atoms (512 B) of 32-byte chunks
+                        const uint64_t ad = umma_desc_sw128(a_addr + k * UMMA_K * 128, SLAB_BYTES, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
+                        const uint64_t bd = umma_desc_sw128(b_addr + k * UMMA_K * 128, SLAB_BYTES, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
+                        umma_ss<kTF32>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const TnWork wk = tn_decode(p, item);
+            const int m = wk.mt * 128 + q * 32 + lane;
+            const bool valid = m < p.M;
+            const long long off = (long long)m * p.ldc + (long long)wk.tap * p.tap_stride + wk.bh * p.c_s1 + wk.bn * p.c_s2;
+            const int kb0 = (int)(((long long)k_boxes * wk.split) / p.splits);
+            const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
+            mbar_wait(&tfull[acc], acc_ph);
+            tc_fence_after();
+            if (kb1 > kb0) {
+#pragma unroll 1
+                for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
+                    const int col0 = wk.nt_in_tap * BLOCK_N + ch * 32;
+                    if (col0 >= p.Ncols) break;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                    tmem_ld_wait();
+                    const int ncols = min(32, p.Ncols - col0);
+                    if (!valid) continue;
+                    if (p.out_mode == 0) {
+                        float* o = reinterpret_cast<float*>(p.out) + off + col0;
+                        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                atomicAdd(reinterpret_cast<float4*>(o) + i,
+                                          make_float4(__uint_as_float(r[4 * i]) * p.alpha, __uint_as_float(r[4 * i + 1]) * p.alpha,
+                                                      __uint_as_float(r[4 * i + 2]) * p.alpha, __uint_as_float(r[4 * i + 3]) * p.alpha));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) atomicAdd(o + i, __uint_as_float(r[i]) * p.alpha);
+                        }
+                    } else if (kTF32) {
+                        float* o = reinterpret_cast<float*>(p.out) + off + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = round_tf32(__uint_as_float(r[i]) * p.alpha);
+                    } else {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + col0;
+                        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 x;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    h2[j] = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 2 * j]) * p.alpha,
+                                                                  __uint_as_float(r[8 * i + 2 * j + 1]) * p.alpha);
+                                reinterpret_cast<uint4*>(o)[i] = x;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = __float2bfloat16(__uint_as_float(r[i]) * p.alpha);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <typename T, int BLOCK_N, int STAGES>
+static int launch_tn_cfg(const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int num_sms, cudaStream_t st) {
+    constexpr int SLAB = 128 / sizeof(T);
+    constexpr int stage_bytes = (128 / SLAB + BLOCK_N / SLAB) * kTnBK * 128;
+    constexpr int total = STAGES * stage_bytes + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static_assert(total <= 227 * 1024, "shared memory budget");
+    auto kern = gemm_tn_kernel<T, BLOCK_N, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+        if (e != cudaSuccess) return set_error("gemm_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int batches = p.batch_mode ? p.H * p.N : 1;
+    const long long items = (long long)p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
+    const int grid = (int)(items < num_sms ? items : num_sms);
+    kern<<<grid, kTnThreads, total, st>>>(a, b, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("gemm_tn launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_gemm_tn(int dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int block_n, cudaStream_t st) {
+    const int sms = device_sm_count();
+    if (dtype == 0) {
+        if (block_n == 256) return launch_tn_cfg<__nv_bfloat16, 256, 4>(a, b, p, sms, st);
+        if (block_n == 128) return launch_tn_cfg<__nv_bfloat16, 128, 6>(a, b, p, sms, st);
+        if (block_n == 64)  return launch_tn_cfg<__nv_bfloat16, 64, 8>(a, b, p, sms, st);
+    } else {
+        if (block_n == 128) return launch_tn_cfg<float, 128, 3>(a, b, p, sms, st);
+        if (block_n == 64)  return launch_tn_cfg<float, 64, 4>(a, b, p, sms, st);
+        if (block_n == 32)  return launch_tn_cfg<float, 32, 5>(a, b, p, sms, st);
+    }
+    return set_error("gemm_tn: unsupported block_n %d for dtype %d", block_n, dtype);
+}
+
+}  // namespace b2

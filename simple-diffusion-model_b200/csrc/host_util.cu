@@ -47,7 +47,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4],
-                 const uint64_t strides_bytes[3], const uint32_t box[4]) {
+                 const uint64_t strides_bytes[3], const uint32_t box[4], bool atom32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("TMA base pointer not 16-byte aligned");
@@ -61,7 +61,7 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
     if (box[0] * elem_bytes != 128) return set_error("TMA inner box must be 128 bytes");
     CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUresult r = enc(out, dt, 4, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error("cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu box %u %u %u %u", (int)r,
                          (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],

@@ -35,10 +35,24 @@ struct IgemmParams {
     int cpg;                     // channels per GroupNorm group
 };
 
-// C[m, n] (+)= sum_k A[k, m] * B[k + shift, n]  -- both operands MN-major ("TN" GEMM): weight
-// gradients (k = pixel), P.V in attention (k = key).
+// C[m, n] (+)= alpha * sum_k A[k, m] * B[k + tap shift, n]  -- both operands MN-major ("TN" GEMM).
+//   weight gradients: k = pixel, m = Cout, n = (tap, Cin)            (reference: autograd's convolution_backward)
+//   attention:        k = key / query index, batched over (head, image)
+// A and B are reached through 4-D TMA maps (channel | W | H | N); a K block is a box of up to 64 pixel rows.
 struct GemmTnParams {
-    int dummy;
+    int W, H, N;                 // pixel extents of the maps' dims 1..3
+    int wb, hb, nb;              // K box (wb*hb*nb <= 64 rows)
+    int kt_w, kt_h, kt_n;        // K boxes per dim; in batch mode kt_h = kt_n = 1 and (H, N) index the batch
+    int batch_mode;              // 0: K spans (w, h, n); 1: K spans w only, tiles are batched over (h, n)
+    int m_tiles, n_tiles;        // output tiles: M / 128, ceil(Ncols_per_tap / BLOCK_N)
+    int taps;                    // taps (n-tile index = tap * n_tiles_per_tap + j)
+    int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dn[kMaxTaps];
+    int splits;                  // split-K factor (work item = tile x split)
+    int M, Ncols;                // valid rows / valid columns per tap
+    void* out;                   // C; row stride ldc, tap stride tap_stride (elements), batch strides c_s1 (h) / c_s2 (n)
+    long long ldc, tap_stride, c_s1, c_s2;
+    int out_mode;                // 0: fp32 atomicAdd (gradient accumulation), 1: store in the operand dtype
+    float alpha;
 };
 
 }  // namespace b2

@@ -107,13 +107,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
 //  K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO = 1024); LBO unused.
 //  MN-major: 64-element (128 B) runs along MN, k rows 128 B apart, 8-k atoms SBO apart, next 64-wide MN slab LBO apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//  layout: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row atoms; the only
+//  MN-major form accepted for 32-bit (tf32) operands -- TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= 1ull << 46;   // descriptor version (Blackwell)
-    d |= 2ull << 61;   // SWIZZLE_128B
+    d |= static_cast<uint64_t>(layout) << 61;
     return d;
 }
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate.

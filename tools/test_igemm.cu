@@ -185,6 +185,106 @@ static void perf_conv(int dtype, int N, int H, int W, int C, int iters) {
     cudaFree(x); cudaFree(y); cudaFree(w); cudaFree(bias);
 }
 
+// weight gradient: reference in double from rounded operands
+static void test_wgrad(int mode, int dtype, int N, int H, int W, int Cin, int Cout) {
+    // (H, W): forward INPUT dims of the conv (mode 1: even; mode 2: input of the transposed conv)
+    const int OH = mode == 0 ? H : (mode == 1 ? H / 2 : 2 * H), OW = mode == 0 ? W : (mode == 1 ? W / 2 : 2 * W);
+    const int KS = mode == 2 ? 4 : 3;
+    Buf x, dz, planes;
+    x.alloc((size_t)N * H * W * Cin, dtype, true, 2.f);
+    dz.alloc((size_t)N * OH * OW * Cout, dtype, true, 1.f);
+    const void* xin = x.d;
+    if (mode == 1) {
+        planes.alloc(x.n, dtype, false);
+        for (int pr = 0; pr < 2; ++pr) for (int pc = 0; pc < 2; ++pc) for (int n = 0; n < N; ++n)
+            for (int i = 0; i < OH; ++i) for (int j = 0; j < OW; ++j) for (int c = 0; c < Cin; ++c)
+                planes.h[(((((size_t)(pr * 2 + pc) * N + n) * OH + i) * OW) + j) * Cin + c] = x.h[(((size_t)n * H + 2 * i + pr) * W + 2 * j + pc) * Cin + c];
+        planes.upload();
+        xin = planes.d;
+    }
+    const size_t gsz = (size_t)Cout * KS * KS * Cin;
+    float* d_g; CK(cudaMalloc(&d_g, gsz * 4)); CK(cudaMemset(d_g, 0, gsz * 4));
+    const int kH = mode == 1 ? OH : H, kW = mode == 1 ? OW : W;
+    B2(b2_conv2d_wgrad(mode, xin, N, kH, kW, Cin, Cin, dz.d, Cout, Cout, d_g, dtype, nullptr));
+    CK(cudaDeviceSynchronize());
+    std::vector<float> g(gsz); CK(cudaMemcpy(g.data(), d_g, gsz * 4, cudaMemcpyDeviceToHost));
+    // reference dW[co][kh][kw][ci]
+    double maxerr = 0, maxref = 0;
+    for (int co = 0; co < Cout; co += 7) for (int kh = 0; kh < KS; ++kh) for (int kw = 0; kw < KS; ++kw) for (int ci = 0; ci < Cin; ci += 5) {
+        double acc = 0;
+        for (int n = 0; n < N; ++n) for (int oh = 0; oh < OH; ++oh) for (int ow = 0; ow < OW; ++ow) {
+            int ih, iw;
+            if (mode == 0) { ih = oh - 1 + kh; iw = ow - 1 + kw; }
+            else if (mode == 1) { ih = 2 * oh - 1 + kh; iw = 2 * ow - 1 + kw; }
+            else { int th = oh + 1 - kh, tw = ow + 1 - kw; if (th % 2 || tw % 2 || th < 0 || tw < 0) continue; ih = th / 2; iw = tw / 2; }
+            if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+            acc += (double)dz.h[(((size_t)n * OH + oh) * OW + ow) * Cout + co] * x.h[(((size_t)n * H + ih) * W + iw) * Cin + ci];
+        }
+        size_t gi;
+        if (mode != 2) gi = (((size_t)co * 9) + kh * 3 + kw) * Cin + ci;
+        else {
+            // packed [g=(a,b)][co][t=(i,j)][ci]; a=0: kh {1,3} ; a=1: kh {2,0}
+            int a = (kh == 1 || kh == 3) ? 0 : 1, i = (kh == 1 || kh == 2) ? 0 : 1;
+            int b = (kw == 1 || kw == 3) ? 0 : 1, j = (kw == 1 || kw == 2) ? 0 : 1;
+            gi = ((((size_t)(a * 2 + b) * Cout + co) * 4) + i * 2 + j) * Cin + ci;
+        }
+        maxerr = fmax(maxerr, fabs(acc - g[gi]));
+        maxref = fmax(maxref, fabs(acc));
+    }
+    char name[256];
+    snprintf(name, sizeof(name), "wgrad mode%d %s N%d H%d W%d Cin%d Cout%d (ref max %.2f)", mode, dtype ? "tf32" : "bf16", N, H, W, Cin, Cout, maxref);
+    report(name, maxerr / (maxref + 1e-9), 2e-3);
+    cudaFree(d_g); x.free_(); dz.free_(); planes.free_();
+}
+
+static void test_gemm_tn(int dtype, int M, int Nc, int K, int b1, int b2, int out_mode, float alpha) {
+    Buf A, B, C;
+    A.alloc((size_t)b2 * b1 * K * M, dtype, true, 1.f);
+    B.alloc((size_t)b2 * b1 * K * Nc, dtype, true, 1.f);
+    const int cdt = out_mode == 0 ? 1 : dtype;
+    C.alloc((size_t)b2 * b1 * M * Nc, cdt, false);
+    B2(b2_gemm_tn(A.d, M, (long long)K * M, (long long)b1 * K * M, B.d, Nc, (long long)K * Nc, (long long)b1 * K * Nc, C.d, Nc,
+                  (long long)M * Nc, (long long)b1 * M * Nc, M, Nc, K, b1, b2, alpha, out_mode, dtype, nullptr));
+    CK(cudaDeviceSynchronize());
+    C.download();
+    double maxerr = 0;
+    for (int b = 0; b < b1 * b2; ++b) for (int m = 0; m < M; ++m) for (int n = 0; n < Nc; ++n) {
+        double acc = 0;
+        for (int k = 0; k < K; ++k) acc += (double)A.h[((size_t)b * K + k) * M + m] * B.h[((size_t)b * K + k) * Nc + n];
+        acc *= alpha;
+        maxerr = fmax(maxerr, fabs(acc - C.h[((size_t)b * M + m) * Nc + n]) / (1.0 + fabs(acc)));
+    }
+    if (maxerr > 0.1) {
+        printf("  debug gemm_tn: first row got/want:");
+        for (int n = 0; n < 8; ++n) { double acc = 0; for (int k = 0; k < K; ++k) acc += (double)A.h[(size_t)k * M + 0] * B.h[(size_t)k * Nc + n]; printf(" %.3f/%.3f", C.h[n], acc * alpha); }
+        printf("\n  row 33:");
+        for (int n = 0; n < 8; ++n) { double acc = 0; for (int k = 0; k < K; ++k) acc += (double)A.h[(size_t)k * M + 33] * B.h[(size_t)k * Nc + n]; printf(" %.3f/%.3f", C.h[(size_t)33 * Nc + n], acc * alpha); }
+        printf("\n");
+    }
+    char name[256];
+    snprintf(name, sizeof(name), "gemm_tn %s M%d N%d K%d b%dx%d mode%d", dtype ? "tf32" : "bf16", M, Nc, K, b1, b2, out_mode);
+    report(name, maxerr, (cdt == 0) ? 1e-2 : 2e-3);
+    A.free_(); B.free_(); C.free_();
+}
+
+static void perf_wgrad(int dtype, int N, int H, int W, int C, int iters) {
+    const size_t eb = dtype == 0 ? 2 : 4;
+    void *x, *dz; float* g;
+    CK(cudaMalloc(&x, (size_t)N * H * W * C * eb)); CK(cudaMalloc(&dz, (size_t)N * H * W * C * eb));
+    CK(cudaMalloc(&g, (size_t)C * 9 * C * 4));
+    CK(cudaMemset(x, 0, (size_t)N * H * W * C * eb)); CK(cudaMemset(dz, 0, (size_t)N * H * W * C * eb)); CK(cudaMemset(g, 0, (size_t)C * 9 * C * 4));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) B2(b2_conv2d_wgrad(0, x, N, H, W, C, C, dz, C, C, g, dtype, nullptr));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) B2(b2_conv2d_wgrad(0, x, N, H, W, C, C, dz, C, C, g, dtype, nullptr));
+    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+    double fl = 2.0 * N * H * W * (double)C * C * 9;
+    printf("perf wgrad3x3 %s N%d %dx%d C%d: %.3f ms  %.1f TFLOP/s\n", dtype ? "tf32" : "bf16", N, H, W, C, ms, fl / ms * 1e-9);
+    cudaFree(x); cudaFree(dz); cudaFree(g);
+}
+
 int main(int argc, char** argv) {
     const bool perf = argc > 1 && std::string(argv[1]) == "perf";
     // plain GEMM first: the simplest use of the pipeline
@@ -209,6 +309,25 @@ int main(int argc, char** argv) {
     test_conv(2, 0, 2, 8, 8, 128, 64, false, false, 1);
     test_conv(2, 0, 3, 2, 2, 256, 128, false, false, 1);
     test_conv(2, 1, 2, 8, 8, 64, 64, false, false, 1);
+    // TN GEMM / weight gradients
+    test_gemm_tn(0, 128, 128, 64, 1, 1, 0, 1.f);
+    test_gemm_tn(0, 128, 256, 512, 1, 1, 0, 1.f);
+    test_gemm_tn(0, 200, 192, 300, 1, 1, 0, 0.5f);
+    test_gemm_tn(0, 64, 512, 64, 2, 3, 1, 1.f);
+    test_gemm_tn(0, 16, 64, 16, 2, 2, 1, 1.f);
+    test_gemm_tn(0, 8, 64, 4, 1, 3, 1, 0.25f);
+    test_gemm_tn(1, 128, 128, 256, 1, 1, 0, 1.f);
+    test_gemm_tn(1, 64, 96, 40, 2, 2, 1, 1.f);
+    test_wgrad(0, 0, 2, 16, 16, 64, 128);
+    test_wgrad(0, 0, 1, 64, 64, 128, 128);
+    test_wgrad(0, 0, 3, 2, 2, 128, 64);
+    test_wgrad(0, 0, 5, 4, 4, 256, 256);
+    test_wgrad(0, 1, 2, 8, 8, 64, 128);
+    test_wgrad(1, 0, 2, 16, 16, 128, 128);
+    test_wgrad(1, 0, 3, 4, 4, 64, 128);
+    test_wgrad(2, 0, 2, 8, 8, 128, 64);
+    test_wgrad(2, 0, 3, 2, 2, 128, 128);
+    test_wgrad(2, 1, 2, 4, 4, 64, 64);
     printf(g_fail ? "FAILED %d checks\n" : "ALL OK\n", g_fail);
     if (perf) {
         perf_conv(0, 256, 16, 16, 1024, 10);
@@ -216,6 +335,10 @@ int main(int argc, char** argv) {
         perf_conv(0, 256, 64, 64, 128, 10);
         perf_conv(0, 8, 16, 16, 1024, 10);
         perf_conv(1, 64, 16, 16, 1024, 5);
+        perf_wgrad(0, 8, 16, 16, 1024, 10);
+        perf_wgrad(0, 32, 16, 16, 1024, 10);
+        perf_wgrad(0, 8, 64, 64, 128, 10);
+        perf_wgrad(0, 32, 32, 32, 512, 10);
     }
     return g_fail ? 1 : 0;
 }
