@@ -29,7 +29,11 @@ int b2_version(void);
  * mode 1: Conv2d 3x3 stride 2 pad 1            (custom_layers.py:196-201), x = parity planes
  *         [2][2][N][H][W][Cin] made by b2_space_to_depth2, (H, W) = OUTPUT size
  * mode 2: ConvTranspose2d 4x4 stride 2 pad 1   (custom_layers.py:174-179), (H, W) = INPUT size, y is 2H x 2W
- * wpacked: weights in kernel layout from b2_pack_conv_weight. act: 0 none, 1 Swish (custom_layers.py:18-20).
+ * mode 3: data gradient of mode 1: x = dz [N][H][W][Cin=fwd Cout], y = dx [N][2H][2W][Cout=fwd Cin], weights kind 5
+ * mode 4: data gradient of mode 2: x = parity planes of dz [2][2][N][H][W][fwd Cout], y = dx [N][H][W], weights kind 6
+ *         (data gradient of mode 0 is mode 0 itself with weights of kind 1)
+ * wpacked: weights in kernel layout from b2_pack_conv_weight. act: 0 none, 1 Swish (custom_layers.py:18-20), 2 tanh,
+ * 3 = store the pre-activation but accumulate the GroupNorm statistics of Swish(value) (training forward).
  * residual (optional, mode 0/1): added after the activation. gn_stats (optional): [N][gn_groups][2] fp32,
  * must be zeroed by the caller; receives per-(image, group) sum and sum of squares of the written values.
  * out_mode 0: y is NHWC in `dtype`; out_mode 1 (mode 0 only): y is fp32 NCHW [N][Cout][H][W] -- the final
@@ -68,17 +72,19 @@ int b2_nchw_to_nhwc_pad(const float* x, void* y, int N, int C, int H, int W, int
 int b2_nhwc_to_nchw(const void* x, long long ldx, float* y, int N, int C, int H, int W, int dtype, void* stream);
 /* planes[pr][pc][n][i][j][:] = x[n][2i+pr][2j+pc][:]; feeds b2_conv2d_nhwc mode 1 (custom_layers.py:196). */
 int b2_space_to_depth2(const void* x, long long ldx, void* planes, int N, int H, int W, int C, int dtype, void* stream);
-/* fp32 master weights -> kernel layout.  kind 0: Conv2d [Cout][Cin][3][3] -> [Cout][9][Cin_pad];
- * kind 1: same weight -> data-gradient layout [Cin][9 flipped][Cout]; kind 2: ConvTranspose2d [Cin][Cout][4][4]
- * -> [4 parities][Cout][4 taps][Cin]; kind 3: Linear [rows=Cout][cols=Cin] -> [rows][Cin_pad].
- * dtype 1 rounds to TF32 (round-to-nearest) so the tensor core's truncation is exact. */
-int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int Cin_pad, int dtype, void* stream);
+/* fp32 master weights -> kernel layout; k_pad zero-pads the contraction side to the 128-byte K block.
+ * kind 0 Conv2d [Cout][Cin][3][3] -> [Cout][9][k_pad>=Cin]; 1 same -> [Cin][9 flipped][k_pad>=Cout] (dgrad, s1);
+ * 2 ConvTranspose2d [Cin][Cout][4][4] -> [4 parities][Cout][4 taps][Cin]; 3 Linear [Cout][Cin] -> [Cout][k_pad>=Cin];
+ * 4 Linear -> transposed [Cin][k_pad>=Cout] (dgrad); 5 Conv2d -> [4][Cin][4 zero-padded taps][Cout] (dgrad, s2);
+ * 6 ConvTranspose2d -> [Cin][16][Cout] (dgrad).  dtype 1 rounds to TF32 (nearest) so the MMA's truncation is exact. */
+int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int k_pad, int dtype, void* stream);
 /* out = s*(gamma*(y-mean)*rstd+beta) + s (+residual): GroupNorm x AdaGN (custom_layers.py:35-45) fused with the
  * ResidualBlock add (custom_layers.py:282-287).  stats from b2_conv2d_nhwc; s = y_scale(emb) [B][C] with row
- * stride s_bstride (0 broadcasts one embedding over the batch, as the samplers do). */
+ * stride s_bstride (0 broadcasts one embedding over the batch, as the samplers do).  pre_swish: y holds the conv
+ * pre-activation (training forward keeps it for the backward pass) and Swish is applied on load. */
 int b2_adagn_apply(const void* y, long long ldy, const float* stats, const float* gamma, const float* beta,
                    const float* s, long long s_bstride, const void* residual, long long ldr, void* out, long long ldo,
-                   int N, int HW, int C, int groups, float eps, int dtype, void* stream);
+                   int N, int HW, int C, int groups, float eps, int pre_swish, int dtype, void* stream);
 /* P[b][i][j] = softmax over the QUERY index i of S[b][i][j] (custom_layers.py:147); S fp32, P `dtype`, row stride ldp. */
 int b2_softmax_query_axis(const float* S, void* P, int B, int Pq, int Pk, long long ldp, int dtype, void* stream);
 /* out[b1][b2][c][r] = in[b1][b2][r][c] (V^T for P.V, custom_layers.py:150). */
@@ -90,6 +96,31 @@ int b2_sinusoid_embedding(const long long* t, float* out, int B, int dim, void* 
  * C (+)= op(A).op(B) (+bias)(Swish). ta: A stored [K][M]; tb 0: B stored [N][K], tb 1: B stored [K][N]. */
 int b2_small_gemm(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C, long long ldc,
                   int M, int N, int K, const float* bias, int act, int accumulate, void* stream);
+
+/* ---- memory-bound backward kernels (the reference gets these from autograd) ------------------------------- */
+
+/* Backward of Conv -> Swish -> AdaGN (custom_layers.py:240-245, :35-45) from dout to the conv pre-activation:
+ * dz = rstd*(s*gamma*dout - m1 - xh*m2) * swish'(z).  Also accumulates ds (gradient of the AdaGN scale vector, row
+ * stride ds_bstride, 0 = embedding broadcast over the batch), dgamma, dbeta, dbias (+=, fp32).  z: pre-activation
+ * saved by the forward; stats: the forward's (sum, sumsq); work: >= 2*N*C + 2*N*groups floats of scratch. */
+int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats, const float* gamma,
+                 const float* beta, const float* s, long long s_bstride, float* work, float* ds, long long ds_bstride,
+                 float* dgamma, float* dbeta, void* dz, long long lddz, float* dbias, int N, int HW, int C, int groups,
+                 float eps, int dtype, void* stream);
+/* mode 0: out = swish(z); mode 1: out = a * swish'(z), dbias += column sums; mode 2: dbias += column sums of a. */
+int b2_act(int mode, const void* a, long long lda, const void* z, long long ldz, void* out, long long ldo, float* dbias,
+           long long rows, int C, int dtype, void* stream);
+/* fp32 helpers for the embedding MLPs: mode 0 swish(z), 1 a*swish'(z), 2 a*(1 - z^2) (tanh backward, z = tanh output). */
+int b2_f32_act(int mode, const float* a, const float* z, float* out, long long n, void* stream);
+/* dS = scale * P * (dP - sum_i P dP): backward of the query-axis softmax (custom_layers.py:147). */
+int b2_softmax_query_axis_bwd(const void* P, const float* dP, void* dS, int B, int Pq, int Pk, long long ldp, float scale,
+                              int dtype, void* stream);
+/* out = a + b on NHWC views (merges the two consumers of a skip tensor, models/U_Net.py:160,168, in the backward pass). */
+int b2_add(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows, int C,
+           int dtype, void* stream);
+/* Kernel-layout fp32 weight gradient -> parameter layout (kind 0: Conv2d, kind 2: ConvTranspose2d). */
+int b2_unpack_weight_grad(int kind, const float* packed, float* grad, int Cout, int Cin, int Cin_pad, int accumulate,
+                          void* stream);
 
 /* ---- diffusion process (fp32 NCHW tensors) -------------------------------------------------------------- */
 

@@ -23,7 +23,13 @@ SIGNATURES = {
     "b2_nhwc_to_nchw": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
     "b2_space_to_depth2": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
     "b2_pack_weight": [_I, _P, _P, _I, _I, _I, _I, _P],
-    "b2_adagn_apply": [_P, _L, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _P],
+    "b2_adagn_apply": [_P, _L, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _I, _P],
+    "b2_adagn_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _P],
+    "b2_act": [_I, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
+    "b2_f32_act": [_I, _P, _P, _P, _L, _P],
+    "b2_softmax_query_axis_bwd": [_P, _P, _P, _I, _I, _I, _L, _F, _I, _P],
+    "b2_add": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P],
+    "b2_unpack_weight_grad": [_I, _P, _P, _I, _I, _I, _I, _P],
     "b2_softmax_query_axis": [_P, _P, _I, _I, _I, _L, _I, _P],
     "b2_transpose_batched": [_P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P],
     "b2_sinusoid_embedding": [_P, _P, _I, _I, _P],

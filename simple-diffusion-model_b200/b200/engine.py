@@ -135,7 +135,7 @@ class UNetEngine:
         h = self.conv_block(blk.conv_block_1, x, ctx)
         return self.conv_block(blk.conv_block_2, h, ctx, out=out, residual=x)
 
-    def attention(self, blk, x, out=None):
+    def attention(self, blk, x, out=None, save=None):
         """AttentionBlock (custom_layers.py:127-163): softmax over the query axis, no norm, residual add."""
         code = ops.code_of(x)
         n, hh, ww, c = x.shape
@@ -167,6 +167,8 @@ class UNetEngine:
             out = torch.empty((n, hh, ww, c), dtype=dt, device=dev)
         ops.gemm_nt(o, wo, n * p_len, c, heads * d, heads * d, heads * d, out, out.stride(2), bias=blk.output.bias,
                     residual=x, ldr=ldx)
+        if save is not None:
+            save.update(qkv=qkv, pm=pm, o=o, ldp=ldp)
         return out
 
     def unet_block(self, blk, x, ctx, out):

@@ -83,31 +83,55 @@ def space_to_depth2(x):
     return planes
 
 
-def pack_weight(kind, w, cout, cin, cin_pad, code):
-    if kind == 0:
-        shape = (cout, 9 * cin_pad)
-    elif kind == 1:
-        shape = (cin, 9 * cout)
-    elif kind == 2:
-        shape = (4 * cout, 4 * cin)
-    else:
-        shape = (cout, cin_pad)
+def pack_weight(kind, w, cout, cin, k_pad, code):
+    """fp32 parameter -> kernel layout (kinds documented at b2_pack_weight in include/sdm_b200.h)."""
+    shape = {0: (cout, 9 * k_pad), 1: (cin, 9 * k_pad), 2: (4 * cout, 4 * cin), 3: (cout, k_pad), 4: (cin, k_pad),
+             5: (4 * cin, 4 * cout), 6: (cin, 16 * cout)}[kind]
     out = torch.empty(shape, dtype=TORCH_DTYPE[code], device=w.device)
-    call("b2_pack_weight", kind, ptr(w.detach().contiguous()), ptr(out), cout, cin, cin_pad, code, stream())
+    call("b2_pack_weight", kind, ptr(w.detach().contiguous()), ptr(out), cout, cin, k_pad, code, stream())
     return out
 
 
-def adagn_apply(y, stats, gamma, beta, s, s_bstride, out=None, residual=None, groups=32, eps=1e-5):
+def adagn_apply(y, stats, gamma, beta, s, s_bstride, out=None, residual=None, groups=32, eps=1e-5, pre_swish=False):
     n, h, w, c, ldy = _nhwc(y)
     if out is None:
         out = torch.empty((n, h, w, c), dtype=y.dtype, device=y.device)
     ldo = _nhwc(out)[4]
     ldr = _nhwc(residual)[4] if residual is not None else 0
     call("b2_adagn_apply", ptr(y), ldy, ptr(stats), ptr(gamma), ptr(beta), ptr(s), s_bstride, ptr(residual), ldr, ptr(out),
-         ldo, n, h * w, c, groups, float(eps), code_of(y), stream())
+         ldo, n, h * w, c, groups, float(eps), 1 if pre_swish else 0, code_of(y), stream())
     return out
 
 
 def small_gemm(a, b, m, n, k, lda, ldb, out, ldc, ta=0, tb=0, bias=None, act=0, accumulate=False):
     call("b2_small_gemm", ptr(a), lda, ta, ptr(b), ldb, tb, ptr(out), ldc, m, n, k, ptr(bias), act, 1 if accumulate else 0, stream())
+    return out
+
+
+def conv2d_wgrad(mode, x, dz, cout, grad_packed):
+    """Accumulates the weight gradient (kernel layout, fp32) of conv mode 0/1/2 into the zeroed `grad_packed`."""
+    code = code_of(x)
+    n, h, w, cin, ldx = _nhwc(x)
+    if mode == 1:
+        n //= 4
+    lddz = _nhwc(dz)[4]
+    call("b2_conv2d_wgrad", mode, ptr(x), n, h, w, cin, ldx, ptr(dz), cout, lddz, ptr(grad_packed), code, stream())
+
+
+def gemm_tn(a, b, m, ncols, k, lda, ldb, out, ldc, alpha=1.0, out_mode=0, batch=(1, 1), a_strides=(0, 0), b_strides=(0, 0),
+            c_strides=(0, 0), code=None):
+    code = code_of(a) if code is None else code
+    call("b2_gemm_tn", ptr(a), lda, a_strides[0], a_strides[1], ptr(b), ldb, b_strides[0], b_strides[1], ptr(out), ldc,
+         c_strides[0], c_strides[1], m, ncols, k, batch[0], batch[1], float(alpha), out_mode, code, stream())
+    return out
+
+
+def act(mode, a, z, out, dbias, rows, c, lda, ldz, ldo, code):
+    call("b2_act", mode, ptr(a), lda, ptr(z), ldz, ptr(out), ldo, ptr(dbias), rows, c, code, stream())
+    return out
+
+
+def add(a, b, out):
+    n, h, w, c, lda = _nhwc(a)
+    call("b2_add", ptr(a), lda, ptr(b), _nhwc(b)[4], ptr(out), _nhwc(out)[4], n * h * w, c, code_of(a), stream())
     return out

@@ -1,0 +1,488 @@
+"""Training-mode executor: forward with a tape + hand-written backward for the whole U-Net.
+
+The reference relies on torch.autograd over ~1.2 k ATen ops (train_diffusion.py:343-358).  Here one autograd node wraps
+the network; its backward replays a tape of layer records in reverse and launches the sm_100a gradient kernels:
+  * data gradients of every convolution re-use the forward implicit-GEMM kernel on re-packed weights,
+  * weight gradients run on the tcgen05 TN kernel (contraction over pixels, split-K, fp32 atomics),
+  * GroupNorm x AdaGN x Swish backward is two streaming passes, bias gradients ride along in those passes,
+  * all parameter gradients land in ONE flat fp32 buffer (`grad_flat`); `param.grad` tensors are views of it, which is
+    what the data-parallel all-reduce and the fused Adam consume (no per-parameter gradient tensors, no copies).
+Parameters that never receive a gradient in the reference (AdaGN.y_shift.*, AttentionBlock.norm.*) are
+excluded statically, so no `find_unused_parameters` machinery is needed.
+"""
+import torch
+
+from . import ops
+from ._lib import B200Error, call, ptr, stream
+from .engine import UNetEngine
+
+
+def _is_dead(name):
+    return ".y_shift." in name or (".attn_layers." in name and ".norm." in name)
+
+
+class GradLayout:
+    """Flat fp32 gradient buffer in bucket order: AdaGN scale weights, AdaGN scale biases (each contiguous so the
+    batched scale-vector GEMM writes them in place), then every other live parameter in reverse execution order
+    (out_layers -> up -> middle -> down -> in_layer -> embedding), the order in which backward completes them."""
+
+    def __init__(self, net, device):
+        from models.custom_layers import AdaGN
+        named = [(n, p) for n, p in net.named_parameters() if not _is_dead(n) and p.requires_grad]
+        adagn = [m for m in net.modules() if isinstance(m, AdaGN)]
+        ys_w = [m.y_scale.weight for m in adagn]
+        ys_b = [m.y_scale.bias for m in adagn]
+        special = {id(p) for p in ys_w + ys_b}
+
+        def order_key(item):
+            n = item[0]
+            if n.startswith("out_layers"):
+                return (0, 0)
+            if n.startswith("up_layers"):
+                return (1, -int(n.split(".")[1]))
+            if n.startswith("middle_layer"):
+                return (2, 0)
+            if n.startswith("down_layers"):
+                return (3, -int(n.split(".")[1]))
+            if n.startswith("in_layer"):
+                return (4, 0)
+            return (5, 0)
+
+        rest = sorted([it for it in named if id(it[1]) not in special], key=order_key)
+        self.params = ys_w + ys_b + [p for _, p in rest]
+        self.offsets, off = {}, 0
+        for p in self.params:
+            self.offsets[id(p)] = off
+            off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.total = off
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.views = {id(p): self.flat[self.offsets[id(p)]:self.offsets[id(p)] + p.numel()].view(p.shape) for p in self.params}
+        self.adagn_w_numel = sum(p.numel() for p in ys_w)
+        self.adagn_b_numel = sum(p.numel() for p in ys_b)
+        # y_scale weights have numel % 4 == 0 whenever C % 4 == 0, so the concatenated views are dense
+        self.dense_adagn = all(p.numel() % 4 == 0 for p in ys_w + ys_b)
+
+    def view(self, p):
+        return self.views[id(p)]
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, t, cond, *params):
+        out, tape = engine._forward_tape(x, t, cond)
+        ctx.engine, ctx.tape = engine, tape
+        ctx.n_params = len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.engine._backward_tape(ctx.tape, dout)
+        ctx.tape = None
+        return (None, None, None, None) + (None,) * ctx.n_params      # grads are written into param.grad views directly
+
+
+class UNetTrainEngine(UNetEngine):
+    def __init__(self, net):
+        super().__init__(net)
+        self.layout = None
+        self.post_backward = None          # optional callable(layout) -> e.g. the data-parallel all-reduce
+
+    # ------------------------------------------------------------------------------------------ public
+    def forward_train(self, x, t=None, cond=None):
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        return _UNetFn.apply(self, x, t, cond, *params)
+
+    def grad_layout(self, device):
+        if self.layout is None or self.layout.flat.device != device:
+            self.layout = GradLayout(self.net, device)
+        return self.layout
+
+    # ------------------------------------------------------------------------------------------ forward with tape
+    @torch.no_grad()
+    def _forward_tape(self, x, t, cond):
+        net = self.net
+        if not x.is_cuda:
+            raise B200Error("U_Net.forward needs CUDA tensors: this build has no CPU path")
+        code = self._code()
+        n, cin, hgt, wid = x.shape
+        levels = len(net.down_layers)
+        if hgt % (1 << levels) or wid % (1 << levels):
+            raise B200Error(f"H and W must be divisible by 2**num_layers = {1 << levels}")
+        dev = x.device
+        tape = []
+        ctx = {"emb": None, "stats_i": 0, "tape": tape, "n": n}
+        if net.cond_emb is None:
+            raise B200Error("training needs the timestep embedding (time_dim is not None)")
+        if net.cond_emb is not None:
+            if t is None:
+                raise B200Error("timestep tensor `t` is required")
+            emb, emb_rec = self._embedding_train(t.to(dev), cond.to(dev) if cond is not None else None)
+            w_all, b_all, off, total = self._adagn_table()
+            be = emb.shape[0]
+            if be not in (1, n):
+                raise B200Error(f"embedding batch {be} does not broadcast over image batch {n}")
+            s_all = torch.empty((be, total), dtype=torch.float32, device=dev)
+            ops.small_gemm(emb, w_all, be, total, emb.shape[1], emb.shape[1], w_all.shape[1], s_all, total, bias=b_all)
+            mods = self._adagn_modules()
+            max_groups = max(m.group_norm.num_groups for m in mods)
+            ctx.update(emb=emb, s_all=s_all, adagn_off=off, s_bstride=(total if be == n else 0), be=be, total=total,
+                       stats=torch.zeros((len(off), n, max_groups, 2), dtype=torch.float32, device=dev),
+                       ds_all=torch.zeros((be, total), dtype=torch.float32, device=dev))
+            tape.append(("emb", emb_rec, ctx))
+        kal = ops.K_ALIGN[code]
+        cpad = ((cin + kal - 1) // kal) * kal
+        h = ops.nchw_to_nhwc_pad(x, cpad, code)
+        h = self._plain_conv_train(net.in_layer[0], h, ctx, need_dx=False)
+        h = self._plain_conv_train(net.in_layer[1], h, ctx)
+        cats = []
+        hh, ww = hgt, wid
+        for blk in net.down_layers:
+            cout = blk.out_layer.conv_layer[0].weight.shape[0]
+            hh, ww = hh // 2, ww // 2
+            cat = ops.new_act(n, hh, ww, 2 * cout, code, dev)
+            h = self._block_train(blk, h, ctx, out=cat[..., cout:])
+            tape.append(("skip_out", len(cats)))             # its gradient also arrives through the concat buffer
+            cats.append(cat)
+        h = self._plain_conv_train(net.middle_layer[0], h, ctx)
+        c_mid = cats[-1].shape[3] // 2
+        self._plain_conv_train(net.middle_layer[1], h, ctx, out=cats[-1][..., :c_mid])
+        n_up = len(net.up_layers)
+        for i, blk in enumerate(net.up_layers):
+            level = len(cats) - 1
+            cat = cats.pop()
+            cout = blk.out_layer.conv_layer[0].weight.shape[1]
+            dst = cats[-1][..., :cout] if i + 1 < n_up else None
+            tape.append(("cat_in", level, cat.shape[3] // 2))   # splits d(cat) into d(x part) and d(skip part)
+            h = self._block_train(blk, cat, ctx, out=dst)
+        h = self._plain_conv_train(net.out_layers[0], h, ctx)
+        last = net.out_layers[1]
+        conv = last.conv_layer[0]
+        c_out = conv.weight.shape[0]
+        y = torch.empty((n, c_out, hgt, wid), dtype=torch.float32, device=dev)
+        w = self.cache.get(conv.weight, 0, code, c_out, conv.weight.shape[1], h.shape[3])
+        ops.conv2d(0, h, w, conv.bias, c_out, act=(2 if net.image_recon else 0), out_nchw_fp32=y)
+        tape.append(("last", last, h, y if net.image_recon else None))
+        return y, tape
+
+    def _embedding_train(self, t, cond):
+        ce = self.net.cond_emb
+        dim = ce.time_dim
+        t = t.to(torch.int64).contiguous()
+        bt = t.shape[0]
+        sin = torch.empty((bt, dim), dtype=torch.float32, device=t.device)
+        call("b2_sinusoid_embedding", ptr(t), ptr(sin), bt, dim, stream())
+
+        def mlp(seq, x0, b, d_in):
+            lins = [seq[0], seq[2], seq[4], seq[6]]
+            acts, pres, h, k = [x0], [], x0, d_in
+            for i, lin in enumerate(lins):
+                nn_ = lin.weight.shape[0]
+                pre = torch.empty((b, nn_), dtype=torch.float32, device=x0.device)
+                ops.small_gemm(h, lin.weight, b, nn_, k, k, lin.weight.shape[1], pre, nn_, bias=lin.bias)
+                if i < 3:
+                    hn = torch.empty_like(pre)
+                    call("b2_f32_act", 0, None, ptr(pre), ptr(hn), pre.numel(), stream())
+                    pres.append(pre)
+                    acts.append(hn)
+                    h = hn
+                else:
+                    h = pre
+                k = nn_
+            return h, (lins, acts, pres)
+
+        emb, rec_t = mlp(ce.time_layer, sin, bt, dim)
+        rec_c = None
+        if ce.cond_layer is not None:
+            if cond is None:
+                raise B200Error("this U_Net was built with cond_dim: `cond` is required")
+            c2 = cond.float().reshape(-1, cond.shape[-1]).contiguous()
+            cemb, rec_c = mlp(ce.cond_layer, c2, c2.shape[0], c2.shape[1])
+            emb = emb + cemb if cemb.shape[0] != emb.shape[0] else emb.add_(cemb)
+        return emb, (rec_t, rec_c, bt)
+
+    def _plain_conv_train(self, blk, x, ctx, out=None, need_dx=True):
+        """Conv + bias + Swish without normalisation (in/middle/out layers): keeps the pre-activation for backward."""
+        conv = blk.conv_layer[0]
+        code = ops.code_of(x)
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        w = self.cache.get(conv.weight, 0, code, cout, cin, x.shape[3])
+        z = ops.conv2d(0, x, w, conv.bias, cout, act=0)
+        n, hh, ww, _ = z.shape
+        if out is None:
+            out = ops.new_act(n, hh, ww, cout, code, x.device)
+        ops.act(0, None, z, out, None, n * hh * ww, cout, 0, z.stride(2), out.stride(2), code)
+        ctx["tape"].append(("plain", blk, x, z, need_dx))
+        return out
+
+    def _gn_conv_train(self, blk, x, ctx, out=None, residual=None):
+        conv = blk.conv_layer[0]
+        code = ops.code_of(x)
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        w = self.cache.get(conv.weight, 0, code, cout, cin, x.shape[3])
+        gn = blk.adagn.group_norm
+        idx = ctx["stats_i"]
+        ctx["stats_i"] += 1
+        stats = ctx["stats"][idx]
+        z = ops.conv2d(0, x, w, conv.bias, cout, act=3, gn_stats=stats, groups=gn.num_groups)
+        off = ctx["adagn_off"][id(blk.adagn)]
+        s = ctx["s_all"][:, off:off + cout]
+        y = ops.adagn_apply(z, stats, gn.weight, gn.bias, s, ctx["s_bstride"], out=out, residual=residual,
+                            groups=gn.num_groups, eps=gn.eps, pre_swish=True)
+        return y, (blk, x, z, stats, off)
+
+    def _block_train(self, blk, x, ctx, out):
+        from models.custom_layers import AttentionBlock, UpsampleBlock
+        tape = ctx["tape"]
+        for res, attn in zip(blk.res_layers, blk.attn_layers):
+            a1, rec1 = self._gn_conv_train(res.conv_block_1, x, ctx)
+            y, rec2 = self._gn_conv_train(res.conv_block_2, a1, ctx, residual=x)
+            tape.append(("res", rec1, rec2))
+            x = y
+            if isinstance(attn, AttentionBlock):
+                x = self._attention_train(attn, x, tape)
+        code = ops.code_of(x)
+        conv = blk.out_layer.conv_layer[0]
+        n, hh, ww, _ = x.shape
+        if isinstance(blk.out_layer, UpsampleBlock):
+            cin, cout = conv.weight.shape[0], conv.weight.shape[1]
+            w = self.cache.get(conv.weight, 2, code, cout, cin, cin)
+            z = ops.conv2d(2, x, w, conv.bias, cout, act=0)
+            if out is None:
+                out = ops.new_act(n, 2 * hh, 2 * ww, cout, code, x.device)
+            ops.act(0, None, z, out, None, n * 4 * hh * ww, cout, 0, z.stride(2), out.stride(2), code)
+            tape.append(("up", blk.out_layer, x, z))
+            return out
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        w = self.cache.get(conv.weight, 0, code, cout, cin, cin)
+        planes = ops.space_to_depth2(x)
+        z = ops.conv2d(1, planes, w, conv.bias, cout, act=0)
+        ops.act(0, None, z, out, None, n * (hh // 2) * (ww // 2), cout, 0, z.stride(2), out.stride(2), code)
+        tape.append(("down", blk.out_layer, planes, z, (n, hh, ww, cin)))
+        return out
+
+    def _attention_train(self, blk, x, tape):
+        saved = {}
+        out = self.attention(blk, x, save=saved)
+        tape.append(("attn", blk, x, saved))
+        return out
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _wgrad_conv(self, mode, conv, x, dz, kind):
+        """Weight gradient in kernel layout -> unpacked into the flat gradient view of the parameter."""
+        code = ops.code_of(x)
+        if mode == 2:
+            cin, cout = conv.weight.shape[0], conv.weight.shape[1]
+            packed = torch.zeros((16 * cout * cin,), dtype=torch.float32, device=x.device)
+            ops.conv2d_wgrad(2, x, dz, cout, packed)
+            call("b2_unpack_weight_grad", 2, ptr(packed), ptr(self.layout.view(conv.weight)), cout, cin, cin, 0, stream())
+            return
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        cin_pad = x.shape[3]
+        packed = torch.zeros((cout * 9 * cin_pad,), dtype=torch.float32, device=x.device)
+        ops.conv2d_wgrad(mode, x, dz, cout, packed)
+        call("b2_unpack_weight_grad", 0, ptr(packed), ptr(self.layout.view(conv.weight)), cout, cin, cin_pad, 0, stream())
+
+    def _dgrad_s1(self, conv, dz, residual=None, out=None):
+        code = ops.code_of(dz)
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        w = self.cache.get(conv.weight, 1, code, cout, cin, dz.shape[3])
+        return ops.conv2d(0, dz, w, None, cin, act=0, residual=residual, out=out)
+
+    def _bwd_gn_conv(self, rec, dout, ctx, residual=None, need_dx=True):
+        blk, x, z, stats, off = rec
+        conv, gn = blk.conv_layer[0], blk.adagn.group_norm
+        code = ops.code_of(z)
+        n, hh, ww, c = z.shape
+        lay = self.layout
+        work = torch.empty((2 * n * c + 2 * n * gn.num_groups,), dtype=torch.float32, device=z.device)
+        dz = torch.empty((n, hh, ww, c), dtype=z.dtype, device=z.device)
+        s = ctx["s_all"][:, off:off + c]
+        ds = ctx["ds_all"][:, off:off + c]
+        call("b2_adagn_bwd", ptr(dout), dout.stride(2), ptr(z), z.stride(2), ptr(stats), ptr(gn.weight), ptr(gn.bias), ptr(s),
+             ctx["s_bstride"], ptr(work), ptr(ds), ctx["total"] if ctx["be"] == n else 0, ptr(lay.view(gn.weight)),
+             ptr(lay.view(gn.bias)), ptr(dz), dz.stride(2), ptr(lay.view(conv.bias)), n, hh * ww, c, gn.num_groups,
+             float(gn.eps), code, stream())
+        self._wgrad_conv(0, conv, x, dz, 0)
+        if not need_dx:
+            return None
+        return self._dgrad_s1(conv, dz, residual=residual)
+
+    def _bwd_act(self, dy, z, dbias_view):
+        code = ops.code_of(z)
+        n, hh, ww, c = z.shape
+        dz = torch.empty((n, hh, ww, c), dtype=z.dtype, device=z.device)
+        ops.act(1, dy, z, dz, dbias_view, n * hh * ww, c, dy.stride(2), z.stride(2), c, code)
+        return dz
+
+    @torch.no_grad()
+    def _backward_tape(self, tape, dout):
+        net = self.net
+        dev = dout.device
+        lay = self.grad_layout(dev)
+        lay.flat.zero_()
+        code = self._code()
+        kal = ops.K_ALIGN[code]
+        ctx = None
+        for entry in tape:
+            if entry[0] == "emb":
+                ctx = entry[2]
+        d = None                     # running gradient w.r.t. the current activation (NHWC, compute dtype)
+        d_skips = {}                 # level -> gradient arriving at a skip tensor through the concat buffer
+        for entry in reversed(tape):
+            kind = entry[0]
+            if kind == "last":
+                _, blk, h_in, y_tanh = entry
+                conv = blk.conv_layer[0]
+                g = dout.contiguous().float()
+                if y_tanh is not None:
+                    g2 = torch.empty_like(g)
+                    call("b2_f32_act", 2, ptr(g), ptr(y_tanh), ptr(g2), g.numel(), stream())
+                    g = g2
+                c_out = conv.weight.shape[0]
+                cp = ((c_out + kal - 1) // kal) * kal
+                dz = ops.nchw_to_nhwc_pad(g, cp, code)
+                n, hh, ww, _ = dz.shape
+                dbias = torch.zeros((cp,), dtype=torch.float32, device=dev)
+                ops.act(2, dz, None, None, dbias, n * hh * ww, cp, cp, 0, 0, code)
+                lay.view(conv.bias).copy_(dbias[:c_out])
+                self._wgrad_conv(0, conv, h_in, dz, 0)
+                d = self._dgrad_s1(conv, dz)
+            elif kind == "plain":
+                _, blk, x_in, z, need_dx = entry
+                conv = blk.conv_layer[0]
+                dz = self._bwd_act(d, z, lay.view(conv.bias))
+                self._wgrad_conv(0, conv, x_in, dz, 0)
+                d = self._dgrad_s1(conv, dz) if need_dx else None
+            elif kind == "up":
+                _, layer, x_in, z = entry
+                conv = layer.conv_layer[0]
+                dz = self._bwd_act(d, z, lay.view(conv.bias))
+                self._wgrad_conv(2, conv, x_in, dz, 2)
+                cin, cout = conv.weight.shape[0], conv.weight.shape[1]
+                w = self.cache.get(conv.weight, 6, code, cout, cin, cout)
+                d = ops.conv2d(4, ops.space_to_depth2(dz), w, None, cin, act=0)
+            elif kind == "down":
+                _, layer, planes, z, in_shape = entry
+                conv = layer.conv_layer[0]
+                dz = self._bwd_act(d, z, lay.view(conv.bias))
+                self._wgrad_conv(1, conv, planes, dz, 0)
+                cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+                w = self.cache.get(conv.weight, 5, code, cout, cin, cout)
+                d = ops.conv2d(3, dz, w, None, cin, act=0)
+            elif kind == "skip_out":
+                level = entry[1]
+                extra = d_skips.pop(level)
+                merged = torch.empty(d.shape, dtype=d.dtype, device=dev)
+                ops.add(d, extra, merged)
+                d = merged
+            elif kind == "cat_in":
+                _, level, c_half = entry
+                d_skips[level] = d[..., c_half:]
+                d = d[..., :c_half]
+            elif kind == "res":
+                _, rec1, rec2 = entry
+                da1 = self._bwd_gn_conv(rec2, d, ctx)
+                d = self._bwd_gn_conv(rec1, da1, ctx, residual=d)
+            elif kind == "attn":
+                _, blk, x_in, saved = entry
+                d = self._bwd_attention(blk, x_in, saved, d)
+            elif kind == "emb":
+                self._bwd_embedding(entry[1], ctx)
+        for p in lay.params:
+            v = lay.view(p)
+            if p.grad is None or p.grad.data_ptr() == v.data_ptr():
+                p.grad = v
+            else:
+                p.grad.add_(v)
+        if self.post_backward is not None:
+            self.post_backward(lay)
+
+    def _bwd_attention(self, blk, x, saved, dout):
+        code = ops.code_of(x)
+        n, hh, ww, c = x.shape
+        ldx = x.stride(2)
+        p_len, heads, d = hh * ww, blk.heads, blk.d_k
+        hd, ldq = heads * d, 3 * heads * d
+        rows = n * p_len
+        dt, dev = x.dtype, x.device
+        lay = self.layout
+        qkv, pm, o, ldp = saved["qkv"], saved["pm"], saved["o"], saved["ldp"]
+        ldd = dout.stride(2)
+        # output projection: out = o Wo^T + bo + x
+        ops.act(2, dout, None, None, lay.view(blk.output.bias), rows, c, ldd, 0, 0, code)
+        ops.gemm_tn(dout, o, c, hd, rows, ldd, hd, lay.view(blk.output.weight), hd, code=code)
+        wo_t = self.cache.get(blk.output.weight, 4, code, c, hd, c)               # [hd][C]
+        d_o = torch.empty((rows, hd), dtype=dt, device=dev)
+        ops.gemm_nt(dout, wo_t, rows, hd, c, ldd, c, d_o, hd)
+        dqkv = torch.empty((rows, ldq), dtype=dt, device=dev)
+        # dP = dO V^T (fp32), dV = P^T dO
+        dp = torch.empty((n, heads, p_len, p_len), dtype=torch.float32, device=dev)
+        ops.gemm_nt(d_o, qkv[:, 2 * d:], p_len, p_len, d, hd, ldq, dp, p_len, out_fp32=True, batch=(heads, n),
+                    a_strides=(d, p_len * hd), b_strides=(3 * d, p_len * ldq), c_strides=(p_len * p_len, heads * p_len * p_len))
+        ops.gemm_tn(pm, d_o, p_len, d, p_len, ldp, hd, dqkv[:, 2 * d:], ldq, out_mode=1, batch=(heads, n),
+                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(d, p_len * hd), c_strides=(3 * d, p_len * ldq))
+        ds = torch.empty((n, heads, p_len, ldp), dtype=dt, device=dev)
+        call("b2_softmax_query_axis_bwd", ptr(pm), ptr(dp), ptr(ds), n * heads, p_len, p_len, ldp, float(blk.scale), code, stream())
+        # dQ = dS K (needs K^T as the NT operand), dK = dS^T Q
+        kt = torch.empty((n, heads, d, ldp), dtype=dt, device=dev)
+        call("b2_transpose_batched", ptr(qkv[:, d:]), ldq, 3 * d, p_len * ldq, ptr(kt), ldp, d * ldp, heads * d * ldp,
+             p_len, d, heads, n, code, stream())
+        ops.gemm_nt(ds, kt, p_len, d, p_len, ldp, ldp, dqkv, ldq, batch=(heads, n),
+                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(d * ldp, heads * d * ldp), c_strides=(3 * d, p_len * ldq))
+        ops.gemm_tn(ds, qkv, p_len, d, p_len, ldp, ldq, dqkv[:, d:], ldq, out_mode=1, batch=(heads, n),
+                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(3 * d, p_len * ldq), c_strides=(3 * d, p_len * ldq))
+        # input projection: qkv = x Wp^T + bp
+        ops.act(2, dqkv, None, None, lay.view(blk.projection.bias), rows, ldq, ldq, 0, 0, code)
+        ops.gemm_tn(dqkv, x, ldq, c, rows, ldq, ldx, lay.view(blk.projection.weight), c, code=code)
+        wp_t = self.cache.get(blk.projection.weight, 4, code, ldq, c, ldq)          # [C][3hd]
+        dx = torch.empty((n, hh, ww, c), dtype=dt, device=dev)
+        ops.gemm_nt(dqkv, wp_t, rows, c, ldq, ldq, ldq, dx, c, residual=dout, ldr=ldd)
+        return dx
+
+    def _bwd_embedding(self, rec, ctx):
+        (rec_t, rec_c, bt) = rec
+        lay = self.layout
+        emb, ds_all, total, be = ctx["emb"], ctx["ds_all"], ctx["total"], ctx["be"]
+        w_all, b_all, off, _ = self._adagn_table()
+        dim = emb.shape[1]
+        mods = self._adagn_modules()
+        dev = emb.device
+        # gradients of all AdaGN scale Linears in one shot: dW_all = ds_all^T emb, db_all = colsum(ds_all)
+        if lay.dense_adagn:
+            dw_all = lay.flat[:lay.adagn_w_numel].view(total, dim)
+            db_all = lay.flat[lay.adagn_w_numel:lay.adagn_w_numel + lay.adagn_b_numel]
+        else:
+            dw_all = torch.zeros((total, dim), dtype=torch.float32, device=dev)
+            db_all = torch.zeros((total,), dtype=torch.float32, device=dev)
+        ops.small_gemm(ds_all, emb, total, dim, be, total, dim, dw_all, dim, ta=1, tb=1, accumulate=True)
+        db_all.add_(ds_all.sum(dim=0)) if be > 1 else db_all.add_(ds_all[0])
+        if not lay.dense_adagn:
+            o = 0
+            for m in mods:
+                cch = m.y_scale.weight.shape[0]
+                lay.view(m.y_scale.weight).copy_(dw_all[o:o + cch])
+                lay.view(m.y_scale.bias).copy_(db_all[o:o + cch])
+                o += cch
+        demb = torch.empty((be, dim), dtype=torch.float32, device=dev)
+        ops.small_gemm(ds_all, w_all, be, dim, total, total, dim, demb, dim, tb=1)
+
+        def mlp_bwd(rec_m, dy):
+            lins, acts, pres = rec_m
+            b = dy.shape[0]
+            for i in (3, 2, 1, 0):
+                lin, h_in = lins[i], acts[i]
+                n_out, n_in = lin.weight.shape
+                ops.small_gemm(dy, h_in, n_out, n_in, b, n_out, n_in, lay.view(lin.weight), n_in, ta=1, tb=1, accumulate=True)
+                lay.view(lin.bias).add_(dy.sum(dim=0))
+                if i == 0:
+                    break
+                dh = torch.empty((b, n_in), dtype=torch.float32, device=dev)
+                ops.small_gemm(dy, lin.weight, b, n_in, n_out, n_out, n_in, dh, n_in, tb=1)
+                dpre = torch.empty_like(dh)
+                call("b2_f32_act", 1, ptr(dh), ptr(pres[i - 1]), ptr(dpre), dh.numel(), stream())
+                dy = dpre
+
+        mlp_bwd(rec_t, demb if demb.shape[0] == bt else demb.sum(dim=0, keepdim=True))
+        if rec_c is not None:
+            bc = rec_c[1][0].shape[0]
+            mlp_bwd(rec_c, demb if demb.shape[0] == bc else demb.sum(dim=0, keepdim=True))

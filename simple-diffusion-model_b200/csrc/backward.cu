@@ -1,0 +1,361 @@
+// Memory-bound kernels of the backward pass (the reference gets these from autograd): GroupNorm x AdaGN backward
+// (two streaming passes + a tiny per-image finalize), Swish / tanh backward with fused bias gradients, query-axis
+// softmax backward, column sums, and the kernel-layout -> parameter-layout gradient unpack.
+#include "host_util.h"
+#include "ptx.cuh"
+#include "sdm_b200.h"
+
+using namespace b2;
+typedef __nv_bfloat16 bf16;
+
+#define LAUNCH_CHECK(name)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = cudaGetLastError();                                                      \
+        if (e_ != cudaSuccess) return set_error(name ": %s", cudaGetErrorString(e_));             \
+        return 0;                                                                                 \
+    } while (0)
+
+template <typename T> struct V16 { static constexpr int N = 16 / sizeof(T); };
+template <typename T>
+__device__ __forceinline__ void ld16(const T* p, float (&f)[V16<T>::N]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    if constexpr (sizeof(T) == 4) {
+        f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+    } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void st16(T* p, const float (&f)[V16<T>::N]) {
+    uint4 u;
+    if constexpr (sizeof(T) == 4) {
+        u.x = __float_as_uint(round_tf32(f[0])); u.y = __float_as_uint(round_tf32(f[1]));
+        u.z = __float_as_uint(round_tf32(f[2])); u.w = __float_as_uint(round_tf32(f[3]));
+    } else {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float swish_grad(float z) { const float s = sigmoidf_(z); return s * (1.0f + z * (1.0f - s)); }
+
+// Launch shape shared by the streaming passes: each thread owns one 16-byte channel vector for the whole kernel
+// (so per-channel partial sums live in registers) and strides over the pixels of one slab of one image.
+struct SlabLaunch { int threads, rows_per_block, slabs; };
+static SlabLaunch slab_launch(int N, int HW, int cv) {
+    SlabLaunch s;
+    int k = 256 / cv; if (k < 1) k = 1;
+    s.threads = cv * k;
+    s.rows_per_block = k;
+    int slabs = (4 * device_sm_count() + N - 1) / N;
+    const int max_slabs = (HW + 4 * k - 1) / (4 * k);
+    if (slabs > max_slabs) slabs = max_slabs;
+    s.slabs = slabs < 1 ? 1 : slabs;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ AdaGN backward
+// Forward (custom_layers.py:35-45, :240-245): y = swish(z); xh = (y - mean) * rstd; out = s*(gamma*xh + beta) + s.
+// Pass 1: a1[n][c] = sum_p dout, a2[n][c] = sum_p dout * xh.
+template <typename T>
+__global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
+                                        const float* __restrict__ stats, float* __restrict__ a1, float* __restrict__ a2,
+                                        int HW, int C, int groups, float eps, int slabs, int rows_per_block) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
+    const int cpg = C / groups;
+    const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
+    float mean[V], rstd[V], s1[V], s2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int g = (c0 + j) / cpg;
+        const float m = stats[((long long)n * groups + g) * 2] * inv_cnt;
+        const float var = fmaxf(stats[((long long)n * groups + g) * 2 + 1] * inv_cnt - m * m, 0.f);
+        mean[j] = m; rstd[j] = rsqrtf(var + eps); s1[j] = 0.f; s2[j] = 0.f;
+    }
+    const int p_per = (HW + slabs - 1) / slabs;
+    const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
+    const long long base = (long long)n * HW;
+    for (int p = p0 + prow; p < p1; p += rows_per_block) {
+        float d[V], zz[V];
+        ld16<T>(dout + (base + p) * ldd + c0, d);
+        ld16<T>(z + (base + p) * ldz + c0, zz);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float xh = (swishf(zz[j]) - mean[j]) * rstd[j];
+            s1[j] += d[j]; s2[j] = fmaf(d[j], xh, s2[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        atomicAdd(a1 + (long long)n * C + c0 + j, s1[j]);
+        atomicAdd(a2 + (long long)n * C + c0 + j, s2[j]);
+    }
+}
+
+// Finalize (one CTA per image): ds[n][c] += gamma*a2 + (beta+1)*a1; dgamma[c] += s*a2; dbeta[c] += s*a1;
+// m[n][g] = (sum_{c in g} s*gamma*a1, sum_{c in g} s*gamma*a2) / (cpg*HW).
+__global__ void adagn_bwd_finalize_kernel(const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ s,
+                                          long long s_bstride, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          float* __restrict__ ds, long long ds_bstride, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta, float* __restrict__ m12, int HW, int C, int groups) {
+    extern __shared__ float gs[];      // [groups][2]
+    const int n = blockIdx.x;
+    const int cpg = C / groups;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gs[i] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float x1 = a1[(long long)n * C + c], x2 = a2[(long long)n * C + c];
+        const float sc = s[(long long)n * s_bstride + c], ga = gamma[c];
+        atomicAdd(ds + (long long)n * ds_bstride + c, ga * x2 + (beta[c] + 1.0f) * x1);
+        atomicAdd(dgamma + c, sc * x2);
+        atomicAdd(dbeta + c, sc * x1);
+        atomicAdd(&gs[(c / cpg) * 2], sc * ga * x1);
+        atomicAdd(&gs[(c / cpg) * 2 + 1], sc * ga * x2);
+    }
+    __syncthreads();
+    const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) m12[(long long)n * groups * 2 + i] = gs[i] * inv_cnt;
+}
+
+// Pass 2: dz = rstd * (s*gamma*dout - m1 - xh*m2) * swish'(z);  dbias[c] += sum dz.
+template <typename T>
+__global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
+                                       const float* __restrict__ stats, const float* __restrict__ m12,
+                                       const float* __restrict__ s, long long s_bstride, const float* __restrict__ gamma,
+                                       T* __restrict__ dz, long long lddz, float* __restrict__ dbias, int HW, int C,
+                                       int groups, float eps, int slabs, int rows_per_block) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
+    const int cpg = C / groups;
+    const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
+    float mean[V], rstd[V], sg[V], m1[V], m2[V], db[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = c0 + j, g = c / cpg;
+        const float m = stats[((long long)n * groups + g) * 2] * inv_cnt;
+        const float var = fmaxf(stats[((long long)n * groups + g) * 2 + 1] * inv_cnt - m * m, 0.f);
+        mean[j] = m; rstd[j] = rsqrtf(var + eps);
+        sg[j] = s[(long long)n * s_bstride + c] * gamma[c];
+        m1[j] = m12[((long long)n * groups + g) * 2]; m2[j] = m12[((long long)n * groups + g) * 2 + 1];
+        db[j] = 0.f;
+    }
+    const int p_per = (HW + slabs - 1) / slabs;
+    const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
+    const long long base = (long long)n * HW;
+    for (int p = p0 + prow; p < p1; p += rows_per_block) {
+        float d[V], zz[V], o[V];
+        ld16<T>(dout + (base + p) * ldd + c0, d);
+        ld16<T>(z + (base + p) * ldz + c0, zz);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float xh = (swishf(zz[j]) - mean[j]) * rstd[j];
+            const float dy = rstd[j] * (sg[j] * d[j] - m1[j] - xh * m2[j]);
+            o[j] = dy * swish_grad(zz[j]);
+            db[j] += o[j];
+        }
+        st16<T>(dz + (base + p) * lddz + c0, o);
+    }
+    if (dbias) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) atomicAdd(dbias + c0 + j, db[j]);
+    }
+}
+
+extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
+                            const float* gamma, const float* beta, const float* s, long long s_bstride, float* work,
+                            float* ds, long long ds_bstride, float* dgamma, float* dbeta, void* dz, long long lddz,
+                            float* dbias, int N, int HW, int C, int groups, float eps, int dtype, void* stream) {
+    const int V = dtype == 0 ? 8 : 4;
+    if (C % V || ldd % V || ldz % V || lddz % V) return set_error("b2_adagn_bwd: channel counts / strides must be 16-byte aligned");
+    if (C % groups) return set_error("b2_adagn_bwd: C %% groups != 0");
+    const int cv = C / V;
+    if (cv > 1024) return set_error("b2_adagn_bwd: C too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    // work: [2][N][C] (a1, a2) + [N][groups][2] (m1, m2), all fp32
+    float* a1 = work;
+    float* a2 = work + (long long)N * C;
+    float* m12 = work + 2LL * N * C;
+    cudaError_t e = cudaMemsetAsync(work, 0, 2LL * N * C * sizeof(float), st);
+    if (e != cudaSuccess) return set_error("b2_adagn_bwd: memset: %s", cudaGetErrorString(e));
+    const SlabLaunch sl = slab_launch(N, HW, cv);
+    if (dtype == 0)
+        adagn_bwd_reduce_kernel<bf16><<<N * sl.slabs, sl.threads, 0, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+    else
+        adagn_bwd_reduce_kernel<float><<<N * sl.slabs, sl.threads, 0, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+    adagn_bwd_finalize_kernel<<<N, 256, groups * 2 * sizeof(float), st>>>(a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, m12, HW, C, groups);
+    if (dtype == 0)
+        adagn_bwd_apply_kernel<bf16><<<N * sl.slabs, sl.threads, 0, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, m12, s, s_bstride, gamma, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+    else
+        adagn_bwd_apply_kernel<float><<<N * sl.slabs, sl.threads, 0, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, m12, s, s_bstride, gamma, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+    LAUNCH_CHECK("b2_adagn_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ activation fwd/bwd
+// mode 0: y = swish(z) (training forward of the un-normalised convs keeps z); mode 1: dz = dy * swish'(z), dbias += sum dz;
+// mode 2: dz = dy (identity), dbias += sum dz (last conv / Linear bias gradients).
+template <typename T>
+__global__ void act_kernel(int mode, const T* __restrict__ a, long long lda, const T* __restrict__ z, long long ldz,
+                           T* __restrict__ out, long long ldo, float* __restrict__ dbias, long long rows, int C,
+                           int rows_per_block) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
+    float db[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) db[j] = 0.f;
+    for (long long r = (long long)blockIdx.x * rows_per_block + prow; r < rows; r += (long long)gridDim.x * rows_per_block) {
+        float x[V], o[V];
+        if (mode == 0) {
+            ld16<T>(z + r * ldz + c0, x);
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] = swishf(x[j]);
+            st16<T>(out + r * ldo + c0, o);
+        } else if (mode == 1) {
+            float zz[V];
+            ld16<T>(a + r * lda + c0, x);
+            ld16<T>(z + r * ldz + c0, zz);
+#pragma unroll
+            for (int j = 0; j < V; ++j) { o[j] = x[j] * swish_grad(zz[j]); db[j] += o[j]; }
+            st16<T>(out + r * ldo + c0, o);
+        } else {
+            ld16<T>(a + r * lda + c0, x);
+#pragma unroll
+            for (int j = 0; j < V; ++j) db[j] += x[j];
+        }
+    }
+    if (dbias && mode != 0) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) atomicAdd(dbias + c0 + j, db[j]);
+    }
+}
+extern "C" int b2_act(int mode, const void* a, long long lda, const void* z, long long ldz, void* out, long long ldo,
+                      float* dbias, long long rows, int C, int dtype, void* stream) {
+    const int V = dtype == 0 ? 8 : 4;
+    if (C % V || (a && lda % V) || (z && ldz % V) || (out && ldo % V)) return set_error("b2_act: channel counts / strides must be 16-byte aligned");
+    const int cv = C / V;
+    if (cv > 1024) return set_error("b2_act: C too large");
+    int k = 256 / cv; if (k < 1) k = 1;
+    long long blocks = (rows + 4LL * k - 1) / (4LL * k);
+    const long long cap = 8LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (dtype == 0) act_kernel<bf16><<<(int)blocks, cv * k, 0, (cudaStream_t)stream>>>(mode, (const bf16*)a, lda, (const bf16*)z, ldz, (bf16*)out, ldo, dbias, rows, C, k);
+    else act_kernel<float><<<(int)blocks, cv * k, 0, (cudaStream_t)stream>>>(mode, (const float*)a, lda, (const float*)z, ldz, (float*)out, ldo, dbias, rows, C, k);
+    LAUNCH_CHECK("b2_act");
+}
+
+// fp32 elementwise helpers for the tiny embedding MLPs: mode 0 y = swish(z); mode 1 dz = dy * swish'(z); mode 2 d *= 1 - y^2 (tanh).
+__global__ void f32_act_kernel(int mode, const float* __restrict__ a, const float* __restrict__ z, float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (mode == 0) out[i] = swishf(z[i]);
+        else if (mode == 1) out[i] = a[i] * swish_grad(z[i]);
+        else out[i] = a[i] * (1.0f - z[i] * z[i]);
+    }
+}
+extern "C" int b2_f32_act(int mode, const float* a, const float* z, float* out, long long n, void* stream) {
+    long long blocks = (n + 255) / 256;
+    const long long cap = 8LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    f32_act_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mode, a, z, out, n);
+    LAUNCH_CHECK("b2_f32_act");
+}
+
+// ------------------------------------------------------------------------------------------------ softmax backward
+// dS[b][i][j] = scale * P[i][j] * (dP[i][j] - sum_i' P[i'][j] dP[i'][j])   (softmax over the query axis i)
+template <typename T>
+__global__ void softmax_query_axis_bwd_kernel(const T* __restrict__ P, const float* __restrict__ dP, T* __restrict__ dS,
+                                              int B, int Pq, int Pk, long long ldp, float scale) {
+    const long long total = (long long)B * Pk;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % Pk);
+        const long long b = idx / Pk;
+        const T* pc = P + b * Pq * ldp + j;
+        const float* dc = dP + b * Pq * Pk + j;
+        float dot = 0.f;
+        for (int i = 0; i < Pq; ++i) dot = fmaf(__ldg(dc + (long long)i * Pk), (float)pc[(long long)i * ldp], dot);
+        T* o = dS + b * Pq * ldp + j;
+        for (int i = 0; i < Pq; ++i) {
+            const float v = scale * (float)pc[(long long)i * ldp] * (__ldg(dc + (long long)i * Pk) - dot);
+            if constexpr (sizeof(T) == 4) o[(long long)i * ldp] = round_tf32(v); else o[(long long)i * ldp] = __float2bfloat16(v);
+        }
+    }
+}
+extern "C" int b2_softmax_query_axis_bwd(const void* P, const float* dP, void* dS, int B, int Pq, int Pk, long long ldp, float scale,
+                                         int dtype, void* stream) {
+    long long blocks = ((long long)B * Pk + 127) / 128;
+    const long long cap = 8LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (dtype == 0) softmax_query_axis_bwd_kernel<bf16><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>((const bf16*)P, dP, (bf16*)dS, B, Pq, Pk, ldp, scale);
+    else softmax_query_axis_bwd_kernel<float><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>((const float*)P, dP, (float*)dS, B, Pq, Pk, ldp, scale);
+    LAUNCH_CHECK("b2_softmax_query_axis_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ gradient unpack
+// kind 0: packed [Cout][9][Cin_pad] -> grad [Cout][Cin][3][3];  kind 2: packed [4][Cout][4][Cin] -> grad [Cin][Cout][4][4].
+__global__ void unpack_weight_grad_kernel(int kind, const float* __restrict__ packed, float* __restrict__ grad, int Cout, int Cin,
+                                          int Cin_pad, int accumulate) {
+    const long long total = kind == 0 ? (long long)Cout * Cin * 9 : (long long)Cin * Cout * 16;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float v;
+        if (kind == 0) {
+            const int tap = (int)(i % 9); const int ci = (int)((i / 9) % Cin); const int co = (int)(i / (9LL * Cin));
+            v = __ldg(packed + ((long long)co * 9 + tap) * Cin_pad + ci);
+        } else {
+            const int kw = (int)(i % 4), kh = (int)((i / 4) % 4); const int co = (int)((i / 16) % Cout); const int ci = (int)(i / (16LL * Cout));
+            const int a = (kh == 1 || kh == 3) ? 0 : 1, ti = (kh == 1 || kh == 2) ? 0 : 1;
+            const int b = (kw == 1 || kw == 3) ? 0 : 1, tj = (kw == 1 || kw == 2) ? 0 : 1;
+            v = __ldg(packed + ((((long long)(a * 2 + b) * Cout + co) * 4) + ti * 2 + tj) * Cin + ci);
+        }
+        grad[i] = accumulate ? grad[i] + v : v;
+    }
+}
+extern "C" int b2_unpack_weight_grad(int kind, const float* packed, float* grad, int Cout, int Cin, int Cin_pad, int accumulate,
+                                     void* stream) {
+    if (kind != 0 && kind != 2) return set_error("b2_unpack_weight_grad: kind must be 0 or 2");
+    const long long total = kind == 0 ? (long long)Cout * Cin * 9 : (long long)Cin * Cout * 16;
+    long long blocks = (total + 255) / 256;
+    const long long cap = 16LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    unpack_weight_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(kind, packed, grad, Cout, Cin, Cin_pad, accumulate);
+    LAUNCH_CHECK("b2_unpack_weight_grad");
+}
+
+// out = a + b on NHWC views (merging the two consumers of a skip tensor in the backward pass).
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, T* __restrict__ out,
+                           long long ldo, long long rows, int cv) {
+    constexpr int V = V16<T>::N;
+    const long long total = rows * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cv; const int c = (int)(i % cv) * V;
+        float x[V], y[V];
+        ld16<T>(a + r * lda + c, x);
+        ld16<T>(b + r * ldb + c, y);
+#pragma unroll
+        for (int j = 0; j < V; ++j) x[j] += y[j];
+        st16<T>(out + r * ldo + c, x);
+    }
+}
+extern "C" int b2_add(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows, int C,
+                      int dtype, void* stream) {
+    const int V = dtype == 0 ? 8 : 4;
+    if (C % V || lda % V || ldb % V || ldo % V) return set_error("b2_add: channel counts / strides must be 16-byte aligned");
+    long long blocks = (rows * (C / V) + 255) / 256;
+    const long long cap = 8LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (dtype == 0) add_kernel<bf16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out, ldo, rows, C / V);
+    else add_kernel<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, (const float*)b, ldb, (float*)out, ldo, rows, C / V);
+    LAUNCH_CHECK("b2_add");
+}

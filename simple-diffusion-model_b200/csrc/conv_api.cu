@@ -40,7 +40,7 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
     const int bk = 128 / eb;
     if (Cin % bk != 0) return set_error("b2_conv2d_nhwc: Cin=%d must be a multiple of %d", Cin, bk);
     if (out_mode != 0 && (mode != 0 || residual)) return set_error("b2_conv2d_nhwc: NCHW fp32 output only for the plain 3x3 conv");
-    if (mode < 0 || mode > 2) return set_error("b2_conv2d_nhwc: bad mode %d", mode);
+    if (mode < 0 || mode > 4) return set_error("b2_conv2d_nhwc: bad mode %d", mode);
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.W = W; p.H = H; p.N = N;
@@ -78,21 +78,39 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         a_images = 4 * N;
         p.oN = (long long)H * W * ldy; p.oH = (long long)W * ldy; p.oW = ldy;
         p.rN = (long long)H * W * ldr; p.rH = (long long)W * ldr; p.rW = ldr;
-    } else {                  // transposed 4x4, stride 2, pad 1; output 2H x 2W; group = output parity (a, b)
+    } else if (mode == 4) {   // data gradient of the transposed 4x4/s2 conv = 4x4/s2 conv over dz: 16 taps on dz's parity planes
+        p.groups = 1; p.taps = 16;
+        for (int kh = 0; kh < 4; ++kh) for (int kw = 0; kw < 4; ++kw) {
+            const int t = kh * 4 + kw;
+            const int pr = (kh == 0 || kh == 2), pc = (kw == 0 || kw == 2);
+            p.tap_dh[t] = kh == 0 ? -1 : (kh == 3 ? 1 : 0);
+            p.tap_dw[t] = kw == 0 ? -1 : (kw == 3 ? 1 : 0);
+            p.tap_dn[t] = (pr * 2 + pc) * N;
+        }
+        a_images = 4 * N;
+        p.oN = (long long)H * W * ldy; p.oH = (long long)W * ldy; p.oW = ldy;
+        p.rN = (long long)H * W * ldr; p.rH = (long long)W * ldr; p.rW = ldr;
+    } else {                  // mode 2: transposed 4x4, stride 2, pad 1; output 2H x 2W; group = output parity (a, b)
+                              // mode 3: data gradient of the 3x3/s2 conv (same addressing; 1-2 real taps per dim, zero-padded weights)
         p.groups = 4; p.taps = 4;
         for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
             const int g = a * 2 + b;
             for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
                 const int t = g * 4 + i * 2 + j;
-                p.tap_dh[t] = (i == 0) ? 0 : (a == 0 ? -1 : 1);
-                p.tap_dw[t] = (j == 0) ? 0 : (b == 0 ? -1 : 1);
+                if (mode == 2) {
+                    p.tap_dh[t] = (i == 0) ? 0 : (a == 0 ? -1 : 1);
+                    p.tap_dw[t] = (j == 0) ? 0 : (b == 0 ? -1 : 1);
+                } else {
+                    p.tap_dh[t] = (i == 1 && a == 1) ? 1 : 0;
+                    p.tap_dw[t] = (j == 1 && b == 1) ? 1 : 0;
+                }
                 p.tap_dn[t] = 0;
             }
             p.goff[g] = ((long long)a * (2 * W) + b) * ldy;
         }
         p.oN = (long long)4 * H * W * ldy; p.oH = (long long)2 * (2 * W) * ldy; p.oW = 2 * ldy;
         p.rN = (long long)4 * H * W * ldr; p.rH = (long long)2 * (2 * W) * ldr; p.rW = 2 * ldr;
-        if (residual) return set_error("b2_conv2d_nhwc: residual not supported for transposed conv");
+        if (residual) return set_error("b2_conv2d_nhwc: residual not supported for the parity-decomposed modes");
     }
     p.oC = 1;
     if (out_mode == 1) {      // final layer: fp32 NCHW straight from the epilogue (ldy ignored)

@@ -133,25 +133,25 @@ template <typename T> __device__ __forceinline__ T pack_val(float v);
 template <> __device__ __forceinline__ bf16 pack_val<bf16>(float v) { return __float2bfloat16(v); }
 template <> __device__ __forceinline__ float pack_val<float>(float v) { return round_tf32(v); }
 
-// kind 0: Conv2d weight [Cout][Cin][3][3] -> [Cout][9][Cin_pad]                     (forward layout)
-// kind 1: Conv2d weight [Cout][Cin][3][3] -> [Cin][9 flipped][Cout]                 (data-gradient layout, stride 1)
-// kind 2: ConvTranspose2d weight [Cin][Cout][4][4] -> [4 parities][Cout][4 taps][Cin]   (forward layout)
-// kind 3: plain cast [rows][cols] -> [rows][cols_pad]                                (Linear weights)
+// Kernel layouts ("K" is the contraction side of the GEMM the weight feeds; k_pad zero-pads it to the 128-byte block):
+// kind 0: Conv2d [Cout][Cin][3][3]          -> [Cout][9][k_pad >= Cin]                  forward (stride 1 and 2)
+// kind 1: Conv2d [Cout][Cin][3][3]          -> [Cin][9 flipped][k_pad >= Cout]          data gradient, stride 1
+// kind 2: ConvTranspose2d [Cin][Cout][4][4] -> [4 parities][Cout][4 taps][Cin]          forward
+// kind 3: Linear [rows=Cout][cols=Cin]      -> [rows][k_pad >= cols]                    forward
+// kind 4: Linear [rows=Cout][cols=Cin]      -> [cols][k_pad >= rows] (transposed)       data gradient
+// kind 5: Conv2d [Cout][Cin][3][3]          -> [4 parities][Cin][4 taps, zero padded][Cout]   data gradient, stride 2
+// kind 6: ConvTranspose2d [Cin][Cout][4][4] -> [Cin][16][Cout]                          data gradient
 template <typename T>
-__global__ void pack_weight_kernel(int kind, const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int Cin_pad) {
-    long long total;
-    if (kind == 0) total = (long long)Cout * 9 * Cin_pad;
-    else if (kind == 1) total = (long long)Cin * 9 * Cout;
-    else if (kind == 2) total = (long long)16 * Cout * Cin;
-    else total = (long long)Cout * Cin_pad;
+__global__ void pack_weight_kernel(int kind, const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int k_pad,
+                                   long long total) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float v;
+        float v = 0.f;
         if (kind == 0) {
-            const int ci = (int)(i % Cin_pad); const int tap = (int)((i / Cin_pad) % 9); const int co = (int)(i / (9LL * Cin_pad));
-            v = ci < Cin ? __ldg(w + ((long long)co * Cin + ci) * 9 + tap) : 0.f;
+            const int ci = (int)(i % k_pad); const int tap = (int)((i / k_pad) % 9); const int co = (int)(i / (9LL * k_pad));
+            if (ci < Cin) v = __ldg(w + ((long long)co * Cin + ci) * 9 + tap);
         } else if (kind == 1) {
-            const int co = (int)(i % Cout); const int tap = (int)((i / Cout) % 9); const int ci = (int)(i / (9LL * Cout));
-            v = __ldg(w + ((long long)co * Cin + ci) * 9 + (8 - tap));
+            const int co = (int)(i % k_pad); const int tap = (int)((i / k_pad) % 9); const int ci = (int)(i / (9LL * k_pad));
+            if (co < Cout) v = __ldg(w + ((long long)co * Cin + ci) * 9 + (8 - tap));
         } else if (kind == 2) {
             const int ci = (int)(i % Cin); long long r = i / Cin;
             const int t = (int)(r % 4); r /= 4;
@@ -160,20 +160,44 @@ __global__ void pack_weight_kernel(int kind, const float* __restrict__ w, T* __r
             const int kh = a == 0 ? (ti == 0 ? 1 : 3) : (ti == 0 ? 2 : 0);
             const int kw = b == 0 ? (tj == 0 ? 1 : 3) : (tj == 0 ? 2 : 0);
             v = __ldg(w + (((long long)ci * Cout + co) * 4 + kh) * 4 + kw);
+        } else if (kind == 3) {
+            const int c = (int)(i % k_pad); const int r = (int)(i / k_pad);
+            if (c < Cin) v = __ldg(w + (long long)r * Cin + c);
+        } else if (kind == 4) {
+            const int r = (int)(i % k_pad); const int c = (int)(i / k_pad);
+            if (r < Cout) v = __ldg(w + (long long)r * Cin + c);
+        } else if (kind == 5) {
+            const int co = (int)(i % Cout); long long r = i / Cout;
+            const int t = (int)(r % 4); r /= 4;
+            const int ci = (int)(r % Cin); const int g = (int)(r / Cin);
+            const int a = g >> 1, b = g & 1, ti = t >> 1, tj = t & 1;
+            const int kh = a == 0 ? (ti == 0 ? 1 : -1) : (ti == 0 ? 2 : 0);
+            const int kw = b == 0 ? (tj == 0 ? 1 : -1) : (tj == 0 ? 2 : 0);
+            if (kh >= 0 && kw >= 0) v = __ldg(w + ((long long)co * Cin + ci) * 9 + kh * 3 + kw);
         } else {
-            const int c = (int)(i % Cin_pad); const int r = (int)(i / Cin_pad);
-            v = c < Cin ? __ldg(w + (long long)r * Cin + c) : 0.f;
+            const int co = (int)(i % Cout); const int t = (int)((i / Cout) % 16); const int ci = (int)(i / (16LL * Cout));
+            v = __ldg(w + ((long long)ci * Cout + co) * 16 + t);
         }
         out[i] = pack_val<T>(v);
     }
 }
-extern "C" int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int Cin_pad, int dtype, void* stream) {
-    if (kind < 0 || kind > 3) return set_error("b2_pack_weight: bad kind");
-    const long long total = kind == 0 ? (long long)Cout * 9 * Cin_pad : kind == 1 ? (long long)Cin * 9 * Cout
-                          : kind == 2 ? (long long)16 * Cout * Cin : (long long)Cout * Cin_pad;
+static long long pack_total(int kind, int Cout, int Cin, int k_pad) {
+    switch (kind) {
+        case 0: return (long long)Cout * 9 * k_pad;
+        case 1: return (long long)Cin * 9 * k_pad;
+        case 2: return 16LL * Cout * Cin;
+        case 3: return (long long)Cout * k_pad;
+        case 4: return (long long)Cin * k_pad;
+        case 5: return 16LL * Cin * Cout;
+        default: return 16LL * Cin * Cout;
+    }
+}
+extern "C" int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int k_pad, int dtype, void* stream) {
+    if (kind < 0 || kind > 6) return set_error("b2_pack_weight: bad kind");
+    const long long total = pack_total(kind, Cout, Cin, k_pad);
     const int g = grid_for(total, 256);
-    if (dtype == 0) pack_weight_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (bf16*)out, Cout, Cin, Cin_pad);
-    else pack_weight_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (float*)out, Cout, Cin, Cin_pad);
+    if (dtype == 0) pack_weight_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (bf16*)out, Cout, Cin, k_pad, total);
+    else pack_weight_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (float*)out, Cout, Cin, k_pad, total);
     LAUNCH_CHECK("b2_pack_weight");
 }
 
@@ -185,7 +209,7 @@ template <typename T>
 __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const float* __restrict__ stats,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ s, long long s_bstride, const T* __restrict__ res, long long ldr,
-                                   T* __restrict__ out, long long ldo, int HW, int C, int groups, float eps, int slabs) {
+                                   T* __restrict__ out, long long ldo, int HW, int C, int groups, float eps, int slabs, int pre_swish) {
     extern __shared__ float sm[];
     float* fa = sm;
     float* fb = sm + C;
@@ -213,6 +237,10 @@ __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const
         const int p = i / cv, c = (i % cv) * V;
         float v[V];
         load16<T>(y + (base + p) * ldy + c, v);
+        if (pre_swish) {        // training: the conv stored its pre-activation z; Swish is applied here on the fly
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = swishf(v[j]);
+        }
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], fa[c + j], fb[c + j]);
         if (res) {
@@ -226,7 +254,7 @@ __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const
 }
 extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, const float* gamma, const float* beta,
                               const float* s, long long s_bstride, const void* residual, long long ldr, void* out,
-                              long long ldo, int N, int HW, int C, int groups, float eps, int dtype, void* stream) {
+                              long long ldo, int N, int HW, int C, int groups, float eps, int pre_swish, int dtype, void* stream) {
     const int V = dtype == 0 ? 8 : 4;
     if (C % V || ldy % V || ldo % V || (residual && ldr % V)) return set_error("b2_adagn_apply: channel counts / strides must be 16-byte aligned");
     if (C % groups) return set_error("b2_adagn_apply: C %% groups != 0");
@@ -238,10 +266,10 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
     const size_t smem = 2 * (size_t)C * sizeof(float);
     if (dtype == 0)
         adagn_apply_kernel<bf16><<<N * slabs, 256, smem, (cudaStream_t)stream>>>((const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
-                                                                                   (const bf16*)residual, ldr, (bf16*)out, ldo, HW, C, groups, eps, slabs);
+                                                                                   (const bf16*)residual, ldr, (bf16*)out, ldo, HW, C, groups, eps, slabs, pre_swish);
     else
         adagn_apply_kernel<float><<<N * slabs, 256, smem, (cudaStream_t)stream>>>((const float*)y, ldy, stats, gamma, beta, s, s_bstride,
-                                                                                    (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs);
+                                                                                    (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs, pre_swish);
     LAUNCH_CHECK("b2_adagn_apply");
 }
 

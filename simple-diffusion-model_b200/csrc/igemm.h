@@ -30,7 +30,7 @@ struct IgemmParams {
     long long rN, rH, rW;
     const float* bias;           // optional [Cout]
     float alpha;                 // acc *= alpha before bias
-    int act;                     // 0 none, 1 swish, 2 tanh
+    int act;                     // 0 none, 1 swish, 2 tanh, 3 none but GN stats of swish(value)
     float* gn_stats;             // optional [N][Cout/cpg][2] (sum, sum of squares), accumulated atomically
     int cpg;                     // channels per GroupNorm group
 };

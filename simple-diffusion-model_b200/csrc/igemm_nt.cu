@@ -235,10 +235,20 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (p.gn_stats && ncols == 32) {
                     float* srow = p.gn_stats + static_cast<long long>(uniform ? n_lane0 : (valid ? n : 0)) * G * 2;
                     const int cpg = p.cpg;
-                    if (cpg >= 32)      gn_partial<32>(v, valid, uniform, lane, srow, col0 / cpg);
-                    else if (cpg == 16) gn_partial<16>(v, valid, uniform, lane, srow, col0 / 16);
-                    else if (cpg == 8)  gn_partial<8>(v, valid, uniform, lane, srow, col0 / 8);
-                    else                gn_partial<4>(v, valid, uniform, lane, srow, col0 / 4);
+                    if (p.act == 3) {       // training: store the pre-activation, normalise Swish(z) later -> stats of Swish(z)
+                        float sw[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sw[i] = swishf(v[i]);
+                        if (cpg >= 32)      gn_partial<32>(sw, valid, uniform, lane, srow, col0 / cpg);
+                        else if (cpg == 16) gn_partial<16>(sw, valid, uniform, lane, srow, col0 / 16);
+                        else if (cpg == 8)  gn_partial<8>(sw, valid, uniform, lane, srow, col0 / 8);
+                        else                gn_partial<4>(sw, valid, uniform, lane, srow, col0 / 4);
+                    } else {
+                        if (cpg >= 32)      gn_partial<32>(v, valid, uniform, lane, srow, col0 / cpg);
+                        else if (cpg == 16) gn_partial<16>(v, valid, uniform, lane, srow, col0 / 16);
+                        else if (cpg == 8)  gn_partial<8>(v, valid, uniform, lane, srow, col0 / 8);
+                        else                gn_partial<4>(v, valid, uniform, lane, srow, col0 / 4);
+                    }
                 }
                 if (valid) {
                     if (f32out) {

@@ -64,8 +64,8 @@ class U_Net(nn.Module):
 
     def engine(self):
         if self._engine is None:
-            from b200.engine import UNetEngine
-            self._engine = UNetEngine(self)
+            from b200.train_engine import UNetTrainEngine
+            self._engine = UNetTrainEngine(self)
         return self._engine
 
     def custom_load_state_dict(self, state_dict):
