@@ -33,12 +33,13 @@ def new_act(n, h, w, c, code, device):
 
 
 def conv2d(mode, x, wpacked, bias, cout, act=0, out=None, residual=None, gn_stats=None, groups=32, out_nchw_fp32=None):
-    """mode 0: 3x3/s1; 1: 3x3/s2 (x = parity planes [4*N, H/2, W/2, C]); 2: transposed 4x4/s2."""
+    """mode 0: 3x3/s1; 1: 3x3/s2 (x = parity planes [4*N, H/2, W/2, C]); 2: transposed 4x4/s2;
+    3: data gradient of mode 1 (x = dz); 4: data gradient of mode 2 (x = parity planes of dz)."""
     code = code_of(x)
     n, h, w, cin, ldx = _nhwc(x)
-    if mode == 1:
+    if mode in (1, 4):          # the A operand is a stack of 4 parity planes
         n //= 4
-    oh, ow = (2 * h, 2 * w) if mode == 2 else (h, w)
+    oh, ow = (2 * h, 2 * w) if mode in (2, 3) else (h, w)
     if out_nchw_fp32 is not None:
         y, ldy, out_mode = out_nchw_fp32, 0, 1
     else:

@@ -59,8 +59,11 @@ def unet_case(name, kwargs, n, h, w):
             no_grad.append(pname)
             continue
         gflat = p.grad.detach().flatten()
+        # large tensors: 4096 evenly strided samples (index i * numel // 4096) instead of the whole gradient
+        idx = (torch.arange(4096, dtype=torch.int64) * gflat.numel()) // 4096 if gflat.numel() > 4096 else None
         grads[pname] = {"norm": float(gflat.norm()), "sum": float(gflat.sum()),
                         "head": gflat[:64].clone(),
+                        "sample": gflat[idx].clone() if idx is not None else None,
                         "full": p.grad.detach().clone() if gflat.numel() <= 4096 else None}
     # batch-1 timestep broadcast (samplers pass t of shape [1])
     net.eval()

@@ -9,8 +9,9 @@ from oracle.weights import synth_state_dict
 
 pytestmark = pytest.mark.gpu
 
-# gradient tolerances (relative L2 per parameter tensor / on the norm)
-TOL = {"tf32": 2e-3, "bf16": 3e-2}
+# (relative L2 of ALL parameter gradients taken together, worst single parameter tensor).
+# tf32 = fp32-accumulate parity mode: the north-star bound of 1e-3 applies to the whole-network gradient.
+TOL = {"tf32": (1e-3, 2e-2), "bf16": (2e-2, 1.5e-1)}
 
 
 def _build(fx, precision):
@@ -34,19 +35,24 @@ def test_unet_backward_matches_reference(name, precision):
     named = dict(net.named_parameters())
     no_grad = sorted(k for k, p in named.items() if p.grad is None)
     assert no_grad == fx["no_grad"]
-    worst = (0.0, None)
+    errs, got_all, want_all = [], [], []
     for pname, g in fx["grads"].items():
         got = named[pname].grad.detach().float().cpu().flatten()
         assert torch.isfinite(got).all(), pname
+        if g["full"] is not None:
+            want, have = g["full"].flatten(), got
+        else:
+            idx = (torch.arange(4096, dtype=torch.int64) * got.numel()) // 4096
+            want, have = g["sample"], got[idx]
+        got_all.append(have)
+        want_all.append(want)
         if g["norm"] < 1e-7:
             continue
-        err_norm = abs(float(got.norm()) - g["norm"]) / g["norm"]
-        err = err_norm
-        if g["full"] is not None:
-            err = max(err, rel_l2(got, g["full"].flatten()))
-        elif float(g["head"].norm()) > 1e-3 * g["norm"] / max(1.0, (got.numel() / 64) ** 0.5):
-            err = max(err, min(rel_l2(got[:64], g["head"]), 10.0) * 0.5)      # 64-element slices are noisier than whole tensors
-        if err > worst[0]:
-            worst = (err, pname)
-        assert err < TOL[precision], (pname, err)
-    print(f"{name} {precision}: worst gradient error {worst[0]:.3e} at {worst[1]}")
+        errs.append((max(rel_l2(have, want), abs(float(got.norm()) - g["norm"]) / g["norm"]), pname))
+    errs.sort(reverse=True)
+    total = rel_l2(torch.cat(got_all), torch.cat(want_all))
+    print(f"{name} {precision}: gradient rel-L2 over all parameters = {total:.3e}; worst tensors: "
+          + "; ".join(f"{n}={e:.2e}" for e, n in errs[:4]))
+    assert total < TOL[precision][0]
+    bad = [(n, e) for e, n in errs if e >= TOL[precision][1]]
+    assert not bad, bad[:20]
