@@ -18,7 +18,7 @@ from ._lib import B200Error, call, ptr, stream
 
 
 def _version_key(params):
-    return tuple((p.data_ptr(), p._version) for p in params)
+    return tuple((p.data_ptr(), p._version, getattr(getattr(p, "_b2_layout", None), "epoch", 0)) for p in params)
 
 
 class WeightCache:
@@ -27,7 +27,8 @@ class WeightCache:
 
     def get(self, param, kind, code, cout, cin, cin_pad):
         key = (id(param), kind, code, cin_pad)
-        ver = (param.data_ptr(), param._version)
+        lay = getattr(param, "_b2_layout", None)      # fused optimiser updates bypass torch's version counter
+        ver = (param.data_ptr(), param._version, lay.epoch if lay is not None else 0)
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
             hit = (ver, ops.pack_weight(kind, param, cout, cin, cin_pad, code))

@@ -1,0 +1,62 @@
+"""FusedAdam: torch.optim.Adam semantics (the reference's optimiser, train_diffusion.py:214-218) executed as ONE
+sm_100a kernel over the flat parameter / gradient / moment buffers of a U_Net (b200.train_engine.GradLayout), or one
+launch per tensor for parameters that are not part of a flat layout.  `state_dict()` keeps torch's per-parameter
+keys ("step", "exp_avg", "exp_avg_sq": views of the flat moments) so optimiser checkpoints interchange."""
+import math
+
+import torch
+
+from ._lib import call, ptr, stream
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps)
+        super().__init__(params, defaults)
+        self.grad_scale = grad_scale          # e.g. 1 / world_size when gradients were sum-all-reduced
+        self._flat = {}                       # id(layout) -> (m_flat, v_flat)
+
+    @staticmethod
+    def _launch(p, g, m, v, n, group, step, grad_scale):
+        b1, b2 = group["betas"]
+        step_size = group["lr"] / (1.0 - b1 ** step)
+        inv_bc2_sqrt = 1.0 / math.sqrt(1.0 - b2 ** step)
+        call("b2_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), n, b1, b2, group["eps"], step_size, inv_bc2_sqrt, grad_scale, stream())
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            done_layouts = set()
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                lay = getattr(p, "_b2_layout", None)
+                flat_ok = lay is not None and p.grad.data_ptr() == lay.view(p).data_ptr() and lay.params_flat is not None \
+                    and p.data_ptr() == lay.param_view(p).data_ptr()
+                st = self.state[p]
+                if flat_ok:
+                    if id(lay) not in self._flat:
+                        self._flat[id(lay)] = (torch.zeros_like(lay.flat), torch.zeros_like(lay.flat))
+                    m_flat, v_flat = self._flat[id(lay)]
+                    if not st:
+                        off = lay.offsets[id(p)]
+                        st["step"] = torch.tensor(0.0)
+                        st["exp_avg"] = m_flat[off:off + p.numel()].view(p.shape)
+                        st["exp_avg_sq"] = v_flat[off:off + p.numel()].view(p.shape)
+                    st["step"] += 1
+                    if id(lay) not in done_layouts:
+                        done_layouts.add(id(lay))
+                        self._launch(lay.params_flat, lay.flat, m_flat, v_flat, lay.total, group, int(st["step"]), self.grad_scale)
+                        lay.epoch += 1          # cached kernel-layout weights are stale now
+                    continue
+                if not st:
+                    st["step"] = torch.tensor(0.0)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                g = p.grad.contiguous()
+                if (p.data_ptr() | g.data_ptr()) % 16 or not p.is_contiguous():
+                    raise RuntimeError("FusedAdam needs 16-byte aligned contiguous fp32 parameters")
+                self._launch(p, g, st["exp_avg"], st["exp_avg_sq"], p.numel(), group, int(st["step"]), self.grad_scale)
+        return loss

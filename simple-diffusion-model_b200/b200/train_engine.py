@@ -55,8 +55,13 @@ class GradLayout:
             self.offsets[id(p)] = off
             off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
         self.total = off
+        self.front_end = sum((p.numel() + 3) // 4 * 4 for p in ys_w + ys_b)
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
         self.views = {id(p): self.flat[self.offsets[id(p)]:self.offsets[id(p)] + p.numel()].view(p.shape) for p in self.params}
+        self.params_flat = None
+        self.epoch = 0                         # bumped by FusedAdam.step(): invalidates cached kernel-layout weights
+        for p in self.params:
+            p._b2_layout = self
         self.adagn_w_numel = sum(p.numel() for p in ys_w)
         self.adagn_b_numel = sum(p.numel() for p in ys_b)
         # y_scale weights have numel % 4 == 0 whenever C % 4 == 0, so the concatenated views are dense
@@ -64,6 +69,33 @@ class GradLayout:
 
     def view(self, p):
         return self.views[id(p)]
+
+    def module_range(self, module):
+        """Flat range covered by a module's live parameters, AdaGN scale Linears excluded (they live in the front
+        region).  Contiguous by construction of the bucket order."""
+        offs = [(self.offsets[id(p)], self.offsets[id(p)] + (p.numel() + 3) // 4 * 4) for p in module.parameters()
+                if id(p) in self.offsets and self.offsets[id(p)] >= self.front_end]
+        if not offs:
+            return 0, 0
+        return min(o[0] for o in offs), max(o[1] for o in offs)
+
+    def flatten_params(self):
+        """Re-homes every live parameter into one flat fp32 buffer laid out like the gradients, so the optimiser
+        (and a parameter broadcast) is a single pass.  Parameter objects, names and shapes are unchanged."""
+        if self.params_flat is None:
+            flat = torch.zeros(self.total, dtype=torch.float32, device=self.flat.device)
+            self.pviews = {}
+            for p in self.params:
+                off = self.offsets[id(p)]
+                v = flat[off:off + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                self.pviews[id(p)] = v
+            self.params_flat = flat
+        return self.params_flat
+
+    def param_view(self, p):
+        return self.pviews[id(p)]
 
 
 class _UNetFn(torch.autograd.Function):
@@ -85,7 +117,8 @@ class UNetTrainEngine(UNetEngine):
     def __init__(self, net):
         super().__init__(net)
         self.layout = None
-        self.post_backward = None          # optional callable(layout) -> e.g. the data-parallel all-reduce
+        self.post_backward = None          # optional callable(layout), runs when every gradient is complete
+        self.on_grads_ready = None         # optional callable(layout, lo, hi): flat range [lo, hi) is final (DP buckets)
 
     # ------------------------------------------------------------------------------------------ public
     def forward_train(self, x, t=None, cond=None):
@@ -132,6 +165,7 @@ class UNetTrainEngine(UNetEngine):
         kal = ops.K_ALIGN[code]
         cpad = ((cin + kal - 1) // kal) * kal
         h = ops.nchw_to_nhwc_pad(x, cpad, code)
+        tape.append(("mark", net.in_layer))
         h = self._plain_conv_train(net.in_layer[0], h, ctx, need_dx=False)
         h = self._plain_conv_train(net.in_layer[1], h, ctx)
         cats = []
@@ -140,9 +174,11 @@ class UNetTrainEngine(UNetEngine):
             cout = blk.out_layer.conv_layer[0].weight.shape[0]
             hh, ww = hh // 2, ww // 2
             cat = ops.new_act(n, hh, ww, 2 * cout, code, dev)
+            tape.append(("mark", blk))
             h = self._block_train(blk, h, ctx, out=cat[..., cout:])
             tape.append(("skip_out", len(cats)))             # its gradient also arrives through the concat buffer
             cats.append(cat)
+        tape.append(("mark", net.middle_layer))
         h = self._plain_conv_train(net.middle_layer[0], h, ctx)
         c_mid = cats[-1].shape[3] // 2
         self._plain_conv_train(net.middle_layer[1], h, ctx, out=cats[-1][..., :c_mid])
@@ -152,8 +188,10 @@ class UNetTrainEngine(UNetEngine):
             cat = cats.pop()
             cout = blk.out_layer.conv_layer[0].weight.shape[1]
             dst = cats[-1][..., :cout] if i + 1 < n_up else None
+            tape.append(("mark", blk))
             tape.append(("cat_in", level, cat.shape[3] // 2))   # splits d(cat) into d(x part) and d(skip part)
             h = self._block_train(blk, cat, ctx, out=dst)
+        tape.append(("mark", net.out_layers))
         h = self._plain_conv_train(net.out_layers[0], h, ctx)
         last = net.out_layers[1]
         conv = last.conv_layer[0]
@@ -388,12 +426,21 @@ class UNetTrainEngine(UNetEngine):
                 d = self._bwd_attention(blk, x_in, saved, d)
             elif kind == "emb":
                 self._bwd_embedding(entry[1], ctx)
+            elif kind == "mark" and self.on_grads_ready is not None:
+                lo, hi = lay.module_range(entry[1])
+                if hi > lo:
+                    self.on_grads_ready(lay, lo, hi)
         for p in lay.params:
             v = lay.view(p)
             if p.grad is None or p.grad.data_ptr() == v.data_ptr():
                 p.grad = v
             else:
                 p.grad.add_(v)
+        if self.on_grads_ready is not None:          # AdaGN scale Linears (front of the buffer) + embedding MLPs (tail)
+            self.on_grads_ready(lay, 0, lay.front_end)
+            lo, hi = lay.module_range(net.cond_emb)
+            if hi > lo:
+                self.on_grads_ready(lay, lo, hi)
         if self.post_backward is not None:
             self.post_backward(lay)
 

@@ -1,0 +1,51 @@
+// Fused Adam over flat fp32 buffers (parameters, gradients, exp_avg, exp_avg_sq): one memory-bound pass of
+// 28 bytes per parameter instead of torch's multi-tensor foreach over ~760 tensors (train_diffusion.py:214-218,361).
+#include "host_util.h"
+#include "sdm_b200.h"
+
+using namespace b2;
+
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 long long n, float beta1, float beta2, float eps, float step_size, float inv_bc2_sqrt,
+                                 float grad_scale) {
+    const long long nv = n / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* pa = reinterpret_cast<float*>(&pp); const float* ga = reinterpret_cast<const float*>(&gg);
+        float* ma = reinterpret_cast<float*>(&mm); float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gr = ga[j] * grad_scale;
+            ma[j] = beta1 * ma[j] + (1.0f - beta1) * gr;
+            va[j] = beta2 * va[j] + (1.0f - beta2) * gr * gr;
+            const float denom = sqrtf(va[j]) * inv_bc2_sqrt + eps;
+            pa[j] -= step_size * (ma[j] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (long long i = nv * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gr = g[i] * grad_scale;
+        m[i] = beta1 * m[i] + (1.0f - beta1) * gr;
+        v[i] = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+        p[i] -= step_size * (m[i] / (sqrtf(v[i]) * inv_bc2_sqrt + eps));
+    }
+}
+
+// step_size = lr / (1 - beta1^t), inv_bc2_sqrt = 1 / sqrt(1 - beta2^t)  (torch.optim.Adam's formulation).
+extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, float beta1, float beta2, float eps,
+                            float step_size, float inv_bc2_sqrt, float grad_scale, void* stream) {
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return set_error("b2_adam_flat: buffers must be 16-byte aligned");
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = 16LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, step_size, inv_bc2_sqrt, grad_scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("b2_adam_flat: %s", cudaGetErrorString(e));
+    return 0;
+}
