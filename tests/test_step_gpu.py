@@ -25,7 +25,7 @@ def test_fused_adam_matches_torch_adam():
         oa.step()
         ob.step()
     for x, y in zip(a, b):
-        assert torch.allclose(x, y, rtol=2e-6, atol=2e-7)
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-6)
     sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
     assert set(sa[0].keys()) == {"step", "exp_avg", "exp_avg_sq"} == set(sb[0].keys())
     assert torch.allclose(sa[0]["exp_avg_sq"], sb[0]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
