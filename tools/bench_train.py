@@ -55,8 +55,12 @@ def run(args):
     l0 = b2lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    import time
+    wall = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         loss = step()
+        wall.append(round(1e3 * (time.perf_counter() - t0), 1))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
@@ -70,7 +74,7 @@ def run(args):
                           "ms_per_step": ms, "per_gpu_batch": n, "size": s, "precision": args.precision, "cond_dim": args.cond_dim,
                           "loss": float(loss), "model_tflops_per_gpu": flops / (ms / 1000.0) / 1e12,
                           "gpu_launches_per_step": (b2lib.LAUNCHES - l0) // args.steps, "scaling": "weak",
-                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "host_ms_per_step": wall}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
