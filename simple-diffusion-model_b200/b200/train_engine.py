@@ -305,18 +305,29 @@ class UNetTrainEngine(UNetEngine):
         return out
 
     # ------------------------------------------------------------------------------------------ backward
+    def _scratch(self, numel, device):
+        """Persistent, zeroed fp32 scratch for kernel-layout weight gradients (stream order makes one buffer enough;
+        re-using it keeps the caching allocator from churning multi-GB blocks every step)."""
+        buf = getattr(self, "_scratch_buf", None)
+        if buf is None or buf.numel() < numel or buf.device != device:
+            buf = torch.empty((max(numel, 1 << 24),), dtype=torch.float32, device=device)
+            self._scratch_buf = buf
+        out = buf[:numel]
+        out.zero_()
+        return out
+
     def _wgrad_conv(self, mode, conv, x, dz, kind):
         """Weight gradient in kernel layout -> unpacked into the flat gradient view of the parameter."""
         code = ops.code_of(x)
         if mode == 2:
             cin, cout = conv.weight.shape[0], conv.weight.shape[1]
-            packed = torch.zeros((16 * cout * cin,), dtype=torch.float32, device=x.device)
+            packed = self._scratch(16 * cout * cin, x.device)
             ops.conv2d_wgrad(2, x, dz, cout, packed)
             call("b2_unpack_weight_grad", 2, ptr(packed), ptr(self.layout.view(conv.weight)), cout, cin, cin, 0, stream())
             return
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
         cin_pad = x.shape[3]
-        packed = torch.zeros((cout * 9 * cin_pad,), dtype=torch.float32, device=x.device)
+        packed = self._scratch(cout * 9 * cin_pad, x.device)
         ops.conv2d_wgrad(mode, x, dz, cout, packed)
         call("b2_unpack_weight_grad", 0, ptr(packed), ptr(self.layout.view(conv.weight)), cout, cin, cin_pad, 0, stream())
 

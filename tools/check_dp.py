@@ -15,7 +15,7 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 from b200.functional import mse_loss
 from b200.parallel import DataParallel, shard_range
-from degraders import CosineNoiseDegradation
+from degraders import NoiseDegradation
 import diffusion_sampling_algorithms as S
 from models.U_Net import U_Net
 
@@ -43,13 +43,14 @@ print(f"rank {rank}: DP gradient vs full-batch gradient rel-L2 = {err:.3e}; buck
 assert err < 2e-3, err
 # sharded sampling == unsharded sampling (no collective in the path)
 net.eval()
-deg = CosineNoiseDegradation(1000)
+deg = NoiseDegradation(5e-3, 9e-3, 1000, device=dev)
 x_T = torch.randn((2 * world, 3, 32, 32), generator=g).to(dev)
 full = S.ddim_sampling(net, deg, x_T, ddim_step_size=250, device=dev, log=lambda *a, **k: None)
 lo, hi = shard_range(2 * world, rank, world)
 mine = S.ddim_sampling(net, deg, x_T[lo:hi].clone(), ddim_step_size=250, device=dev, log=lambda *a, **k: None)
 same = torch.equal(mine, full[lo:hi])
-md = float((mine - full[lo:hi]).abs().max())
-print(f"rank {rank}: sharded DDIM == unsharded: {same} (max abs diff {md:.2e})", flush=True)
+rel = float((mine - full[lo:hi]).norm() / full[lo:hi].norm())
+print(f"rank {rank}: sharded DDIM vs unsharded: bitwise {same}, rel-L2 {rel:.2e} (GroupNorm sums use fp32 atomics: order-dependent in the last bits)", flush=True)
+assert rel < 1e-3, rel
 dist.barrier()
 dist.destroy_process_group()
