@@ -200,6 +200,7 @@ class UNetTrainEngine(UNetEngine):
         w = self.cache.get(conv.weight, 0, code, c_out, conv.weight.shape[1], h.shape[3])
         ops.conv2d(0, h, w, conv.bias, c_out, act=(2 if net.image_recon else 0), out_nchw_fp32=y)
         tape.append(("last", last, h, y if net.image_recon else None))
+        del ctx["tape"]          # break the ctx <-> tape reference cycle: activations must die by refcount, not by GC
         return y, tape
 
     def _embedding_train(self, t, cond):
@@ -452,6 +453,7 @@ class UNetTrainEngine(UNetEngine):
             lo, hi = lay.module_range(net.cond_emb)
             if hi > lo:
                 self.on_grads_ready(lay, lo, hi)
+        tape.clear()
         if self.post_backward is not None:
             self.post_backward(lay)
 
