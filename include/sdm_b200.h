@@ -150,7 +150,7 @@ int b2_mse_loss_grad(const float* pred, const float* target, float* grad, float*
 /* torch.optim.Adam (train_diffusion.py:214-218: betas (0.5, 0.999), eps 1e-8, no weight decay) over flat fp32
  * buffers: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= step_size * m / (sqrt(v) * inv_bc2_sqrt + eps), with
  * g = grad * grad_scale (1/world_size after a sum all-reduce), step_size = lr/(1-b1^t), inv_bc2_sqrt = 1/sqrt(1-b2^t). */
-int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, float beta1, float beta2, float eps,
+int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
                  float step_size, float inv_bc2_sqrt, float grad_scale, void* stream);
 
 #ifdef __cplusplus

@@ -11,7 +11,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsdm_b200.so")
 
-_P, _I, _L, _F, _U = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_ulonglong
+_P, _I, _L, _F, _U, _D = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_ulonglong,
+                          ctypes.c_double)
 
 # name -> argument ctypes, in the order of include/sdm_b200.h
 SIGNATURES = {
@@ -39,7 +40,7 @@ SIGNATURES = {
     "b2_ddim_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "b2_ddpm_step": [_P, _P, _P, _P, _L, _F, _F, _F, _I, _U, _U, _L, _P],
     "b2_cold_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P],
-    "b2_adam_flat": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P],
+    "b2_adam_flat": [_P, _P, _P, _P, _L, _D, _D, _F, _F, _F, _F, _P],
     "b2_mse_loss_grad": [_P, _P, _P, _P, _L, _F, _P],
 }
 

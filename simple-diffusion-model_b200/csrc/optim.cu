@@ -6,8 +6,8 @@
 using namespace b2;
 
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                 long long n, float beta1, float beta2, float eps, float step_size, float inv_bc2_sqrt,
-                                 float grad_scale) {
+                                 long long n, float beta1, float omb1, float beta2, float omb2, float eps, float step_size,
+                                 float inv_bc2_sqrt, float grad_scale) {
     const long long nv = n / 4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -19,8 +19,8 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float gr = ga[j] * grad_scale;
-            ma[j] = beta1 * ma[j] + (1.0f - beta1) * gr;
-            va[j] = beta2 * va[j] + (1.0f - beta2) * gr * gr;
+            ma[j] = beta1 * ma[j] + omb1 * gr;
+            va[j] = beta2 * va[j] + omb2 * (gr * gr);
             const float denom = sqrtf(va[j]) * inv_bc2_sqrt + eps;
             pa[j] -= step_size * (ma[j] / denom);
         }
@@ -30,21 +30,22 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
     }
     for (long long i = nv * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gr = g[i] * grad_scale;
-        m[i] = beta1 * m[i] + (1.0f - beta1) * gr;
-        v[i] = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+        m[i] = beta1 * m[i] + omb1 * gr;
+        v[i] = beta2 * v[i] + omb2 * (gr * gr);
         p[i] -= step_size * (m[i] / (sqrtf(v[i]) * inv_bc2_sqrt + eps));
     }
 }
 
+// betas arrive as doubles so that 1 - beta is rounded once, like torch's Python-side scalar (1 - 0.999f != 0.001f).
 // step_size = lr / (1 - beta1^t), inv_bc2_sqrt = 1 / sqrt(1 - beta2^t)  (torch.optim.Adam's formulation).
-extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, float beta1, float beta2, float eps,
+extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
                             float step_size, float inv_bc2_sqrt, float grad_scale, void* stream) {
     if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return set_error("b2_adam_flat: buffers must be 16-byte aligned");
     long long blocks = (n / 4 + 255) / 256;
     const long long cap = 16LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, step_size, inv_bc2_sqrt, grad_scale);
+    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat: %s", cudaGetErrorString(e));
     return 0;
