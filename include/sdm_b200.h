@@ -153,6 +153,12 @@ int b2_mse_loss_grad(const float* pred, const float* target, float* grad, float*
 int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
                  float step_size, float inv_bc2_sqrt, float grad_scale, void* stream);
 
+/* CUDA-graph friendly form: `state` is a DEVICE float[8] = {steps taken, lr, grad_scale, (out) step_size, (out)
+ * inv_bc2_sqrt, ...}; every call advances the step counter on the device, so a captured graph replays correctly.
+ * The host changes the learning rate (train_diffusion.py:368-371) by writing state[1]. */
+int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
+                       float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,175 @@
+"""CUDA-graph execution of the hot loops.
+
+The reference's train step issues ~4 k ATen launches from Python (train_diffusion.py:333-364) and each sampler step
+~1.2 k (diffusion_sampling_algorithms.py:34-55); at small per-GPU batches both are bound by the host.  Every kernel of
+this library is allocation-free, sync-free and takes its tensors by pointer, so a whole optimisation step
+(q-sample -> U-Net forward -> MSE + gradient -> backward -> gradient all-reduce -> Adam) and a whole U-Net evaluation
+can be captured once and replayed with static input buffers.  Step-dependent scalars (Adam bias corrections, learning
+rate) live in device memory (b2_adam_flat_graph), so the captured kernels never change.
+"""
+import torch
+
+from ._lib import B200Error, call, ptr, stream
+
+
+class GraphedTrainStep:
+    """One trainer step as a replayable graph.  kind: "eps" (train_diffusion.py:336-350, train_doodle_diffusion.py:304-315;
+    target = eps), "x0" (train_noise_cold_diffusion.py:330-340; target = x0) or "target" (train_SR_diffusion.py:366-372;
+    explicit target tensor).  The optimiser must be a FusedAdam(capturable=True) over `net.parameters()`."""
+
+    def __init__(self, net, degrader, optimizer, kind="eps", warmup=2):
+        if kind not in ("eps", "x0", "target"):
+            raise ValueError("kind must be 'eps', 'x0' or 'target'")
+        if not getattr(optimizer, "capturable", False):
+            raise B200Error("GraphedTrainStep needs FusedAdam(..., capturable=True)")
+        self.net, self.degrader, self.opt, self.kind, self.warmup = net, degrader, optimizer, kind, warmup
+        self.graph = None
+        self.key = None
+        self.replays = 0
+
+    # the step body, written against the engine directly (no autograd graph is built)
+    def _body(self):
+        s = self.static
+        x_t = self.degrader(s["x0"], s["t"], s["eps"])
+        inp = torch.cat((x_t, s["cond_img"]), dim=1) if s["cond_img"] is not None else x_t
+        eng = self.net.engine()
+        with torch.no_grad():
+            pred, tape = eng._forward_tape(inp, s["t"], s["labels"])
+            target = {"eps": s["eps"], "x0": s["x0"], "target": s["target"]}[self.kind]
+            call("b2_mse_loss_grad", ptr(pred), ptr(target), ptr(s["dpred"]), ptr(s["loss"]), pred.numel(), 1.0, stream())
+            eng._backward_tape(tape, s["dpred"])
+            self.opt.step()
+
+    def _capture(self, x0, t, eps, labels, cond_img, target):
+        dev = x0.device
+        clone = lambda v: None if v is None else v.detach().clone().contiguous()
+        self.static = {"x0": clone(x0.float()), "t": clone(t.to(torch.int64)), "eps": clone(eps.float()), "labels": clone(labels),
+                       "cond_img": clone(cond_img), "target": clone(target), "loss": torch.zeros((), dtype=torch.float32, device=dev)}
+        n, _, h, w = x0.shape
+        out_ch = self.net.out_layers[1].conv_layer[0].weight.shape[0]
+        self.static["dpred"] = torch.empty((n, out_ch, h, w), dtype=torch.float32, device=dev)
+        lay = self.net.engine().grad_layout(dev)
+        lay.flatten_params()
+        # The warm-up iterations (allocator, NCCL communicators, weight cache) run the real step; parameters, moments
+        # and step counters are restored afterwards so that capturing has no training side effect.
+        opt = self.opt
+        had_moments = id(lay) in opt._flat
+        saved = [lay.params_flat.clone()] + ([m.clone() for m in opt._flat[id(lay)]] if had_moments else [])
+        steps_before = 0.0
+        for group in opt.param_groups:
+            for p in group["params"]:
+                st = opt.state.get(p)
+                if st and "step" in st:
+                    steps_before = float(st["step"])
+                    break
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self._body()
+        lay.params_flat.copy_(saved[0])
+        m_flat, v_flat = opt._flat[id(lay)]
+        if had_moments:
+            m_flat.copy_(saved[1])
+            v_flat.copy_(saved[2])
+        else:
+            m_flat.zero_()
+            v_flat.zero_()
+        for group in opt.param_groups:
+            dev_state = opt.device_state(lay, group)
+            dev_state[0:1].fill_(steps_before)
+            for p in group["params"]:
+                st = opt.state.get(p)
+                if st and "step" in st:
+                    st["step"].fill_(steps_before)
+        lay.epoch += 1
+        del saved
+
+    def __call__(self, x0, t, eps, labels=None, cond_img=None, target=None):
+        if not x0.is_cuda:
+            raise B200Error("training needs CUDA tensors: this build has no CPU path")
+        key = (tuple(x0.shape), tuple(t.shape), None if labels is None else tuple(labels.shape),
+               None if cond_img is None else tuple(cond_img.shape), None if target is None else tuple(target.shape),
+               self.net.precision)
+        if self.graph is None or key != self.key:
+            self.key = key
+            self._capture(x0, t, eps, labels, cond_img, target)
+        s = self.static
+        s["x0"].copy_(x0, non_blocking=True)
+        s["t"].copy_(t, non_blocking=True)
+        s["eps"].copy_(eps, non_blocking=True)
+        for name, v in (("labels", labels), ("cond_img", cond_img), ("target", target)):
+            if v is not None:
+                s[name].copy_(v, non_blocking=True)
+        self.opt.sync_lr()
+        self.graph.replay()
+        self.replays += 1
+        self.opt.note_replayed()
+        lay = self.net.engine().layout
+        lay.epoch += 1                           # eager users of the weight cache (eval / sampling) must re-pack
+        return s["loss"]
+
+
+class GraphedUNet:
+    """Inference-mode U_Net evaluation as a replayable graph with the call signature the samplers use
+    (`diffusion_net(x, t, labels)`, diffusion_sampling_algorithms.py:34-37).  One graph per input signature."""
+
+    def __init__(self, net, warmup=1):
+        self.net, self.warmup = net, warmup
+        self.graphs = {}
+
+    def eval(self):
+        self.net.eval()
+        return self
+
+    def train(self, mode=True):
+        self.net.train(mode)
+        return self
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["net"], name)
+
+    def _weights_key(self):
+        lay = getattr(self.net.engine(), "layout", None)
+        return (self.net.precision, lay.epoch if lay is not None else 0,
+                tuple(p._version for p in self.net.parameters()))
+
+    def __call__(self, x, t=None, cond=None):
+        if not x.is_cuda:
+            raise B200Error("U_Net.forward needs CUDA tensors: this build has no CPU path")
+        key = (tuple(x.shape), None if t is None else tuple(t.shape), None if cond is None else tuple(cond.shape))
+        wkey = self._weights_key()
+        entry = self.graphs.get(key)
+        if entry is None or entry["wkey"] != wkey:
+            entry = self._capture(x, t, cond, wkey)
+            self.graphs[key] = entry
+        entry["x"].copy_(x, non_blocking=True)
+        if t is not None:
+            entry["t"].copy_(t, non_blocking=True)
+        if cond is not None:
+            entry["cond"].copy_(cond, non_blocking=True)
+        entry["graph"].replay()
+        return entry["out"]
+
+    def _capture(self, x, t, cond, wkey):
+        dev = x.device
+        eng = self.net.engine()
+        st = {"x": x.detach().clone().contiguous().float(), "t": None if t is None else t.detach().clone().to(torch.int64),
+              "cond": None if cond is None else cond.detach().clone().float(), "wkey": wkey}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup):         # packs the kernel-layout weights outside the graph
+                eng.forward(st["x"], st["t"], st["cond"])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"), torch.no_grad():
+            st["out"] = eng.forward(st["x"], st["t"], st["cond"])
+        st["graph"] = g
+        return st

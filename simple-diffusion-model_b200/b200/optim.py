@@ -10,11 +10,42 @@ from ._lib import call, ptr, stream
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, capturable=False):
         defaults = dict(lr=lr, betas=betas, eps=eps)
         super().__init__(params, defaults)
         self.grad_scale = grad_scale          # e.g. 1 / world_size when gradients were sum-all-reduced
         self._flat = {}                       # id(layout) -> (m_flat, v_flat)
+        # capturable: step count / lr / grad scale live in device memory (b2_adam_flat_graph) so that a CUDA graph
+        # holding step() replays correctly; b200.graph.GraphedTrainStep keeps the host-side counters in sync.
+        self.capturable = capturable
+        self._dev_state = {}                  # id(layout) -> device float[8]
+        self._dev_lr = {}
+
+    def device_state(self, lay, group, steps=0.0):
+        st = self._dev_state.get(id(lay))
+        if st is None:
+            st = torch.tensor([steps, group["lr"], self.grad_scale, 0, 0, 0, 0, 0], dtype=torch.float32, device=lay.flat.device)
+            self._dev_state[id(lay)] = st
+            self._dev_lr[id(lay)] = group["lr"]
+        return st
+
+    def sync_lr(self):
+        """Pushes a changed learning rate (the reference halves it every lr_steps, train_diffusion.py:368-371) to the device."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                lay = getattr(p, "_b2_layout", None)
+                if lay is not None and id(lay) in self._dev_state and self._dev_lr[id(lay)] != group["lr"]:
+                    self._dev_state[id(lay)][1:2].fill_(group["lr"])
+                    self._dev_lr[id(lay)] = group["lr"]
+                break
+
+    def note_replayed(self):
+        """A captured step() ran on the device: advance the host-side per-parameter step counters to match."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st and "step" in st:
+                    st["step"] += 1
 
     @staticmethod
     def _launch(p, g, m, v, n, group, step, grad_scale):
@@ -44,10 +75,18 @@ class FusedAdam(torch.optim.Optimizer):
                         st["step"] = torch.tensor(0.0)
                         st["exp_avg"] = m_flat[off:off + p.numel()].view(p.shape)
                         st["exp_avg_sq"] = v_flat[off:off + p.numel()].view(p.shape)
+                    if self.capturable:
+                        self.device_state(lay, group, float(st["step"]))      # created once, from the pre-step count
                     st["step"] += 1
                     if id(lay) not in done_layouts:
                         done_layouts.add(id(lay))
-                        self._launch(lay.params_flat, lay.flat, m_flat, v_flat, lay.total, group, int(st["step"]), self.grad_scale)
+                        if self.capturable:
+                            b1, b2 = group["betas"]
+                            dev = self.device_state(lay, group)
+                            call("b2_adam_flat_graph", ptr(lay.params_flat), ptr(lay.flat), ptr(m_flat), ptr(v_flat), lay.total,
+                                 float(b1), float(b2), group["eps"], ptr(dev), stream())
+                        else:
+                            self._launch(lay.params_flat, lay.flat, m_flat, v_flat, lay.total, group, int(st["step"]), self.grad_scale)
                         lay.epoch += 1          # cached kernel-layout weights are stale now
                     continue
                 if not st:

@@ -43,6 +43,24 @@ __device__ __forceinline__ void st16(T* p, const float (&f)[V16<T>::N]) {
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float swish_grad(float z) { const float s = sigmoidf_(z); return s * (1.0f + z * (1.0f - s)); }
 
+
+// Per-channel partial sums held by `threads = cv * k` threads (thread owns V channels of pixel-row `prow`) are summed
+// over the k pixel rows in shared memory; one fp32 atomic per channel per CTA then reaches global memory (instead of
+// one per thread, which serialises thousands of same-address atomics in L2).
+template <int V>
+__device__ __forceinline__ void block_colsum_atomic(const float (&v)[V], float* red, int C, int c0, int prow, int k,
+                                                    float* __restrict__ dst) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[prow * C + c0 + j] = v[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < k; ++r) acc += red[r * C + c];
+        atomicAdd(dst + c, acc);
+    }
+    __syncthreads();
+}
+
 // Launch shape shared by the streaming passes: each thread owns one 16-byte channel vector for the whole kernel
 // (so per-channel partial sums live in registers) and strides over the pixels of one slab of one image.
 struct SlabLaunch { int threads, rows_per_block, slabs; };
@@ -82,21 +100,29 @@ __global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ld
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    for (int p = p0 + prow; p < p1; p += rows_per_block) {
-        float d[V], zz[V];
-        ld16<T>(dout + (base + p) * ldd + c0, d);
-        ld16<T>(z + (base + p) * ldz + c0, zz);
+    constexpr int U = 4;                 // independent 16-byte loads in flight per thread
+    for (int pb = p0 + prow; pb < p1; pb += U * rows_per_block) {
+        float d[U][V], zz[U][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const float xh = (swishf(zz[j]) - mean[j]) * rstd[j];
-            s1[j] += d[j]; s2[j] = fmaf(d[j], xh, s2[j]);
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * rows_per_block;
+            if (p < p1) { ld16<T>(dout + (base + p) * ldd + c0, d[u]); ld16<T>(z + (base + p) * ldz + c0, zz[u]); }
+            else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) { d[u][j] = 0.f; zz[u][j] = 0.f; }
+            }
         }
-    }
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        atomicAdd(a1 + (long long)n * C + c0 + j, s1[j]);
-        atomicAdd(a2 + (long long)n * C + c0 + j, s2[j]);
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float xh = (swishf(zz[u][j]) - mean[j]) * rstd[j];
+                s1[j] += d[u][j]; s2[j] = fmaf(d[u][j], xh, s2[j]);
+            }
     }
+    extern __shared__ float red[];
+    block_colsum_atomic<V>(s1, red, C, c0, prow, rows_per_block, a1 + (long long)n * C);
+    block_colsum_atomic<V>(s2, red, C, c0, prow, rows_per_block, a2 + (long long)n * C);
 }
 
 // Finalize (one CTA per image): ds[n][c] += gamma*a2 + (beta+1)*a1; dgamma[c] += s*a2; dbeta[c] += s*a1;
@@ -151,22 +177,35 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    for (int p = p0 + prow; p < p1; p += rows_per_block) {
-        float d[V], zz[V], o[V];
-        ld16<T>(dout + (base + p) * ldd + c0, d);
-        ld16<T>(z + (base + p) * ldz + c0, zz);
+    constexpr int U = 4;
+    for (int pb = p0 + prow; pb < p1; pb += U * rows_per_block) {
+        float d[U][V], zz[U][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const float xh = (swishf(zz[j]) - mean[j]) * rstd[j];
-            const float dy = rstd[j] * (sg[j] * d[j] - m1[j] - xh * m2[j]);
-            o[j] = dy * swish_grad(zz[j]);
-            db[j] += o[j];
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * rows_per_block;
+            if (p < p1) { ld16<T>(dout + (base + p) * ldd + c0, d[u]); ld16<T>(z + (base + p) * ldz + c0, zz[u]); }
         }
-        st16<T>(dz + (base + p) * lddz + c0, o);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * rows_per_block;
+            if (p < p1) {
+                float o[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float zv = zz[u][j];
+                    const float sig = sigmoidf_(zv);
+                    const float xh = (zv * sig - mean[j]) * rstd[j];
+                    const float dy = rstd[j] * (sg[j] * d[u][j] - m1[j] - xh * m2[j]);
+                    o[j] = dy * (sig * (1.0f + zv * (1.0f - sig)));
+                    db[j] += o[j];
+                }
+                st16<T>(dz + (base + p) * lddz + c0, o);
+            }
+        }
     }
     if (dbias) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) atomicAdd(dbias + c0 + j, db[j]);
+        extern __shared__ float red[];
+        block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
     }
 }
 
@@ -187,15 +226,16 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
     cudaError_t e = cudaMemsetAsync(work, 0, 2LL * N * C * sizeof(float), st);
     if (e != cudaSuccess) return set_error("b2_adagn_bwd: memset: %s", cudaGetErrorString(e));
     const SlabLaunch sl = slab_launch(N, HW, cv);
+    const size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
     if (dtype == 0)
-        adagn_bwd_reduce_kernel<bf16><<<N * sl.slabs, sl.threads, 0, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        adagn_bwd_reduce_kernel<bf16><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     else
-        adagn_bwd_reduce_kernel<float><<<N * sl.slabs, sl.threads, 0, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        adagn_bwd_reduce_kernel<float><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     adagn_bwd_finalize_kernel<<<N, 256, groups * 2 * sizeof(float), st>>>(a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, m12, HW, C, groups);
     if (dtype == 0)
-        adagn_bwd_apply_kernel<bf16><<<N * sl.slabs, sl.threads, 0, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, m12, s, s_bstride, gamma, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        adagn_bwd_apply_kernel<bf16><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, m12, s, s_bstride, gamma, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     else
-        adagn_bwd_apply_kernel<float><<<N * sl.slabs, sl.threads, 0, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, m12, s, s_bstride, gamma, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        adagn_bwd_apply_kernel<float><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, m12, s, s_bstride, gamma, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     LAUNCH_CHECK("b2_adagn_bwd");
 }
 
@@ -212,29 +252,41 @@ __global__ void act_kernel(int mode, const T* __restrict__ a, long long lda, con
     float db[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) db[j] = 0.f;
-    for (long long r = (long long)blockIdx.x * rows_per_block + prow; r < rows; r += (long long)gridDim.x * rows_per_block) {
-        float x[V], o[V];
-        if (mode == 0) {
-            ld16<T>(z + r * ldz + c0, x);
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * rows_per_block;
+    for (long long rb = (long long)blockIdx.x * rows_per_block + prow; rb < rows; rb += U * stride) {
+        float x[U][V], zz[U][V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) o[j] = swishf(x[j]);
-            st16<T>(out + r * ldo + c0, o);
-        } else if (mode == 1) {
-            float zz[V];
-            ld16<T>(a + r * lda + c0, x);
-            ld16<T>(z + r * ldz + c0, zz);
+        for (int u = 0; u < U; ++u) {
+            const long long r = rb + u * stride;
+            if (r < rows) {
+                if (mode != 0) ld16<T>(a + r * lda + c0, x[u]);
+                if (mode != 2) ld16<T>(z + r * ldz + c0, zz[u]);
+            }
+        }
 #pragma unroll
-            for (int j = 0; j < V; ++j) { o[j] = x[j] * swish_grad(zz[j]); db[j] += o[j]; }
-            st16<T>(out + r * ldo + c0, o);
-        } else {
-            ld16<T>(a + r * lda + c0, x);
+        for (int u = 0; u < U; ++u) {
+            const long long r = rb + u * stride;
+            if (r < rows) {
+                float o[V];
+                if (mode == 0) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) db[j] += x[j];
+                    for (int j = 0; j < V; ++j) o[j] = swishf(zz[u][j]);
+                    st16<T>(out + r * ldo + c0, o);
+                } else if (mode == 1) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) { o[j] = x[u][j] * swish_grad(zz[u][j]); db[j] += o[j]; }
+                    st16<T>(out + r * ldo + c0, o);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) db[j] += x[u][j];
+                }
+            }
         }
     }
     if (dbias && mode != 0) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) atomicAdd(dbias + c0 + j, db[j]);
+        extern __shared__ float red[];
+        block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
     }
 }
 extern "C" int b2_act(int mode, const void* a, long long lda, const void* z, long long ldz, void* out, long long ldo,
@@ -248,8 +300,8 @@ extern "C" int b2_act(int mode, const void* a, long long lda, const void* z, lon
     const long long cap = 8LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (dtype == 0) act_kernel<bf16><<<(int)blocks, cv * k, 0, (cudaStream_t)stream>>>(mode, (const bf16*)a, lda, (const bf16*)z, ldz, (bf16*)out, ldo, dbias, rows, C, k);
-    else act_kernel<float><<<(int)blocks, cv * k, 0, (cudaStream_t)stream>>>(mode, (const float*)a, lda, (const float*)z, ldz, (float*)out, ldo, dbias, rows, C, k);
+    if (dtype == 0) act_kernel<bf16><<<(int)blocks, cv * k, (size_t)k * C * sizeof(float), (cudaStream_t)stream>>>(mode, (const bf16*)a, lda, (const bf16*)z, ldz, (bf16*)out, ldo, dbias, rows, C, k);
+    else act_kernel<float><<<(int)blocks, cv * k, (size_t)k * C * sizeof(float), (cudaStream_t)stream>>>(mode, (const float*)a, lda, (const float*)z, ldz, (float*)out, ldo, dbias, rows, C, k);
     LAUNCH_CHECK("b2_act");
 }
 

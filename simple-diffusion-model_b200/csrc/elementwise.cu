@@ -209,47 +209,60 @@ template <typename T>
 __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const float* __restrict__ stats,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ s, long long s_bstride, const T* __restrict__ res, long long ldr,
-                                   T* __restrict__ out, long long ldo, int HW, int C, int groups, float eps, int slabs, int pre_swish) {
-    extern __shared__ float sm[];
-    float* fa = sm;
-    float* fb = sm + C;
+                                   T* __restrict__ out, long long ldo, int HW, int C, int groups, float eps, int slabs,
+                                   int rows_per_block, int pre_swish) {
+    // each thread owns one 16-byte channel vector (its folded affine lives in registers) and walks the pixels of its
+    // slab with U independent 16-byte loads in flight
+    constexpr int V = Vec16<T>::N;
+    const int cv = C / V;
     const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
     const int cpg = C / groups;
     const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
+    float fa[V], fb[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = c0 + j, g = c / cpg;
         const float s1 = stats[((long long)n * groups + g) * 2], s2 = stats[((long long)n * groups + g) * 2 + 1];
         const float mean = s1 * inv_cnt;
         const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
         const float sc = s[(long long)n * s_bstride + c];
         const float ga = gamma[c] * rstd;
-        fa[c] = sc * ga;
-        fb[c] = sc * (beta[c] - ga * mean) + sc;
+        fa[j] = sc * ga;
+        fb[j] = sc * (beta[c] - ga * mean) + sc;
     }
-    __syncthreads();
-    constexpr int V = Vec16<T>::N;
-    const int cv = C / V;
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    for (int i = threadIdx.x + p0 * cv; i < p1 * cv; i += blockDim.x) {
-        const int p = i / cv, c = (i % cv) * V;
-        float v[V];
-        load16<T>(y + (base + p) * ldy + c, v);
-        if (pre_swish) {        // training: the conv stored its pre-activation z; Swish is applied here on the fly
+    constexpr int U = 4;
+    for (int pb = p0 + prow; pb < p1; pb += U * rows_per_block) {
+        float v[U][V], r[U][V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = swishf(v[j]);
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * rows_per_block;
+            if (p < p1) {
+                load16<T>(y + (base + p) * ldy + c0, v[u]);
+                if (res) load16<T>(res + (base + p) * ldr + c0, r[u]);
+            }
         }
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], fa[c + j], fb[c + j]);
-        if (res) {
-            float r[V];
-            load16<T>(res + (base + p) * ldr + c, r);
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * rows_per_block;
+            if (p < p1) {
+                if (pre_swish) {        // training: the conv stored its pre-activation z; Swish is applied here on the fly
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] += r[j];
+                    for (int j = 0; j < V; ++j) v[u][j] = swishf(v[u][j]);
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[u][j] = fmaf(v[u][j], fa[j], fb[j]);
+                if (res) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[u][j] += r[u][j];
+                }
+                store16<T>(out + (base + p) * ldo + c0, v[u]);
+            }
         }
-        store16<T>(out + (base + p) * ldo + c, v);
     }
 }
 extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, const float* gamma, const float* beta,
@@ -258,18 +271,20 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
     const int V = dtype == 0 ? 8 : 4;
     if (C % V || ldy % V || ldo % V || (residual && ldr % V)) return set_error("b2_adagn_apply: channel counts / strides must be 16-byte aligned");
     if (C % groups) return set_error("b2_adagn_apply: C %% groups != 0");
+    const int cv = C / V;
+    if (cv > 1024) return set_error("b2_adagn_apply: C too large");
     const int sms = device_sm_count();
-    int slabs = (4 * sms + N - 1) / N;
-    const int max_slabs = (HW * (C / V) + 1023) / 1024;
+    int k = 256 / cv; if (k < 1) k = 1;
+    int slabs = (8 * sms + N - 1) / N;
+    const int max_slabs = (HW + 4 * k - 1) / (4 * k);
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
-    const size_t smem = 2 * (size_t)C * sizeof(float);
     if (dtype == 0)
-        adagn_apply_kernel<bf16><<<N * slabs, 256, smem, (cudaStream_t)stream>>>((const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
-                                                                                   (const bf16*)residual, ldr, (bf16*)out, ldo, HW, C, groups, eps, slabs, pre_swish);
+        adagn_apply_kernel<bf16><<<N * slabs, cv * k, 0, (cudaStream_t)stream>>>((const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
+                                                                                  (const bf16*)residual, ldr, (bf16*)out, ldo, HW, C, groups, eps, slabs, k, pre_swish);
     else
-        adagn_apply_kernel<float><<<N * slabs, 256, smem, (cudaStream_t)stream>>>((const float*)y, ldy, stats, gamma, beta, s, s_bstride,
-                                                                                    (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs, pre_swish);
+        adagn_apply_kernel<float><<<N * slabs, cv * k, 0, (cudaStream_t)stream>>>((const float*)y, ldy, stats, gamma, beta, s, s_bstride,
+                                                                                   (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs, k, pre_swish);
     LAUNCH_CHECK("b2_adagn_apply");
 }
 
@@ -362,14 +377,21 @@ __global__ void small_gemm_kernel(const float* __restrict__ A, long long lda, in
     for (int k0 = 0; k0 < K; k0 += 32) {
         for (int i = ty; i < 32; i += 8) {
             // As[i][tx] = A[m0+i][k0+tx]
-            const int m = m0 + i, k = k0 + tx;
-            float v = 0.f;
-            if (m < M && k < K) v = ta ? A[(long long)k * lda + m] : A[(long long)m * lda + k];
-            As[i][tx] = v;
-            const int n = n0 + i;
-            float w = 0.f;
-            if (n < N && k < K) w = tb ? Bm[(long long)k * ldb + n] : Bm[(long long)n * ldb + k];
-            Bs[i][tx] = w;
+            // tx always walks the contiguous dimension of the operand in memory (coalesced either way)
+            if (ta) {
+                const int k = k0 + i, m = m0 + tx;
+                As[tx][i] = (m < M && k < K) ? A[(long long)k * lda + m] : 0.f;
+            } else {
+                const int m = m0 + i, k = k0 + tx;
+                As[i][tx] = (m < M && k < K) ? A[(long long)m * lda + k] : 0.f;
+            }
+            if (tb) {
+                const int k = k0 + i, n = n0 + tx;
+                Bs[tx][i] = (n < N && k < K) ? Bm[(long long)k * ldb + n] : 0.f;
+            } else {
+                const int n = n0 + i, k = k0 + tx;
+                Bs[i][tx] = (n < N && k < K) ? Bm[(long long)n * ldb + k] : 0.f;
+            }
         }
         __syncthreads();
 #pragma unroll

@@ -7,7 +7,10 @@ using namespace b2;
 
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  long long n, float beta1, float omb1, float beta2, float omb2, float eps, float step_size,
-                                 float inv_bc2_sqrt, float grad_scale) {
+                                 float inv_bc2_sqrt, float grad_scale, const float* __restrict__ dev_state) {
+    if (dev_state) {          // CUDA-graph mode: the step-dependent scalars come from device memory (b2_adam_flat_graph)
+        grad_scale = dev_state[2]; step_size = dev_state[3]; inv_bc2_sqrt = dev_state[4];
+    }
     const long long nv = n / 4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -45,8 +48,32 @@ extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long l
     const long long cap = 16LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale);
+    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale, nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// state[0] = steps taken so far, state[1] = learning rate, state[2] = gradient scale; this kernel advances the step and
+// derives state[3] = lr / (1 - beta1^t), state[4] = 1 / sqrt(1 - beta2^t) in double precision (torch computes them on the host).
+__global__ void adam_advance_kernel(float* state, double beta1, double beta2) {
+    const double t = (double)state[0] + 1.0;
+    state[0] = (float)t;
+    state[3] = (float)((double)state[1] / (1.0 - pow(beta1, t)));
+    state[4] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
+}
+
+extern "C" int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2,
+                                  float eps, float* state, void* stream) {
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return set_error("b2_adam_flat_graph: buffers must be 16-byte aligned");
+    if (!state) return set_error("b2_adam_flat_graph: state must be a device float[8]");
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = 16LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, 0.f, 0.f, 0.f, state);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("b2_adam_flat_graph: %s", cudaGetErrorString(e));
     return 0;
 }

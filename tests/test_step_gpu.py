@@ -80,3 +80,47 @@ def test_training_steps_match_oracle(sched_name):
     err = (num / den) ** 0.5
     print("relative error of the 3-step weight update:", err)
     assert err < 5e-2         # Adam's sign-like first steps amplify tiny gradient differences near zero crossings
+
+
+def test_graphed_train_step_equals_eager_step():
+    """CUDA-graph replay of the whole step (b200/graph.py) must train exactly like the eager kernel sequence."""
+    from b200.graph import GraphedTrainStep
+    from b200.optim import FusedAdam
+    from b200.steps import eps_prediction_step
+    from degraders import NoiseDegradation
+    from models.U_Net import U_Net
+    fx = load_golden("unet_gpu_small.pt")
+    sd0 = synth_state_dict(fx["shapes"], fx["seed"])
+    nets, opts = [], []
+    for capturable in (False, True):
+        net = U_Net(**fx["kwargs"])
+        net.load_state_dict(sd0)
+        net = net.cuda().train().set_precision("tf32")
+        net.engine().grad_layout(torch.device("cuda")).flatten_params()
+        nets.append(net)
+        opts.append(FusedAdam(net.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=capturable))
+    deg = NoiseDegradation(5e-3, 9e-3, 1000, device="cuda")
+    graphed = GraphedTrainStep(nets[1], deg, opts[1], kind="eps")
+    g = torch.Generator().manual_seed(11)
+    for step in range(4):
+        x0 = (torch.rand((2, 3, 32, 32), generator=g) * 2 - 1).cuda()
+        eps = torch.randn((2, 3, 32, 32), generator=g).cuda()
+        t = torch.randint(1, 1000, (2,), generator=g).cuda()
+        if step == 2:                       # the reference halves the learning rate on the fly (train_diffusion.py:368-371)
+            for o in opts:
+                for grp in o.param_groups:
+                    grp["lr"] *= 0.5
+        l_eager = float(eps_prediction_step(nets[0], deg, opts[0], x0, t, eps))
+        l_graph = float(graphed(x0, t, eps))
+        assert abs(l_eager - l_graph) < 1e-4 * abs(l_eager), (step, l_eager, l_graph)
+    assert graphed.replays == 4
+    # compare the accumulated 4-step update (GroupNorm sums use fp32 atomics, so not bit-identical)
+    p0 = {k: v.cuda() for k, v in sd0.items()}
+    num = den = 0.0
+    for (k, pa), (_, pb) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+        da, db = pa.detach() - p0[k], pb.detach() - p0[k]
+        num += float((da - db).double().pow(2).sum())
+        den += float(da.double().pow(2).sum())
+    assert (num / den) ** 0.5 < 2e-2
+    st = opts[1].state_dict()["state"]
+    assert float(st[0]["step"]) == 4.0

@@ -1,0 +1,165 @@
+"""Achieved HBM bandwidth of the memory-bound kernels at the shapes of the class-default U-Net (CUDA events, rotating
+buffer sets larger than the 126 MB L2 so every launch streams from HBM).  Bytes are ALGORITHMIC.
+
+    python tools/bench_membound.py [--batch 32] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "simple-diffusion-model_b200"))
+sys.path.insert(1, ROOT)
+import torch  # noqa: E402
+
+from b200 import ops  # noqa: E402
+from b200._lib import call, ptr, stream  # noqa: E402
+
+PEAK = 6552.0
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+DEV = "cuda"
+L2_BYTES = 256 << 20
+
+
+def timeit(make_args, launch, nbytes, iters=20):
+    """make_args() -> one argument set; enough sets are built that consecutive launches never hit L2."""
+    reps = max(2, min(16, L2_BYTES // max(nbytes, 1) + 1))
+    sets = [make_args() for _ in range(reps)]
+    for a in sets:
+        launch(*a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        launch(*sets[i % reps])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return ms, nbytes / ms / 1e6
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    n = args.batch
+    bf = torch.bfloat16
+    rows = []
+
+    def report(name, shape, ms, gbs):
+        rows.append({"kernel": name, "shape": shape, "ms": round(ms, 4), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / PEAK, 3)})
+        print(f"{name:28s} {shape:26s} {ms * 1e3:9.1f} us  {gbs:8.1f} GB/s  {gbs / PEAK * 100:5.1f} %", flush=True)
+
+    layers = [(128, 64), (256, 32), (512, 32), (512, 16), (1024, 16), (1024, 8), (512, 8)]
+    for c, hw in layers:
+        p = hw * hw
+        elems = n * p * c
+
+        def mk():
+            y = torch.randn((n, hw, hw, c), device=DEV, dtype=bf)
+            res = torch.randn((n, hw, hw, c), device=DEV, dtype=bf)
+            out = torch.empty_like(y)
+            stats = torch.stack([torch.zeros((n, 32), device=DEV), torch.full((n, 32), float(p * c // 32), device=DEV)], dim=-1).contiguous()
+            gamma = torch.ones(c, device=DEV)
+            beta = torch.zeros(c, device=DEV)
+            s = torch.randn((n, c), device=DEV)
+            return y, res, out, stats, gamma, beta, s
+
+        shape = f"N{n} C{c} {hw}x{hw}"
+        ms, g = timeit(mk, lambda y, res, out, st, ga, be, s: ops.adagn_apply(y, st, ga, be, s, c, out=out, pre_swish=True), elems * 4)
+        report("adagn_apply(swish)", shape, ms, g)
+        ms, g = timeit(mk, lambda y, res, out, st, ga, be, s: ops.adagn_apply(y, st, ga, be, s, c, out=out, residual=res), elems * 6)
+        report("adagn_apply(+res)", shape, ms, g)
+
+        def mk_b():
+            y, res, out, stats, gamma, beta, s = mk()
+            work = torch.empty((2 * n * c + 2 * n * 32,), device=DEV)
+            ds = torch.zeros((n, c), device=DEV)
+            dg, db, dbias = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+            return y, res, out, stats, gamma, beta, s, work, ds, dg, db, dbias
+
+        def bwd(z, dout, dz, st, ga, be, s, work, ds, dg, db, dbias):
+            call("b2_adagn_bwd", ptr(dout), c, ptr(z), c, ptr(st), ptr(ga), ptr(be), ptr(s), c, ptr(work), ptr(ds), c, ptr(dg), ptr(db),
+                 ptr(dz), c, ptr(dbias), n, p, c, 32, 1e-5, 0, stream())
+
+        ms, g = timeit(mk_b, bwd, elems * 10)
+        report("adagn_bwd(3 kernels)", shape, ms, g)
+
+        def mk_a():
+            a = torch.randn((n, hw, hw, c), device=DEV, dtype=bf)
+            z = torch.randn((n, hw, hw, c), device=DEV, dtype=bf)
+            o = torch.empty_like(a)
+            db = torch.zeros(c, device=DEV)
+            return a, z, o, db
+
+        ms, g = timeit(mk_a, lambda a, z, o, db: ops.act(0, None, z, o, None, n * p, c, 0, c, c, 0), elems * 4)
+        report("act(swish fwd)", shape, ms, g)
+        ms, g = timeit(mk_a, lambda a, z, o, db: ops.act(1, a, z, o, db, n * p, c, c, c, c, 0), elems * 6)
+        report("act(swish bwd + dbias)", shape, ms, g)
+        ms, g = timeit(mk_a, lambda a, z, o, db: ops.add(a, z, o), elems * 6)
+        report("add", shape, ms, g)
+        ms, g = timeit(mk_a, lambda a, z, o, db: ops.space_to_depth2(a), elems * 4)
+        report("space_to_depth2", shape, ms, g)
+
+    # fp32 NCHW diffusion-process kernels at the sampler batch
+    nb = 256
+    per = 3 * 64 * 64
+    tot = nb * per
+
+    def mk_d():
+        return tuple(torch.randn((nb, 3, 64, 64), device=DEV) for _ in range(4)) + (torch.randint(1, 1000, (nb,), device=DEV),)
+
+    for _ in range(2):      # tensors are small (12 MB): give the rotation enough sets
+        pass
+    ms, g = timeit(mk_d, lambda a, b, c_, d, t: call("b2_qsample", ptr(a), ptr(b), ptr(c_), ptr(t), nb, None, 1000, nb, per, stream()), tot * 12)
+    report("qsample(cosine)", f"N{nb} 3x64x64 fp32", ms, g)
+    ms, g = timeit(mk_d, lambda a, b, c_, d, t: call("b2_ddim_step", ptr(a), ptr(b), None, ptr(c_), None, tot, 1.1, 0.3, 0.9, 0.2, 0.0, 0, stream()), tot * 12)
+    report("ddim_step", f"N{nb} 3x64x64 fp32", ms, g)
+    ms, g = timeit(mk_d, lambda a, b, c_, d, t: call("b2_cold_step", ptr(a), ptr(b), ptr(c_), ptr(d), tot, 0.9, 0.1, 0.95, 0.05, stream()), tot * 16)
+    report("cold_step", f"N{nb} 3x64x64 fp32", ms, g)
+    loss = torch.zeros((), device=DEV)
+    ms, g = timeit(mk_d, lambda a, b, c_, d, t: call("b2_mse_loss_grad", ptr(a), ptr(b), ptr(c_), ptr(loss), tot, 1.0, stream()), tot * 12)
+    report("mse_loss_grad", f"N{nb} 3x64x64 fp32", ms, g)
+
+    # optimiser + weight packing on a 64 M-parameter slice (1024->1024 3x3 conv x ~7)
+    npar = 64 << 20
+
+    def mk_o():
+        return tuple(torch.randn(npar, device=DEV).abs_() for _ in range(4))
+
+    ms, g = timeit(mk_o, lambda p_, g_, m, v: call("b2_adam_flat", ptr(p_), ptr(g_), ptr(m), ptr(v), npar, 0.5, 0.999, 1e-8, 1e-4, 1.0, 1.0, stream()), npar * 28, iters=10)
+    report("adam_flat", f"{npar >> 20} Mi params", ms, g)
+
+    co = ci = 1024
+
+    def mk_w():
+        return torch.randn((co, ci, 3, 3), device=DEV), torch.empty((co, 9 * ci), device=DEV, dtype=bf), torch.empty((co, ci, 3, 3), device=DEV), torch.randn((co, 9 * ci), device=DEV)
+
+    ms, g = timeit(mk_w, lambda w, o, gr, pk: call("b2_pack_weight", 0, ptr(w), ptr(o), co, ci, ci, 0, stream()), co * ci * 9 * 6)
+    report("pack_weight(kind 0)", "1024x1024x3x3", ms, g)
+    ms, g = timeit(mk_w, lambda w, o, gr, pk: call("b2_pack_weight", 1, ptr(w), ptr(o), co, ci, ci, 0, stream()), co * ci * 9 * 6)
+    report("pack_weight(kind 1)", "1024x1024x3x3", ms, g)
+    ms, g = timeit(mk_w, lambda w, o, gr, pk: call("b2_unpack_weight_grad", 0, ptr(pk), ptr(gr), co, ci, ci, 0, stream()), co * ci * 9 * 8)
+    report("unpack_weight_grad", "1024x1024x3x3", ms, g)
+
+    # AdaGN scale-vector GEMMs (tiny FLOPs, weight-streaming): s_all = emb W^T and dW_all = ds^T emb
+    total, dim = 61440, 64
+
+    def mk_s():
+        return torch.randn((n, dim), device=DEV), torch.randn((total, dim), device=DEV), torch.randn((n, total), device=DEV), torch.zeros((total, dim), device=DEV)
+
+    ms, g = timeit(mk_s, lambda e, w, sa, dw: ops.small_gemm(e, w, n, total, dim, dim, dim, sa, total), (total * dim + n * total) * 4)
+    report("small_gemm(s_all)", f"{n}x{total}x{dim}", ms, g)
+    ms, g = timeit(mk_s, lambda e, w, sa, dw: ops.small_gemm(sa, e, total, dim, n, total, dim, dw, dim, ta=1, tb=1, accumulate=True), (2 * total * dim + n * total) * 4)
+    report("small_gemm(dW_all)", f"{total}x{dim}x{n}", ms, g)
+
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump({"hbm_peak_gbs": PEAK, "batch": n, "rows": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

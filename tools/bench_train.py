@@ -35,16 +35,23 @@ def run(args):
     torch.manual_seed(0)
     net = U_Net(cond_dim=args.cond_dim if args.cond_dim > 0 else None).to(dev).train().set_precision(args.precision)
     dp = DataParallel(net, device=dev)
-    opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), grad_scale=dp.grad_scale)
+    opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=args.graph)
     deg = NoiseDegradation(5e-3, 9e-3, 1000, device=dev)
     n, s = args.batch, args.size
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x0 = torch.rand((n, 3, s, s), device=dev, generator=gen) * 2 - 1
     labels = (torch.rand((n, args.cond_dim), device=dev, generator=gen) > 0.7).float() if args.cond_dim > 0 else None
 
+    graphed = None
+    if args.graph:
+        from b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(net, deg, opt, kind="eps")
+
     def step():
         eps = torch.randn_like(x0)
         t = torch.randint(1, 1000, (n,), device=dev)
+        if graphed is not None:
+            return graphed(x0, t, eps, labels)
         return eps_prediction_step(net, deg, opt, x0, t, eps, labels)
 
     for _ in range(args.warmup):
@@ -74,7 +81,7 @@ def run(args):
                           "ms_per_step": ms, "per_gpu_batch": n, "size": s, "precision": args.precision, "cond_dim": args.cond_dim,
                           "loss": float(loss), "model_tflops_per_gpu": flops / (ms / 1000.0) / 1e12,
                           "gpu_launches_per_step": (b2lib.LAUNCHES - l0) // args.steps, "scaling": "weak",
-                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "host_ms_per_step": wall}), flush=True)
+                          "graph": bool(args.graph), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "host_ms_per_step": wall}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -87,4 +94,5 @@ if __name__ == "__main__":
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="replay the whole step as one CUDA graph (b200/graph.py)")
     run(ap.parse_args())
