@@ -78,6 +78,9 @@ int b2_space_to_depth2(const void* x, long long ldx, void* planes, int N, int H,
  * 4 Linear -> transposed [Cin][k_pad>=Cout] (dgrad); 5 Conv2d -> [4][Cin][4 zero-padded taps][Cout] (dgrad, s2);
  * 6 ConvTranspose2d -> [Cin][16][Cout] (dgrad).  dtype 1 rounds to TF32 (nearest) so the MMA's truncation is exact. */
 int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int k_pad, int dtype, void* stream);
+/* bf16 [Cout][9][Cin] (a 3x3 weight stored channels-last, the layout of kind 0) -> [Cin][9 flipped][Cout] (kind 1):
+ * data-gradient weights derived from the optimiser's bf16 copy; Cout, Cin multiples of 64. */
+int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int Cin, void* stream);
 /* out = s*(gamma*(y-mean)*rstd+beta) + s (+residual): GroupNorm x AdaGN (custom_layers.py:35-45) fused with the
  * ResidualBlock add (custom_layers.py:282-287).  stats from b2_conv2d_nhwc; s = y_scale(emb) [B][C] with row
  * stride s_bstride (0 broadcasts one embedding over the batch, as the samplers do).  pre_swish: y holds the conv
@@ -149,15 +152,16 @@ int b2_mse_loss_grad(const float* pred, const float* target, float* grad, float*
 
 /* torch.optim.Adam (train_diffusion.py:214-218: betas (0.5, 0.999), eps 1e-8, no weight decay) over flat fp32
  * buffers: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= step_size * m / (sqrt(v) * inv_bc2_sqrt + eps), with
- * g = grad * grad_scale (1/world_size after a sum all-reduce), step_size = lr/(1-b1^t), inv_bc2_sqrt = 1/sqrt(1-b2^t). */
+ * g = grad * grad_scale (1/world_size after a sum all-reduce), step_size = lr/(1-b1^t), inv_bc2_sqrt = 1/sqrt(1-b2^t).
+ * shadow_bf16 (optional): receives bf16(p) in the same pass -- the copy the tensor-core kernels read. */
 int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
-                 float step_size, float inv_bc2_sqrt, float grad_scale, void* stream);
+                 float step_size, float inv_bc2_sqrt, float grad_scale, void* shadow_bf16, void* stream);
 
 /* CUDA-graph friendly form: `state` is a DEVICE float[8] = {steps taken, lr, grad_scale, (out) step_size, (out)
  * inv_bc2_sqrt, ...}; every call advances the step counter on the device, so a captured graph replays correctly.
  * The host changes the learning rate (train_diffusion.py:368-371) by writing state[1]. */
 int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
-                       float* state, void* stream);
+                       float* state, void* shadow_bf16, void* stream);
 
 #ifdef __cplusplus
 }

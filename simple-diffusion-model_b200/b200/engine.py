@@ -28,6 +28,21 @@ class WeightCache:
     def get(self, param, kind, code, cout, cin, cin_pad):
         key = (id(param), kind, code, cin_pad)
         lay = getattr(param, "_b2_layout", None)      # fused optimiser updates bypass torch's version counter
+        if lay is not None and code == ops.BF16 and lay.shadow is not None:
+            # training with the fused optimiser: its bf16 copy already is the kernel layout of channels-last stored
+            # 3x3 weights (kind 0) and of Linear weights (kind 3); the stride-1 data-gradient layout is one transpose away
+            if (kind == 0 and lay.is_cl(param) and cin_pad == cin) or (kind == 3 and cin_pad == cin and id(param) in lay.offsets):
+                sl = lay.shadow_slice(param)
+                return sl.view(cout, -1)
+            if kind == 1 and lay.is_cl(param) and cin_pad == cout and cout % 64 == 0:
+                ver = (param.data_ptr(), param._version, lay.epoch)
+                hit = self._packed.get(key)
+                if hit is None or hit[0] != ver:
+                    out = hit[1] if hit is not None else torch.empty((cin, 9 * cout), dtype=torch.bfloat16, device=param.device)
+                    call("b2_transpose_weight_cl", ptr(lay.shadow_slice(param)), ptr(out), cout, cin, stream())
+                    hit = (ver, out)
+                    self._packed[key] = hit
+                return hit[1]
         ver = (param.data_ptr(), param._version, lay.epoch if lay is not None else 0)
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:

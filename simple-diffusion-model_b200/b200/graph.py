@@ -88,6 +88,9 @@ class GraphedTrainStep:
                 if st and "step" in st:
                     st["step"].fill_(steps_before)
         lay.epoch += 1
+        if lay.shadow is not None:              # the bf16 copy must describe the restored weights
+            lay.shadow.copy_(lay.params_flat)
+            lay.stepped(True)
         del saved
 
     def __call__(self, x0, t, eps, labels=None, cond_img=None, target=None):
@@ -111,7 +114,7 @@ class GraphedTrainStep:
         self.replays += 1
         self.opt.note_replayed()
         lay = self.net.engine().layout
-        lay.epoch += 1                           # eager users of the weight cache (eval / sampling) must re-pack
+        lay.stepped(lay.shadow is not None)      # eager users of the weight cache (eval / sampling) must re-pack
         return s["loss"]
 
 

@@ -18,6 +18,7 @@ class FusedAdam(torch.optim.Optimizer):
         # capturable: step count / lr / grad scale live in device memory (b2_adam_flat_graph) so that a CUDA graph
         # holding step() replays correctly; b200.graph.GraphedTrainStep keeps the host-side counters in sync.
         self.capturable = capturable
+        self.bf16_shadow = True               # emit the bf16 copy of the weights the tensor-core kernels read (flat layouts)
         self._dev_state = {}                  # id(layout) -> device float[8]
         self._dev_lr = {}
 
@@ -48,11 +49,12 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] += 1
 
     @staticmethod
-    def _launch(p, g, m, v, n, group, step, grad_scale):
+    def _launch(p, g, m, v, n, group, step, grad_scale, shadow=None):
         b1, b2 = group["betas"]
         step_size = group["lr"] / (1.0 - b1 ** step)
         inv_bc2_sqrt = 1.0 / math.sqrt(1.0 - b2 ** step)
-        call("b2_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), n, b1, b2, group["eps"], step_size, inv_bc2_sqrt, grad_scale, stream())
+        call("b2_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), n, b1, b2, group["eps"], step_size, inv_bc2_sqrt, grad_scale,
+             ptr(shadow), stream())
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -80,14 +82,16 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] += 1
                     if id(lay) not in done_layouts:
                         done_layouts.add(id(lay))
+                        shadow = lay.ensure_shadow() if self.bf16_shadow else None
                         if self.capturable:
                             b1, b2 = group["betas"]
                             dev = self.device_state(lay, group)
                             call("b2_adam_flat_graph", ptr(lay.params_flat), ptr(lay.flat), ptr(m_flat), ptr(v_flat), lay.total,
-                                 float(b1), float(b2), group["eps"], ptr(dev), stream())
+                                 float(b1), float(b2), group["eps"], ptr(dev), ptr(shadow), stream())
                         else:
-                            self._launch(lay.params_flat, lay.flat, m_flat, v_flat, lay.total, group, int(st["step"]), self.grad_scale)
-                        lay.epoch += 1          # cached kernel-layout weights are stale now
+                            self._launch(lay.params_flat, lay.flat, m_flat, v_flat, lay.total, group, int(st["step"]),
+                                         self.grad_scale, shadow)
+                        lay.stepped(shadow is not None)          # cached kernel-layout weights are stale now
                     continue
                 if not st:
                     st["step"] = torch.tensor(0.0)
@@ -98,4 +102,6 @@ class FusedAdam(torch.optim.Optimizer):
                 if (p.data_ptr() | g.data_ptr()) % 16 or not p.is_contiguous():
                     raise RuntimeError("FusedAdam needs 16-byte aligned contiguous fp32 parameters")
                 self._launch(p, g, st["exp_avg"], st["exp_avg_sq"], p.numel(), group, int(st["step"]), self.grad_scale)
+                if lay is not None:
+                    lay.epoch += 1
         return loss

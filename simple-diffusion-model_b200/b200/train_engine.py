@@ -24,10 +24,22 @@ def _is_dead(name):
 class GradLayout:
     """Flat fp32 gradient buffer in bucket order: AdaGN scale weights, AdaGN scale biases (each contiguous so the
     batched scale-vector GEMM writes them in place), then every other live parameter in reverse execution order
-    (out_layers -> up -> middle -> down -> in_layer -> embedding), the order in which backward completes them."""
+    (out_layers -> up -> middle -> down -> in_layer -> embedding), the order in which backward completes them.
+
+    3x3 Conv2d weights whose channel counts fill whole 128-byte K blocks are STORED channels-last
+    ([Cout][3][3][Cin] == the tensor-core kernels' [Cout][tap][Cin] layout); the nn.Parameter keeps the reference's
+    shape [Cout][Cin][3][3] as a permuted view, so state_dicts interchange.  With that storage
+      * the weight-gradient GEMM writes straight into the flat gradient buffer (no scratch, no unpack pass),
+      * the forward weights are a plain bf16 cast of the master copy, which the fused Adam emits in the same pass
+        (`shadow`), so no per-step weight packing remains on the forward path."""
 
     def __init__(self, net, device):
+        import torch.nn as nn
         from models.custom_layers import AdaGN
+        self.cl = {}          # id(param) -> (Cout, Cin) for channels-last stored 3x3 conv weights
+        for m in net.modules():
+            if isinstance(m, nn.Conv2d) and tuple(m.kernel_size) == (3, 3) and m.weight.shape[1] % 64 == 0:
+                self.cl[id(m.weight)] = (m.weight.shape[0], m.weight.shape[1])
         named = [(n, p) for n, p in net.named_parameters() if not _is_dead(n) and p.requires_grad]
         adagn = [m for m in net.modules() if isinstance(m, AdaGN)]
         ys_w = [m.y_scale.weight for m in adagn]
@@ -57,8 +69,11 @@ class GradLayout:
         self.total = off
         self.front_end = sum((p.numel() + 3) // 4 * 4 for p in ys_w + ys_b)
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
-        self.views = {id(p): self.flat[self.offsets[id(p)]:self.offsets[id(p)] + p.numel()].view(p.shape) for p in self.params}
+        self.views = {id(p): self._shaped(self.flat, p) for p in self.params}
         self.params_flat = None
+        self.shadow = None                     # bf16 copy of params_flat (same offsets), maintained by FusedAdam
+        self.shadow_key = {}                   # id(p) -> (p._version, epoch) for which the shadow slice is current
+        self.shadow_bulk_epoch = -1            # epoch at which a fused optimiser pass rewrote the whole shadow
         self.epoch = 0                         # bumped by FusedAdam.step(): invalidates cached kernel-layout weights
         for p in self.params:
             p._b2_layout = self
@@ -67,8 +82,54 @@ class GradLayout:
         # y_scale weights have numel % 4 == 0 whenever C % 4 == 0, so the concatenated views are dense
         self.dense_adagn = all(p.numel() % 4 == 0 for p in ys_w + ys_b)
 
+    def _shaped(self, flat, p):
+        """The slice of `flat` that belongs to p, shaped like p (a permuted view for channels-last stored weights)."""
+        off = self.offsets[id(p)]
+        raw = flat[off:off + p.numel()]
+        if id(p) in self.cl:
+            cout, cin = self.cl[id(p)]
+            return raw.view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        return raw.view(p.shape)
+
     def view(self, p):
         return self.views[id(p)]
+
+    def raw_grad(self, p):
+        """Gradient storage of p as the flat slice (kernel layout for channels-last weights)."""
+        off = self.offsets[id(p)]
+        return self.flat[off:off + p.numel()]
+
+    def is_cl(self, p):
+        return id(p) in self.cl
+
+    def shadow_slice(self, p):
+        """Current bf16 copy of p in storage layout, or None when no fused optimiser maintains one.  A slice that went
+        stale (load_state_dict, a non-fused optimiser) is refreshed from the fp32 master with one cast."""
+        if self.shadow is None or self.params_flat is None:
+            return None
+        off = self.offsets[id(p)]
+        sl = self.shadow[off:off + p.numel()]
+        key = self.shadow_key.get(id(p))
+        fresh = key is not None and key[0] == p._version and (key[1] == self.epoch or self.shadow_bulk_epoch == self.epoch)
+        if not fresh:
+            sl.copy_(self.params_flat[off:off + p.numel()])
+            self.shadow_key[id(p)] = (p._version, self.epoch)
+        return sl
+
+    def stepped(self, shadow_written):
+        """A fused optimiser pass changed every parameter (bypassing torch's version counters)."""
+        self.epoch += 1
+        if shadow_written:
+            self.shadow_bulk_epoch = self.epoch
+            if not self.shadow_key:
+                self.shadow_key = {id(p): (p._version, self.epoch) for p in self.params}
+
+    def ensure_shadow(self):
+        if self.shadow is None and self.params_flat is not None:
+            self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=self.flat.device)
+            self.shadow.copy_(self.params_flat)
+            self.shadow_key = {id(p): (p._version, self.epoch) for p in self.params}
+        return self.shadow
 
     def module_range(self, module):
         """Flat range covered by a module's live parameters, AdaGN scale Linears excluded (they live in the front
@@ -86,8 +147,7 @@ class GradLayout:
             flat = torch.zeros(self.total, dtype=torch.float32, device=self.flat.device)
             self.pviews = {}
             for p in self.params:
-                off = self.offsets[id(p)]
-                v = flat[off:off + p.numel()].view(p.shape)
+                v = self._shaped(flat, p)
                 v.copy_(p.data)
                 p.data = v
                 self.pviews[id(p)] = v
@@ -328,6 +388,10 @@ class UNetTrainEngine(UNetEngine):
             return
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
         cin_pad = x.shape[3]
+        if self.layout.is_cl(conv.weight) and cin_pad == cin:
+            # channels-last stored weight: the flat gradient slice IS the kernel layout (zeroed at the start of backward)
+            ops.conv2d_wgrad(mode, x, dz, cout, self.layout.raw_grad(conv.weight))
+            return
         packed = self._scratch(cout * 9 * cin_pad, x.device)
         ops.conv2d_wgrad(mode, x, dz, cout, packed)
         call("b2_unpack_weight_grad", 0, ptr(packed), ptr(self.layout.view(conv.weight)), cout, cin, cin_pad, 0, stream())

@@ -3,6 +3,7 @@
 // softmax backward, column sums, and the kernel-layout -> parameter-layout gradient unpack.
 #include "host_util.h"
 #include "ptx.cuh"
+#include "stream.cuh"
 #include "sdm_b200.h"
 
 using namespace b2;
@@ -15,31 +16,10 @@ typedef __nv_bfloat16 bf16;
         return 0;                                                                                 \
     } while (0)
 
-template <typename T> struct V16 { static constexpr int N = 16 / sizeof(T); };
 template <typename T>
-__device__ __forceinline__ void ld16(const T* p, float (&f)[V16<T>::N]) {
-    uint4 u = *reinterpret_cast<const uint4*>(p);
-    if constexpr (sizeof(T) == 4) {
-        f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
-    } else {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-    }
-}
+__device__ __forceinline__ void ld16(const T* p, float (&f)[V16<T>::N]) { unpack16<T>(*reinterpret_cast<const uint4*>(p), f); }
 template <typename T>
-__device__ __forceinline__ void st16(T* p, const float (&f)[V16<T>::N]) {
-    uint4 u;
-    if constexpr (sizeof(T) == 4) {
-        u.x = __float_as_uint(round_tf32(f[0])); u.y = __float_as_uint(round_tf32(f[1]));
-        u.z = __float_as_uint(round_tf32(f[2])); u.w = __float_as_uint(round_tf32(f[3]));
-    } else {
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    }
-    *reinterpret_cast<uint4*>(p) = u;
-}
+__device__ __forceinline__ void st16(T* p, const float (&f)[V16<T>::N]) { stg16(p, pack16<T>(f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float swish_grad(float z) { const float s = sigmoidf_(z); return s * (1.0f + z * (1.0f - s)); }
 
@@ -100,26 +80,33 @@ __global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ld
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    constexpr int U = 4;                 // independent 16-byte loads in flight per thread
-    for (int pb = p0 + prow; pb < p1; pb += U * rows_per_block) {
-        float d[U][V], zz[U][V];
+    constexpr int U = 2;
+    constexpr bool kFast = sizeof(T) == 2;
+    struct Buf { uint4 d[U], z[U]; };
+    const long long k = rows_per_block;
+    auto load = [&](Buf& b, long long p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int p = pb + u * rows_per_block;
-            if (p < p1) { ld16<T>(dout + (base + p) * ldd + c0, d[u]); ld16<T>(z + (base + p) * ldz + c0, zz[u]); }
-            else {
+            const long long q = p + u * k;
+            if (q < p1) { b.d[u] = ldg16(dout + (base + q) * ldd + c0); b.z[u] = ldg16(z + (base + q) * ldz + c0); }
+        }
+    };
+    auto proc = [&](Buf& b, long long p) {
 #pragma unroll
-                for (int j = 0; j < V; ++j) { d[u][j] = 0.f; zz[u][j] = 0.f; }
+        for (int u = 0; u < U; ++u) {
+            if (p + u * k < p1) {
+                float d[V], zz[V];
+                unpack16<T>(b.d[u], d);
+                unpack16<T>(b.z[u], zz);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float xh = (swish_t<kFast>(zz[j]) - mean[j]) * rstd[j];
+                    s1[j] += d[j]; s2[j] = fmaf(d[j], xh, s2[j]);
+                }
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const float xh = (swishf(zz[u][j]) - mean[j]) * rstd[j];
-                s1[j] += d[u][j]; s2[j] = fmaf(d[u][j], xh, s2[j]);
-            }
-    }
+    };
+    pipelined_rows<Buf>(p0 + prow, p1, U * k, load, proc);
     extern __shared__ float red[];
     block_colsum_atomic<V>(s1, red, C, c0, prow, rows_per_block, a1 + (long long)n * C);
     block_colsum_atomic<V>(s2, red, C, c0, prow, rows_per_block, a2 + (long long)n * C);
@@ -177,32 +164,39 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    constexpr int U = 4;
-    for (int pb = p0 + prow; pb < p1; pb += U * rows_per_block) {
-        float d[U][V], zz[U][V];
+    constexpr int U = 2;
+    constexpr bool kFast = sizeof(T) == 2;
+    struct Buf { uint4 d[U], z[U]; };
+    const long long k = rows_per_block;
+    auto load = [&](Buf& b, long long p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int p = pb + u * rows_per_block;
-            if (p < p1) { ld16<T>(dout + (base + p) * ldd + c0, d[u]); ld16<T>(z + (base + p) * ldz + c0, zz[u]); }
+            const long long q = p + u * k;
+            if (q < p1) { b.d[u] = ldg16(dout + (base + q) * ldd + c0); b.z[u] = ldg16(z + (base + q) * ldz + c0); }
         }
+    };
+    auto proc = [&](Buf& b, long long p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int p = pb + u * rows_per_block;
-            if (p < p1) {
-                float o[V];
+            const long long q = p + u * k;
+            if (q < p1) {
+                float d[V], zz[V], o[V];
+                unpack16<T>(b.d[u], d);
+                unpack16<T>(b.z[u], zz);
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    const float zv = zz[u][j];
-                    const float sig = sigmoidf_(zv);
+                    const float zv = zz[j];
+                    const float sig = sigmoid_t<kFast>(zv);
                     const float xh = (zv * sig - mean[j]) * rstd[j];
-                    const float dy = rstd[j] * (sg[j] * d[u][j] - m1[j] - xh * m2[j]);
+                    const float dy = rstd[j] * (sg[j] * d[j] - m1[j] - xh * m2[j]);
                     o[j] = dy * (sig * (1.0f + zv * (1.0f - sig)));
                     db[j] += o[j];
                 }
-                st16<T>(dz + (base + p) * lddz + c0, o);
+                stg16(dz + (base + q) * lddz + c0, pack16<T>(o));
             }
         }
-    }
+    };
+    pipelined_rows<Buf>(p0 + prow, p1, U * k, load, proc);
     if (dbias) {
         extern __shared__ float red[];
         block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
@@ -252,38 +246,50 @@ __global__ void act_kernel(int mode, const T* __restrict__ a, long long lda, con
     float db[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) db[j] = 0.f;
-    constexpr int U = 4;
+    constexpr int U = 2;
+    constexpr bool kFast = sizeof(T) == 2;
+    struct Buf { uint4 a[U], z[U]; };
     const long long stride = (long long)gridDim.x * rows_per_block;
-    for (long long rb = (long long)blockIdx.x * rows_per_block + prow; rb < rows; rb += U * stride) {
-        float x[U][V], zz[U][V];
+    auto load = [&](Buf& b, long long r0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long r = rb + u * stride;
+            const long long r = r0 + u * stride;
             if (r < rows) {
-                if (mode != 0) ld16<T>(a + r * lda + c0, x[u]);
-                if (mode != 2) ld16<T>(z + r * ldz + c0, zz[u]);
+                if (mode != 0) b.a[u] = ldg16(a + r * lda + c0);
+                if (mode != 2) b.z[u] = ldg16(z + r * ldz + c0);
             }
         }
+    };
+    auto proc = [&](Buf& b, long long r0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long r = rb + u * stride;
+            const long long r = r0 + u * stride;
             if (r < rows) {
-                float o[V];
+                float x[V], zz[V], o[V];
                 if (mode == 0) {
+                    unpack16<T>(b.z[u], zz);
 #pragma unroll
-                    for (int j = 0; j < V; ++j) o[j] = swishf(zz[u][j]);
-                    st16<T>(out + r * ldo + c0, o);
+                    for (int j = 0; j < V; ++j) o[j] = swish_t<kFast>(zz[j]);
+                    stg16(out + r * ldo + c0, pack16<T>(o));
                 } else if (mode == 1) {
+                    unpack16<T>(b.a[u], x);
+                    unpack16<T>(b.z[u], zz);
 #pragma unroll
-                    for (int j = 0; j < V; ++j) { o[j] = x[u][j] * swish_grad(zz[u][j]); db[j] += o[j]; }
-                    st16<T>(out + r * ldo + c0, o);
+                    for (int j = 0; j < V; ++j) {
+                        const float sig = sigmoid_t<kFast>(zz[j]);
+                        o[j] = x[j] * (sig * (1.0f + zz[j] * (1.0f - sig)));
+                        db[j] += o[j];
+                    }
+                    stg16(out + r * ldo + c0, pack16<T>(o));
                 } else {
+                    unpack16<T>(b.a[u], x);
 #pragma unroll
-                    for (int j = 0; j < V; ++j) db[j] += x[u][j];
+                    for (int j = 0; j < V; ++j) db[j] += x[j];
                 }
             }
         }
-    }
+    };
+    pipelined_rows<Buf>((long long)blockIdx.x * rows_per_block + prow, rows, U * stride, load, proc);
     if (dbias && mode != 0) {
         extern __shared__ float red[];
         block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);

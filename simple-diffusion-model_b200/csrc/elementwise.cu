@@ -3,6 +3,7 @@
 // (16-byte accesses where the layout allows) and sized in multiples of the SM count.
 #include "host_util.h"
 #include "ptx.cuh"
+#include "stream.cuh"
 #include "sdm_b200.h"
 
 using namespace b2;
@@ -201,6 +202,38 @@ extern "C" int b2_pack_weight(int kind, const float* w, void* out, int Cout, int
     LAUNCH_CHECK("b2_pack_weight");
 }
 
+// Data-gradient weights of a 3x3/s1 conv straight from the bf16 "channels-last" copy the optimiser maintains:
+// in [Cout][9][Cin] -> out [Cin][9 flipped][Cout].  64x64 tiles through shared memory, 128-byte rows on both sides.
+__global__ void transpose_weight_cl_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int Cout, int Cin) {
+    __shared__ bf16 tile[64][64 + 8];
+    const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
+    const int t = threadIdx.x;                       // 256 threads
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t + i * 256;                 // 512 16-byte vectors: 64 rows (co) x 8
+        const int r = idx >> 3, v = idx & 7;
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * 9 + tap) * Cin + ci0 + v * 8));
+        *reinterpret_cast<uint4*>(&tile[r][v * 8]) = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t + i * 256;                 // output rows (ci) x 8 vectors of 8 co
+        const int r = idx >> 3, v = idx & 7;
+        uint4 x;
+        bf16* e = reinterpret_cast<bf16*>(&x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = tile[v * 8 + j][r];
+        *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * 9 + (8 - tap)) * Cout + co0 + v * 8) = x;
+    }
+}
+extern "C" int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int Cin, void* stream) {
+    if (Cout % 64 || Cin % 64) return set_error("b2_transpose_weight_cl: Cout and Cin must be multiples of 64");
+    dim3 grid(Cin / 64, Cout / 64, 9);
+    transpose_weight_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)w_cl, (bf16*)out, Cout, Cin);
+    LAUNCH_CHECK("b2_transpose_weight_cl");
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm x AdaGN apply
 // out = s * (gamma * (y - mean) * rstd + beta) + s  (+ residual)        [custom_layers.py:35-45, :282-287]
 // stats = per-(image, group) (sum, sum of squares) produced by the conv epilogue.  One CTA streams a slab of
@@ -213,7 +246,7 @@ __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const
                                    int rows_per_block, int pre_swish) {
     // each thread owns one 16-byte channel vector (its folded affine lives in registers) and walks the pixels of its
     // slab with U independent 16-byte loads in flight
-    constexpr int V = Vec16<T>::N;
+    constexpr int V = V16<T>::N;
     const int cv = C / V;
     const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
     const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
@@ -235,35 +268,44 @@ __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    constexpr int U = 4;
-    for (int pb = p0 + prow; pb < p1; pb += U * rows_per_block) {
-        float v[U][V], r[U][V];
+    constexpr int U = 2;
+    constexpr bool kFast = sizeof(T) == 2;
+    struct Buf { uint4 y[U], r[U]; };
+    const long long k = rows_per_block;
+    auto load = [&](Buf& b, long long p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int p = pb + u * rows_per_block;
-            if (p < p1) {
-                load16<T>(y + (base + p) * ldy + c0, v[u]);
-                if (res) load16<T>(res + (base + p) * ldr + c0, r[u]);
+            const long long q = p + u * k;
+            if (q < p1) {
+                b.y[u] = ldg16(y + (base + q) * ldy + c0);
+                if (res) b.r[u] = ldg16(res + (base + q) * ldr + c0);
             }
         }
+    };
+    auto proc = [&](Buf& b, long long p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int p = pb + u * rows_per_block;
-            if (p < p1) {
+            const long long q = p + u * k;
+            if (q < p1) {
+                float v[V];
+                unpack16<T>(b.y[u], v);
                 if (pre_swish) {        // training: the conv stored its pre-activation z; Swish is applied here on the fly
 #pragma unroll
-                    for (int j = 0; j < V; ++j) v[u][j] = swishf(v[u][j]);
+                    for (int j = 0; j < V; ++j) v[j] = swish_t<kFast>(v[j]);
                 }
 #pragma unroll
-                for (int j = 0; j < V; ++j) v[u][j] = fmaf(v[u][j], fa[j], fb[j]);
+                for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], fa[j], fb[j]);
                 if (res) {
+                    float r[V];
+                    unpack16<T>(b.r[u], r);
 #pragma unroll
-                    for (int j = 0; j < V; ++j) v[u][j] += r[u][j];
+                    for (int j = 0; j < V; ++j) v[j] += r[j];
                 }
-                store16<T>(out + (base + p) * ldo + c0, v[u]);
+                stg16(out + (base + q) * ldo + c0, pack16<T>(v));
             }
         }
-    }
+    };
+    pipelined_rows<Buf>(p0 + prow, p1, U * k, load, proc);
 }
 extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, const float* gamma, const float* beta,
                               const float* s, long long s_bstride, const void* residual, long long ldr, void* out,
@@ -369,28 +411,32 @@ extern "C" int b2_sinusoid_embedding(const long long* t, float* out, int B, int 
 //   C[M][N] (+)= op(A) . op(B) (+ bias[N]) (Swish).  ta: A is [K][M]; tb == 0: B is [N][K] (Linear weight), tb == 1: B is [K][N].
 __global__ void small_gemm_kernel(const float* __restrict__ A, long long lda, int ta, const float* __restrict__ Bm, long long ldb, int tb,
                                   float* __restrict__ C, long long ldc, int M, int N, int K, const float* __restrict__ bias, int act,
-                                  int accumulate) {
+                                  int accumulate, int k_per_split) {
     __shared__ float As[32][33], Bs[32][33];
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < K; k0 += 32) {
+    // split-K (gridDim.z > 1): each z-slice reduces its K range and adds atomically into a zeroed / accumulated C
+    const int k_begin = blockIdx.z * k_per_split;
+    const int k_end = min(K, k_begin + k_per_split);
+    const bool split = gridDim.z > 1;
+    for (int k0 = k_begin; k0 < k_end; k0 += 32) {
         for (int i = ty; i < 32; i += 8) {
             // As[i][tx] = A[m0+i][k0+tx]
             // tx always walks the contiguous dimension of the operand in memory (coalesced either way)
             if (ta) {
                 const int k = k0 + i, m = m0 + tx;
-                As[tx][i] = (m < M && k < K) ? A[(long long)k * lda + m] : 0.f;
+                As[tx][i] = (m < M && k < k_end) ? A[(long long)k * lda + m] : 0.f;
             } else {
                 const int m = m0 + i, k = k0 + tx;
-                As[i][tx] = (m < M && k < K) ? A[(long long)m * lda + k] : 0.f;
+                As[i][tx] = (m < M && k < k_end) ? A[(long long)m * lda + k] : 0.f;
             }
             if (tb) {
                 const int k = k0 + i, n = n0 + tx;
-                Bs[tx][i] = (n < N && k < K) ? Bm[(long long)k * ldb + n] : 0.f;
+                Bs[tx][i] = (n < N && k < k_end) ? Bm[(long long)k * ldb + n] : 0.f;
             } else {
                 const int n = n0 + i, k = k0 + tx;
-                Bs[i][tx] = (n < N && k < K) ? Bm[(long long)n * ldb + k] : 0.f;
+                Bs[i][tx] = (n < N && k < k_end) ? Bm[(long long)n * ldb + k] : 0.f;
             }
         }
         __syncthreads();
@@ -408,9 +454,10 @@ __global__ void small_gemm_kernel(const float* __restrict__ A, long long lda, in
         for (int r = 0; r < 4; ++r) {
             const int m = m0 + ty + 8 * r;
             if (m < M) {
-                float v = acc[r] + (bias ? bias[n] : 0.f);
-                if (act == 1) v = swishf(v);
+                float v = acc[r] + ((bias && blockIdx.z == 0) ? bias[n] : 0.f);
                 float* o = C + (long long)m * ldc + n;
+                if (split) { atomicAdd(o, v); continue; }
+                if (act == 1) v = swishf(v);
                 *o = accumulate ? (*o + v) : v;
             }
         }
@@ -419,6 +466,22 @@ __global__ void small_gemm_kernel(const float* __restrict__ A, long long lda, in
 extern "C" int b2_small_gemm(const float* A, long long lda, int ta, const float* B, long long ldb, int tb, float* C, long long ldc,
                              int M, int N, int K, const float* bias, int act, int accumulate, void* stream) {
     dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
-    small_gemm_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, bias, act, accumulate);
+    // long contractions with a tiny output (d emb = ds_all . W_all: K = sum of all AdaGN widths) would run on a couple of
+    // CTAs: split K across the grid instead
+    int splits = 1;
+    const long long tiles = (long long)grid.x * grid.y;
+    if (act == 0 && K >= 2048 && tiles < 2LL * device_sm_count()) {
+        splits = (int)((2LL * device_sm_count() + tiles - 1) / tiles);
+        const int max_splits = (K + 255) / 256;
+        if (splits > max_splits) splits = max_splits;
+    }
+    int k_per_split = (((K + splits - 1) / splits) + 31) / 32 * 32;
+    splits = (K + k_per_split - 1) / k_per_split;
+    if (splits > 1 && !accumulate) {
+        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, (cudaStream_t)stream);
+        if (e != cudaSuccess) return set_error("b2_small_gemm: memset: %s", cudaGetErrorString(e));
+    }
+    grid.z = splits;
+    small_gemm_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, bias, act, accumulate, k_per_split);
     LAUNCH_CHECK("b2_small_gemm");
 }

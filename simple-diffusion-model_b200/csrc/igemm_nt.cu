@@ -227,7 +227,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (p.act == 1) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = swishf(v[i]);
+                    for (int i = 0; i < 32; ++i) v[i] = swish_t<!kTF32>(v[i]);
                 } else if (p.act == 2) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
@@ -238,7 +238,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (p.act == 3) {       // training: store the pre-activation, normalise Swish(z) later -> stats of Swish(z)
                         float sw[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) sw[i] = swishf(v[i]);
+                        for (int i = 0; i < 32; ++i) sw[i] = swish_t<!kTF32>(v[i]);
                         if (cpg >= 32)      gn_partial<32>(sw, valid, uniform, lane, srow, col0 / cpg);
                         else if (cpg == 16) gn_partial<16>(sw, valid, uniform, lane, srow, col0 / 16);
                         else if (cpg == 8)  gn_partial<8>(sw, valid, uniform, lane, srow, col0 / 8);

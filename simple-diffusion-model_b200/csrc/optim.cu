@@ -2,12 +2,14 @@
 // 28 bytes per parameter instead of torch's multi-tensor foreach over ~760 tensors (train_diffusion.py:214-218,361).
 #include "host_util.h"
 #include "sdm_b200.h"
+#include <cuda_bf16.h>
 
 using namespace b2;
 
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  long long n, float beta1, float omb1, float beta2, float omb2, float eps, float step_size,
-                                 float inv_bc2_sqrt, float grad_scale, const float* __restrict__ dev_state) {
+                                 float inv_bc2_sqrt, float grad_scale, const float* __restrict__ dev_state,
+                                 __nv_bfloat16* __restrict__ shadow) {
     if (dev_state) {          // CUDA-graph mode: the step-dependent scalars come from device memory (b2_adam_flat_graph)
         grad_scale = dev_state[2]; step_size = dev_state[3]; inv_bc2_sqrt = dev_state[4];
     }
@@ -28,6 +30,12 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
             pa[j] -= step_size * (ma[j] / denom);
         }
         reinterpret_cast<float4*>(p)[i] = pp;
+        if (shadow) {           // bf16 copy consumed by the tensor-core kernels: saves a separate cast pass over the weights
+            uint2 sh;
+            *reinterpret_cast<__nv_bfloat162*>(&sh.x) = __floats2bfloat162_rn(pp.x, pp.y);
+            *reinterpret_cast<__nv_bfloat162*>(&sh.y) = __floats2bfloat162_rn(pp.z, pp.w);
+            reinterpret_cast<uint2*>(shadow)[i] = sh;
+        }
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
     }
@@ -36,19 +44,20 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
         m[i] = beta1 * m[i] + omb1 * gr;
         v[i] = beta2 * v[i] + omb2 * (gr * gr);
         p[i] -= step_size * (m[i] / (sqrtf(v[i]) * inv_bc2_sqrt + eps));
+        if (shadow) shadow[i] = __float2bfloat16(p[i]);
     }
 }
 
 // betas arrive as doubles so that 1 - beta is rounded once, like torch's Python-side scalar (1 - 0.999f != 0.001f).
 // step_size = lr / (1 - beta1^t), inv_bc2_sqrt = 1 / sqrt(1 - beta2^t)  (torch.optim.Adam's formulation).
 extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
-                            float step_size, float inv_bc2_sqrt, float grad_scale, void* stream) {
-    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return set_error("b2_adam_flat: buffers must be 16-byte aligned");
+                            float step_size, float inv_bc2_sqrt, float grad_scale, void* shadow_bf16, void* stream) {
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)shadow_bf16) & 15) return set_error("b2_adam_flat: buffers must be 16-byte aligned");
     long long blocks = (n / 4 + 255) / 256;
     const long long cap = 16LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale, nullptr);
+    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale, nullptr, (__nv_bfloat16*)shadow_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat: %s", cudaGetErrorString(e));
     return 0;
@@ -64,7 +73,7 @@ __global__ void adam_advance_kernel(float* state, double beta1, double beta2) {
 }
 
 extern "C" int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2,
-                                  float eps, float* state, void* stream) {
+                                  float eps, float* state, void* shadow_bf16, void* stream) {
     if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return set_error("b2_adam_flat_graph: buffers must be 16-byte aligned");
     if (!state) return set_error("b2_adam_flat_graph: state must be a device float[8]");
     long long blocks = (n / 4 + 255) / 256;
@@ -72,7 +81,7 @@ extern "C" int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
-    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, 0.f, 0.f, 0.f, state);
+    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, 0.f, 0.f, 0.f, state, (__nv_bfloat16*)shadow_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat_graph: %s", cudaGetErrorString(e));
     return 0;

@@ -133,4 +133,18 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 __device__ __forceinline__ float swishf(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// One-MUFU forms used by the bf16 kernels: sigmoid(x) = 0.5 + 0.5 tanh(x/2) with tanh.approx.f32 (max relative error
+// 2^-11, below bf16 resolution); the exp/rcp forms above (two MUFU ops) stay in the fp32/TF32 parity path.
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float swish_fast(float x) { const float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
+template <bool kFast> __device__ __forceinline__ float swish_t(float x) { return kFast ? swish_fast(x) : swishf(x); }
+template <bool kFast> __device__ __forceinline__ float sigmoid_t(float x) {
+    return kFast ? sigmoid_fast(x) : __fdividef(1.0f, 1.0f + __expf(-x));
+}
+
 }  // namespace b2

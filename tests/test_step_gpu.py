@@ -124,3 +124,49 @@ def test_graphed_train_step_equals_eager_step():
     assert (num / den) ** 0.5 < 2e-2
     st = opts[1].state_dict()["state"]
     assert float(st[0]["step"]) == 4.0
+
+
+def test_bf16_shadow_weights_equal_packed_weights():
+    """FusedAdam's bf16 copy of the channels-last stored weights (+ the transposing data-gradient pack) must train like
+    the plain path that re-packs every kernel-layout weight from the fp32 masters (torch.optim.Adam: no shadow)."""
+    from b200.optim import FusedAdam
+    from b200.steps import eps_prediction_step
+    from degraders import NoiseDegradation
+    from models.U_Net import U_Net
+    fx = load_golden("unet_gpu_small.pt")
+    sd0 = synth_state_dict(fx["shapes"], fx["seed"])
+    nets, opts = [], []
+    for fused in (True, False):
+        net = U_Net(**fx["kwargs"])
+        net.load_state_dict(sd0)
+        net = net.cuda().train().set_precision("bf16")
+        net.engine().grad_layout(torch.device("cuda")).flatten_params()
+        nets.append(net)
+        live = [p for n_, p in net.named_parameters() if ".y_shift." not in n_ and not (".attn_layers." in n_ and ".norm." in n_)]
+        opts.append(FusedAdam(net.parameters(), lr=2e-4, betas=(0.5, 0.999)) if fused
+                    else torch.optim.Adam(live, lr=2e-4, betas=(0.5, 0.999)))
+    deg = NoiseDegradation(5e-3, 9e-3, 1000, device="cuda")
+    g = torch.Generator().manual_seed(3)
+    for step in range(3):
+        x0 = (torch.rand((2, 3, 32, 32), generator=g) * 2 - 1).cuda()
+        eps = torch.randn((2, 3, 32, 32), generator=g).cuda()
+        t = torch.randint(1, 1000, (2,), generator=g).cuda()
+        la = float(eps_prediction_step(nets[0], deg, opts[0], x0, t, eps))
+        lb = float(eps_prediction_step(nets[1], deg, opts[1], x0, t, eps))
+        assert abs(la - lb) < 3e-3 * abs(lb), (step, la, lb)
+    lay = nets[0].engine().layout
+    assert lay.shadow is not None and len(lay.cl) > 0
+    # the shadow is exactly bf16(master) and the permuted parameter views still have the reference's shapes
+    assert torch.equal(lay.shadow, lay.params_flat.to(torch.bfloat16))
+    for k, v in nets[0].state_dict().items():
+        assert tuple(v.shape) == tuple(sd0[k].shape)
+    # eval after training reads the same (current) weights through the cache
+    nets[0].eval()
+    with torch.no_grad():
+        x = (torch.rand((2, 3, 32, 32), generator=g) * 2 - 1).cuda()
+        tt = torch.tensor([5, 700]).cuda()
+        y_shadow = nets[0](x, tt)
+        lay.shadow = None
+        nets[0].engine().cache.clear()
+        y_packed = nets[0](x, tt)
+    assert rel_l2(y_shadow, y_packed) < 1e-6
