@@ -26,6 +26,7 @@ import torch  # noqa: E402
 METRIC = "ddim50_sampled_images_per_s"
 UNIT = "img/s"
 IMG, BATCH, STEP_SIZE, T_MAX = 64, 256, 20, 1000
+TRAIN_IMG, TRAIN_BATCH, TRAIN_COND = 128, 16, 10        # BASELINE.json configs[2]: 128x128 label-conditioned, bf16, DP
 
 
 def load_peaks():
@@ -157,6 +158,97 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ---------------------------------------------------------------------------------------------------- train-step leg
+def cpu_reference_train(threads, batch=2, img=64):
+    """Bounded CPU sample of the reference train step (oracle port): forward + autograd backward + torch Adam at 64x64."""
+    from oracle import diffusion_oracle as orc
+    from oracle.weights import synth_state_dict
+    from models.U_Net import U_Net
+    torch.set_num_threads(threads)
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in U_Net().state_dict().items()}
+    sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(shapes, 0).items()}
+    live = [v for k, v in sd.items() if ".y_shift." not in k and not (".attn_layers." in k and ".norm." in k)]
+    opt = torch.optim.Adam(live, lr=2e-5, betas=(0.5, 0.999))
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand((batch, 3, img, img), generator=g) * 2 - 1
+    eps = torch.randn((batch, 3, img, img), generator=g)
+    t = torch.randint(1, 1000, (batch,), generator=g)
+    t0 = time.perf_counter()
+    opt.zero_grad()
+    loss = orc.train_step_loss(sd, ("linear", 5e-3, 9e-3, 1000), x0, t, eps)
+    loss.backward()
+    opt.step()
+    dt = time.perf_counter() - t0
+    return batch / dt, dt, f"1 eps-prediction step at batch {batch}, {img}x{img} (class-default U_Net, fp32, torch CPU autograd + Adam)"
+
+
+def run_train_leg(args, dev, world, rank, barrier, max_over_ranks):
+    """Secondary metric of BASELINE.json (configs[2]): eps-prediction DDPM train step (q-sample -> forward -> MSE ->
+    backward -> gradient all-reduce -> Adam) of the label-conditioned class-default U-Net at 128x128, bf16, batch-sharded
+    data parallel, the whole step replayed as one CUDA graph.  Returns the `train` object of the JSON line."""
+    from b200.flops import unet_forward_flops
+    from b200.graph import GraphedTrainStep
+    from b200.optim import FusedAdam
+    from b200.parallel import DataParallel
+    from degraders import NoiseDegradation
+    from models.U_Net import U_Net
+
+    torch.manual_seed(0)
+    net = U_Net(cond_dim=TRAIN_COND).to(dev).train().set_precision(args.precision)
+    dp = DataParallel(net, device=dev)
+    opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=True)
+    deg = NoiseDegradation(5e-3, 9e-3, T_MAX, device=dev)
+    step = GraphedTrainStep(net, deg, opt, kind="eps")
+    n, s = args.train_batch, TRAIN_IMG
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    x0_host = (torch.rand((n, 3, s, s)) * 2 - 1).pin_memory()
+    lab_host = (torch.rand((n, TRAIN_COND)) > 0.7).float().pin_memory()
+    x0 = x0_host.to(dev)
+    labels = lab_host.to(dev)
+
+    def one(h2d):
+        if h2d:                                   # e2e: this step's batch arrives from pinned host memory
+            x0.copy_(x0_host, non_blocking=True)
+            labels.copy_(lab_host, non_blocking=True)
+        eps = torch.randn(x0.shape, device=dev, generator=gen)
+        t = torch.randint(1, T_MAX, (n,), device=dev, generator=gen)
+        return step(x0, t, eps, labels)
+
+    for _ in range(3):
+        loss = one(False)
+    barrier()
+    k = max(args.steps * 3, 8)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        loss = one(False)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / k
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        loss = one(True)
+        loss_host = float(loss)                   # the reference reads the loss every step (train_diffusion.py:366)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / k
+    flops = 3.0 * unet_forward_flops(net, s, s, batch=n, tensor_core_only=True)
+    out = {"metric": "train_images_per_s", "value": world * n / (ms / 1000.0), "unit": "img/s", "ms_per_step": ms,
+           "e2e": {"value": world * n / (ms_e2e / 1000.0), "unit": "img/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": x0_host.numel() * 4 + lab_host.numel() * 4, "d2h_bytes_per_step": 4},
+           "config": {"workload": f"eps-prediction DDPM train step, class-default U_Net(cond_dim={TRAIN_COND}) {s}x{s}, "
+                                  f"batch {n}/GPU, Adam(0.5, 0.999), data-parallel gradient all-reduce overlapped with backward, "
+                                  f"CUDA-graph replay", "global_batch": world * n},
+           "dtype": args.precision, "steps": k, "loss": loss_host, "model_tflops_per_gpu": flops / (ms / 1000.0) / 1e12,
+           "flops_per_step_per_gpu": flops, "gpu_launches_per_step": step.launches_per_step,
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del step, opt, dp, net
+    torch.cuda.empty_cache()
+    return out
+
 # ---------------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -167,6 +259,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary (train-step) measurement")
+    ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -254,6 +348,10 @@ def main():
     e2e_value = world * batch / (ms_e2e / 1000.0)
     finite = bool(torch.isfinite(out_host).all())
 
+    del net
+    torch.cuda.empty_cache()
+    train = None if args.no_train else run_train_leg(args, dev, world, rank, barrier, max_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -278,11 +376,17 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "finite_output": finite},
             "gpu_launches": launches, "roofline": roofline}
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, dt, sample_desc = cpu_reference_sample(threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc,
                                 "seconds": dt}
+        if train is not None:
+            v, dt, sample_desc = cpu_reference_train(threads)
+            train["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample_desc,
+                                     "seconds": dt}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

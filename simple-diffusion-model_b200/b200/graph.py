@@ -9,6 +9,7 @@ rate) live in device memory (b2_adam_flat_graph), so the captured kernels never 
 """
 import torch
 
+from . import _lib
 from ._lib import B200Error, call, ptr, stream
 
 
@@ -26,6 +27,7 @@ class GraphedTrainStep:
         self.graph = None
         self.key = None
         self.replays = 0
+        self.launches_per_step = 0
 
     # the step body, written against the engine directly (no autograd graph is built)
     def _body(self):
@@ -70,8 +72,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._body()
+        self.launches_per_step = _lib.LAUNCHES - l0      # C-ABI calls recorded in the graph = launched by every replay
         lay.params_flat.copy_(saved[0])
         m_flat, v_flat = opt._flat[id(lay)]
         if had_moments:
@@ -112,6 +116,7 @@ class GraphedTrainStep:
         self.opt.sync_lr()
         self.graph.replay()
         self.replays += 1
+        _lib.LAUNCHES += self.launches_per_step
         self.opt.note_replayed()
         lay = self.net.engine().layout
         lay.stepped(lay.shadow is not None)      # eager users of the weight cache (eval / sampling) must re-pack

@@ -65,9 +65,9 @@ class GradLayout:
         self.offsets, off = {}, 0
         for p in self.params:
             self.offsets[id(p)] = off
-            off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+            off += (p.numel() + 7) // 8 * 8          # keep every fp32 view 32-byte and every bf16 shadow view 16-byte aligned (TMA base)
         self.total = off
-        self.front_end = sum((p.numel() + 3) // 4 * 4 for p in ys_w + ys_b)
+        self.front_end = sum((p.numel() + 7) // 8 * 8 for p in ys_w + ys_b)
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
         self.views = {id(p): self._shaped(self.flat, p) for p in self.params}
         self.params_flat = None
@@ -80,7 +80,7 @@ class GradLayout:
         self.adagn_w_numel = sum(p.numel() for p in ys_w)
         self.adagn_b_numel = sum(p.numel() for p in ys_b)
         # y_scale weights have numel % 4 == 0 whenever C % 4 == 0, so the concatenated views are dense
-        self.dense_adagn = all(p.numel() % 4 == 0 for p in ys_w + ys_b)
+        self.dense_adagn = all(p.numel() % 8 == 0 for p in ys_w + ys_b)
 
     def _shaped(self, flat, p):
         """The slice of `flat` that belongs to p, shaped like p (a permuted view for channels-last stored weights)."""
@@ -134,7 +134,7 @@ class GradLayout:
     def module_range(self, module):
         """Flat range covered by a module's live parameters, AdaGN scale Linears excluded (they live in the front
         region).  Contiguous by construction of the bucket order."""
-        offs = [(self.offsets[id(p)], self.offsets[id(p)] + (p.numel() + 3) // 4 * 4) for p in module.parameters()
+        offs = [(self.offsets[id(p)], self.offsets[id(p)] + (p.numel() + 7) // 8 * 8) for p in module.parameters()
                 if id(p) in self.offsets and self.offsets[id(p)] >= self.front_end]
         if not offs:
             return 0, 0

@@ -70,13 +70,9 @@ __global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ld
     const int cpg = C / groups;
     const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
     float mean[V], rstd[V], s1[V], s2[V];
+    gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        const int g = (c0 + j) / cpg;
-        const float m = stats[((long long)n * groups + g) * 2] * inv_cnt;
-        const float var = fmaxf(stats[((long long)n * groups + g) * 2 + 1] * inv_cnt - m * m, 0.f);
-        mean[j] = m; rstd[j] = rsqrtf(var + eps); s1[j] = 0.f; s2[j] = 0.f;
-    }
+    for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
@@ -151,15 +147,18 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
     const int cpg = C / groups;
     const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
     float mean[V], rstd[V], sg[V], m1[V], m2[V], db[V];
+    gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
+    {
+        float sc[V], ga[V];
+        ldg_f32<V>(s + (long long)n * s_bstride + c0, sc);
+        ldg_f32<V>(gamma + c0, ga);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        const int c = c0 + j, g = c / cpg;
-        const float m = stats[((long long)n * groups + g) * 2] * inv_cnt;
-        const float var = fmaxf(stats[((long long)n * groups + g) * 2 + 1] * inv_cnt - m * m, 0.f);
-        mean[j] = m; rstd[j] = rsqrtf(var + eps);
-        sg[j] = s[(long long)n * s_bstride + c] * gamma[c];
-        m1[j] = m12[((long long)n * groups + g) * 2]; m2[j] = m12[((long long)n * groups + g) * 2 + 1];
-        db[j] = 0.f;
+        for (int j = 0; j < V; ++j) {
+            const int g = (c0 + j) / cpg;
+            sg[j] = sc[j] * ga[j];
+            m1[j] = m12[((long long)n * groups + g) * 2]; m2[j] = m12[((long long)n * groups + g) * 2 + 1];
+            db[j] = 0.f;
+        }
     }
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);

@@ -253,17 +253,18 @@ __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const
     const int cpg = C / groups;
     const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
     float fa[V], fb[V];
+    {
+        float mean[V], rstd[V], sc[V], ga[V], be[V];
+        gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
+        ldg_f32<V>(s + (long long)n * s_bstride + c0, sc);
+        ldg_f32<V>(gamma + c0, ga);
+        ldg_f32<V>(beta + c0, be);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        const int c = c0 + j, g = c / cpg;
-        const float s1 = stats[((long long)n * groups + g) * 2], s2 = stats[((long long)n * groups + g) * 2 + 1];
-        const float mean = s1 * inv_cnt;
-        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
-        const float sc = s[(long long)n * s_bstride + c];
-        const float ga = gamma[c] * rstd;
-        fa[j] = sc * ga;
-        fb[j] = sc * (beta[c] - ga * mean) + sc;
+        for (int j = 0; j < V; ++j) {
+            const float g = ga[j] * rstd[j];
+            fa[j] = sc[j] * g;
+            fb[j] = sc[j] * (be[j] - g * mean[j]) + sc[j];
+        }
     }
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);

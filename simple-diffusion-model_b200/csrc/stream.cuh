@@ -36,6 +36,36 @@ __device__ __forceinline__ uint4 pack16(const float (&f)[V16<T>::N]) {
 }
 __device__ __forceinline__ void stg16(void* p, const uint4& u) { *reinterpret_cast<uint4*>(p) = u; }
 
+// V consecutive per-channel fp32 values (gamma, beta, AdaGN scale ...) with 16-byte loads; p must be 16-byte aligned.
+template <int V>
+__device__ __forceinline__ void ldg_f32(const float* p, float (&f)[V]) {
+#pragma unroll
+    for (int i = 0; i < V / 4; ++i) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(p) + i);
+        f[4 * i] = x.x; f[4 * i + 1] = x.y; f[4 * i + 2] = x.z; f[4 * i + 3] = x.w;
+    }
+}
+// GroupNorm mean / rstd of the V channels starting at c0 from the (sum, sum of squares) pairs of the conv epilogue.
+// When a group holds at least V channels (the usual case) all V share one pair: two loads instead of 2*V.
+template <int V>
+__device__ __forceinline__ void gn_mean_rstd(const float* __restrict__ stats_n /* [groups][2] of image n */, int c0, int cpg,
+                                             float inv_cnt, float eps, float (&mean)[V], float (&rstd)[V]) {
+    if (cpg % V == 0) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(stats_n) + c0 / cpg);
+        const float m = st.x * inv_cnt;
+        const float r = rsqrtf(fmaxf(st.y * inv_cnt - m * m, 0.f) + eps);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { mean[j] = m; rstd[j] = r; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float2 st = __ldg(reinterpret_cast<const float2*>(stats_n) + (c0 + j) / cpg);
+            const float m = st.x * inv_cnt;
+            mean[j] = m; rstd[j] = rsqrtf(fmaxf(st.y * inv_cnt - m * m, 0.f) + eps);
+        }
+    }
+}
+
 // load(buf, p) issues the global loads of row group p; proc(buf, p) consumes them.  Groups are `step` rows apart.
 template <typename Buf, typename Load, typename Proc>
 __device__ __forceinline__ void pipelined_rows(long long p_begin, long long p_end, long long step, Load load, Proc proc) {
