@@ -144,6 +144,9 @@ int b2_ddpm_step(const float* x_t, const float* eps_hat, const float* z, float* 
 /* diffusion_sampling_algorithms.py:193-208: x' = x - (a_t x0 + b_t noise) + (a_n x0 + b_n noise). */
 int b2_cold_step(const float* x_t, const float* x0_hat, const float* noise, float* out, long long n, float a_t,
                  float b_t, float a_n, float b_n, void* stream);
+/* F.interpolate(mode="area") on fp32 NCHW planes (train_SR_diffusion.py:321-328, generate_sr_images_diffusion.py:170-173):
+ * adaptive average pooling, out[o] = mean in[floor(o*I/O) .. ceil((o+1)*I/O)); planes = N*C. */
+int b2_area_resample(const float* x, float* y, long long planes, int H, int W, int OH, int OW, void* stream);
 /* loss = mean((pred-target)^2) (train_diffusion.py:350), grad (optional) = 2 (pred-target)/n * grad_scale. */
 int b2_mse_loss_grad(const float* pred, const float* target, float* grad, float* loss, long long n, float grad_scale,
                      void* stream);

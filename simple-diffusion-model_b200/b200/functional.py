@@ -24,3 +24,17 @@ class _MSE(torch.autograd.Function):
 def mse_loss(pred, target):
     """F.mse_loss(pred, target) (mean reduction) on CUDA tensors: one kernel yields the loss and d(loss)/d(pred)."""
     return _MSE.apply(pred, target)
+
+
+def area_resize(x, size):
+    """F.interpolate(x, size=size, mode="area") on an fp32 NCHW CUDA tensor (the SR trainers' low-resolution
+    conditioning image, train_SR_diffusion.py:321-328): one kernel, adaptive-average-pool semantics."""
+    if not x.is_cuda:
+        from ._lib import B200Error
+        raise B200Error("area_resize needs a CUDA tensor: this build has no CPU path")
+    oh, ow = (size, size) if isinstance(size, int) else size
+    xc = x.contiguous().float()
+    n, c, h, w = xc.shape
+    out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    call("b2_area_resample", ptr(xc), ptr(out), n * c, h, w, oh, ow, stream())
+    return out

@@ -103,9 +103,22 @@ class GraphedTrainStep:
         key = (tuple(x0.shape), tuple(t.shape), None if labels is None else tuple(labels.shape),
                None if cond_img is None else tuple(cond_img.shape), None if target is None else tuple(target.shape),
                self.net.precision)
-        if self.graph is None or key != self.key:
+        if self.graph is None:
             self.key = key
             self._capture(x0, t, eps, labels, cond_img, target)
+        elif key != self.key:
+            # a differently shaped batch (the short last batch of an epoch): run the same kernel sequence eagerly
+            captured, self.static = self.static, {
+                "x0": x0.contiguous().float(), "t": t.to(torch.int64), "eps": eps.contiguous().float(), "labels": labels,
+                "cond_img": cond_img, "target": target, "loss": torch.zeros((), dtype=torch.float32, device=x0.device),
+                "dpred": torch.empty((x0.shape[0], captured["dpred"].shape[1]) + tuple(x0.shape[2:]), dtype=torch.float32,
+                                     device=x0.device)}
+            try:
+                self.opt.sync_lr()
+                self._body()
+                return self.static["loss"]
+            finally:
+                self.static = captured
         s = self.static
         s["x0"].copy_(x0, non_blocking=True)
         s["t"].copy_(t, non_blocking=True)

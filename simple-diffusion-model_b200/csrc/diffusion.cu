@@ -218,3 +218,27 @@ extern "C" int b2_mse_loss_grad(const float* pred, const float* target, float* g
     mse_loss_grad_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(pred, target, grad, loss, n, 1.0f / (float)n, grad_scale);
     LAUNCH_CHECK("b2_mse_loss_grad");
 }
+
+// ------------------------------------------------------------------------------------------------ area resample
+// F.interpolate(mode="area") == adaptive average pooling (train_SR_diffusion.py:321-328, generate_sr_images_diffusion.py:170-173):
+// out[o] = mean of in[floor(o*I/O) .. ceil((o+1)*I/O)) per axis.  Integer down-scaling averages k x k windows, integer
+// up-scaling replicates.  fp32 NCHW planes; one thread per output element (consecutive threads walk the output row).
+__global__ void area_resample_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int H, int W, int OH, int OW) {
+    const long long total = planes * OH * OW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(i % OW), oh = (int)((i / OW) % OH);
+        const long long pl = i / ((long long)OW * OH);
+        const int h0 = (int)(((long long)oh * H) / OH), h1 = (int)((((long long)oh + 1) * H + OH - 1) / OH);
+        const int w0 = (int)(((long long)ow * W) / OW), w1 = (int)((((long long)ow + 1) * W + OW - 1) / OW);
+        const float* src = x + pl * H * W;
+        float acc = 0.f;
+        for (int h = h0; h < h1; ++h)
+            for (int w = w0; w < w1; ++w) acc += __ldg(src + (long long)h * W + w);
+        y[i] = acc / (float)((h1 - h0) * (w1 - w0));
+    }
+}
+extern "C" int b2_area_resample(const float* x, float* y, long long planes, int H, int W, int OH, int OW, void* stream) {
+    if (H < 1 || W < 1 || OH < 1 || OW < 1) return set_error("b2_area_resample: bad sizes");
+    area_resample_kernel<<<ew_grid(planes * OH * OW, 256), 256, 0, (cudaStream_t)stream>>>(x, y, planes, H, W, OH, OW);
+    LAUNCH_CHECK("b2_area_resample");
+}

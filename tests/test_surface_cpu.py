@@ -70,3 +70,55 @@ def test_c_abi_exports_every_declared_symbol():
     assert set(SIGNATURES) == declared - {"b2_last_error", "b2_version"}
     handle.b2_version.restype = ctypes.c_int
     assert handle.b2_version() >= 100
+
+
+def test_entry_points_keep_reference_names_and_fail_loudly_without_cuda(tmp_path):
+    """train_*/generate_* (reference L4 scripts): same module / function names, config validation errors of the
+    reference (train_diffusion.py:69-116), and no silent CPU path."""
+    import inspect
+    import json
+    import generate_images_cold_diffusion as gc
+    import generate_images_diffusion as gd
+    import generate_sr_images_diffusion as gs
+    import train_diffusion, train_doodle_diffusion, train_noise_cold_diffusion, train_SR_diffusion
+    from b200._lib import B200Error
+    assert list(inspect.signature(gd.generate_images_diffusion).parameters) == ["raw_args", "log", "cond_img", "save_locally"]
+    assert list(inspect.signature(gc.generate_images_cold_diffusion).parameters) == ["raw_args", "log", "save_locally"]
+    assert list(inspect.signature(gs.generate_sr_images_diffusion).parameters) == ["raw_args", "lr_img", "log", "save_locally"]
+    cfg = dict(dataset_path="synthetic:4x3x32x32", out_dir=str(tmp_path / "o"), checkpoint_steps=1, lr_steps=1, max_epoch=1,
+               plot_img_count=1, noise_scheduler="BOGUS", diffusion_alg="DDIM", min_noise_step=1, max_noise_step=10,
+               max_actual_noise_step=10, skip_step=2)
+    path = tmp_path / "c.json"
+    for mod in (train_diffusion, train_doodle_diffusion, train_noise_cold_diffusion, train_SR_diffusion):
+        path.write_text(json.dumps(cfg))
+        with pytest.raises(B200Error):
+            mod.main(["-c", str(path), "--device", "cpu"])
+        with pytest.raises(ValueError, match="noise scheduler"):
+            mod.main(["-c", str(path)])
+    cfg.update(noise_scheduler="COSINE", skip_step=50)
+    path.write_text(json.dumps(cfg))
+    with pytest.raises(ValueError, match="step values"):
+        train_diffusion.main(["-c", str(path)])
+    cfg.update(skip_step=2, diffusion_alg="XYZ")
+    path.write_text(json.dumps(cfg))
+    with pytest.raises(ValueError, match="diffusion algorithm"):
+        train_diffusion.main(["-c", str(path)])
+    with pytest.raises(B200Error):
+        gd.generate_images_diffusion(["-c", str(path), "--device", "cpu"])
+
+
+def test_dataset_table_reader(tmp_path):
+    """TinyDB files are JSON documents: the labelled datasets read them without the tinydb package."""
+    import json
+    from custom_dataset._tables import load_tables
+    from custom_dataset.img_dataset import SyntheticImages
+    db = {"Data": {"1": {"filename": "a.png", "smile": 1, "hat": 0}, "2": {"filename": "b.png", "smile": 0, "hat": 1}},
+          "Labels": {"1": {"labels": ["smile", "hat"]}}}
+    p = tmp_path / "db.json"
+    p.write_text(json.dumps(db))
+    rows, labels = load_tables(str(p))
+    assert labels == ["smile", "hat"] and len(rows) == 2
+    ds = SyntheticImages("synthetic:5x3x16x16:4")
+    img, lab = ds[2]
+    assert len(ds) == 5 and img.shape == (3, 16, 16) and lab.shape == (4,) and float(img.abs().max()) <= 1.0
+    assert torch.equal(ds[2][0], img)
