@@ -331,6 +331,61 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
     LAUNCH_CHECK("b2_adagn_apply");
 }
 
+// GroupNorm statistics as a separate pass, for widths the conv epilogue does not fuse (fewer than 4 channels per
+// group: C = 32 or 64 with the reference's 32 groups).  stats[n][g] += (sum, sum of squares) of y (or of Swish(y)).
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ y, long long ldy, float* __restrict__ stats, int HW, int C, int groups,
+                                int slabs, int rows_per_block, int pre_swish) {
+    extern __shared__ float gsum[];                  // [groups][2]
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
+    const int cpg = C / groups;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gsum[i] = 0.f;
+    __syncthreads();
+    const int p_per = (HW + slabs - 1) / slabs;
+    const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
+    float s1[V], s2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    for (int p = p0 + prow; p < p1; p += rows_per_block) {
+        float v[V];
+        unpack16<T>(ldg16(y + ((long long)n * HW + p) * ldy + c0), v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float x = pre_swish ? swish_t<sizeof(T) == 2>(v[j]) : v[j];
+            s1[j] += x; s2[j] = fmaf(x, x, s2[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        atomicAdd(&gsum[((c0 + j) / cpg) * 2], s1[j]);
+        atomicAdd(&gsum[((c0 + j) / cpg) * 2 + 1], s2[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(stats + (long long)n * groups * 2 + i, gsum[i]);
+}
+namespace b2 {
+int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, int C, int groups, int pre_swish, int dtype,
+                    cudaStream_t st) {
+    const int V = dtype == 0 ? 8 : 4;
+    if (C % V || ldy % V || C % groups) return set_error("gn_stats: channel count / stride must be 16-byte aligned and divisible by groups");
+    const int cv = C / V;
+    int k = 256 / cv; if (k < 1) k = 1;
+    int slabs = (4 * device_sm_count() + N - 1) / N;
+    const int max_slabs = (HW + 4 * k - 1) / (4 * k);
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    const size_t smem = (size_t)groups * 2 * sizeof(float);
+    if (dtype == 0) gn_stats_kernel<bf16><<<N * slabs, cv * k, smem, st>>>((const bf16*)y, ldy, stats, HW, C, groups, slabs, k, pre_swish);
+    else gn_stats_kernel<float><<<N * slabs, cv * k, smem, st>>>((const float*)y, ldy, stats, HW, C, groups, slabs, k, pre_swish);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("gn_stats: %s", cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace b2
+
 // ------------------------------------------------------------------------------------------------ attention helpers
 // Query-axis softmax (custom_layers.py:147): S[b][i][j] fp32 (already scaled) -> P[b][i][j] = exp(S - max_i) / sum_i.
 // One thread owns one key column j (coalesced across the warp), walking the query axis twice.

@@ -31,3 +31,36 @@ def test_unet_forward_matches_reference(name, precision):
         assert err < TOL[precision]
         out1 = net(fx["x"].cuda(), fx["t"][:1].cuda(), cond[0] if cond is not None else None)
         assert rel_l2(out1.cpu(), fx["out_t1"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_cond"])
+def test_narrow_unet_forward_backward_tf32(name):
+    """32/64-channel nets (1-2 channels per GroupNorm group: statistics come from the separate pass, not the conv epilogue),
+    two attention heads, 6 input channels, tanh output -- forward and every gradient against the reference fixtures."""
+    import torch.nn.functional as F
+    fx = load_golden(f"unet_{name}.pt")
+    net = _build(fx, "tf32").train()
+    cond = fx["cond"].cuda() if fx["cond"] is not None else None
+    out = net(fx["x"].cuda(), fx["t"].cuda(), cond)
+    assert rel_l2(out.detach().cpu(), fx["out"]) < TOL["tf32"]
+    loss = F.mse_loss(out, fx["target"].cuda())
+    loss.backward()
+    named = dict(net.named_parameters())
+    got, want = [], []
+    for pname, g in fx["grads"].items():
+        have = named[pname].grad.detach().float().cpu().flatten()
+        if g["full"] is not None:
+            got.append(have); want.append(g["full"].flatten())
+        else:
+            idx = (torch.arange(4096, dtype=torch.int64) * have.numel()) // 4096
+            got.append(have[idx]); want.append(g["sample"])
+    assert rel_l2(torch.cat(got), torch.cat(want)) < 2e-3
+
+
+def test_reference_unit_test_shape():
+    """The reference's only test (tests/test_u_net_model.py:21-23): default U_Net, 1x3x128x128, t = [1000] -> same shape."""
+    from models.U_Net import U_Net
+    net = U_Net().cuda().eval()
+    with torch.no_grad():
+        y = net(torch.randn((1, 3, 128, 128), device="cuda"), torch.tensor([1000], device="cuda"))
+    assert tuple(y.shape) == (1, 3, 128, 128) and torch.isfinite(y).all()
