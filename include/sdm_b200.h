@@ -50,6 +50,22 @@ int b2_gemm_nt(const void* A, long long lda, long long a_s1, long long a_s2, con
                int Ncols, int K, int batch1, int batch2, const float* bias, float alpha, int act,
                const void* residual, long long ldr, int out_fp32, int dtype, void* stream);
 
+/* Fused attention scores (custom_layers.py:144-147): P^T[n][h][j][i] = softmax over the QUERY index i of
+ * scale * q_i . k_j, computed as S^T = K Q^T on the tensor cores with the softmax in the epilogue (one thread owns one
+ * key row in TMEM), so the fp32 score matrix is never written.  k, q: [P][d] slices of the packed qkv tensor (row stride
+ * ld, head stride sh, image stride sn, in elements); pt: [N][heads][P][ldp], ldp a multiple of 8.  work: 2*N*heads*P*
+ * ceil(P/256) floats, used only when P > 256 (per-tile statistics + a normalising fix-up pass).  P.V then is
+ * b2_gemm_tn(pt, v): no transpose of V is needed. */
+int b2_attn_scores_softmax(const void* k, const void* q, long long ld, long long sh, long long sn, void* pt, long long ldp,
+                           int P, int d, int heads, int N, float scale, float* work, int dtype, void* stream);
+/* Backward of the above in one tensor-core pass: dS^T = scale * P^T .* (V dO^T - dot[key]), dot from b2_rowdot(v, dv). */
+int b2_attn_scores_bwd(const void* v, long long ld, long long sh, long long sn, const void* d_o, long long ld_do,
+                       long long do_sh, long long do_sn, const void* pt, const float* dot, void* dst, long long ldp, int P,
+                       int d, int heads, int N, float scale, int dtype, void* stream);
+/* out[r][h] = sum_{c<d} a[r][h*head_stride + c] * b[r][h*head_stride + c]  (fp32). */
+int b2_rowdot(const void* a, long long lda, const void* b, long long ldb, long long head_stride, float* out, long long rows,
+              int heads, int d, int dtype, void* stream);
+
 /* ---- gradients of the dense contractions (tcgen05 "TN" GEMM: contraction over pixel / sequence rows) -------- */
 
 /* Weight gradient of b2_conv2d_nhwc's three modes (autograd's convolution_backward in the reference), accumulated

@@ -164,27 +164,26 @@ class UNetEngine:
         qkv = torch.empty((n * p_len, 3 * heads * d), dtype=dt, device=dev)
         ops.gemm_nt(x, wp, n * p_len, 3 * heads * d, c, ldx, c, qkv, 3 * heads * d, bias=blk.projection.bias)
         ldq = 3 * heads * d
-        # S[n][h][i][j] = scale * q_i . k_j
-        s_mat = torch.empty((n, heads, p_len, p_len), dtype=torch.float32, device=dev)
-        ops.gemm_nt(qkv, qkv[:, d:], p_len, p_len, d, ldq, ldq, s_mat, p_len, alpha=blk.scale, out_fp32=True,
-                    batch=(heads, n), a_strides=(3 * d, p_len * ldq), b_strides=(3 * d, p_len * ldq),
-                    c_strides=(p_len * p_len, heads * p_len * p_len))
+        # P^T[n][h][j][i] = softmax_i(scale * q_i . k_j): scores and the query-axis softmax in ONE tensor-core kernel
+        # (S^T = K Q^T, one thread per key row in TMEM) -- the fp32 score matrix of the reference never exists
         ldp = ((p_len + 7) // 8) * 8
-        pm = torch.empty((n, heads, p_len, ldp), dtype=dt, device=dev)
-        call("b2_softmax_query_axis", ptr(s_mat), ptr(pm), n * heads, p_len, p_len, ldp, code, stream())
-        vt = torch.empty((n, heads, d, ldp), dtype=dt, device=dev)
-        call("b2_transpose_batched", ptr(qkv[:, 2 * d:]), ldq, 3 * d, p_len * ldq, ptr(vt), ldp, d * ldp, heads * d * ldp,
-             p_len, d, heads, n, code, stream())
+        pt = torch.empty((n, heads, p_len, ldp), dtype=dt, device=dev)
+        tiles = (p_len + 255) // 256
+        work = torch.empty((2 * n * heads * p_len * tiles,), dtype=torch.float32, device=dev) if tiles > 1 else None
+        call("b2_attn_scores_softmax", ptr(qkv[:, d:]), ptr(qkv), ldq, 3 * d, p_len * ldq, ptr(pt), ldp, p_len, d, heads, n,
+             float(blk.scale), ptr(work), code, stream())
+        # O[i][c] = sum_j P^T[j][i] V[j][c]: both operands have the contraction index as their row index, which is the
+        # TN kernel's native form -- V is consumed in place inside qkv, no transpose
         o = torch.empty((n * p_len, heads * d), dtype=dt, device=dev)
-        ops.gemm_nt(pm, vt, p_len, d, p_len, ldp, ldp, o, heads * d, batch=(heads, n),
-                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(d * ldp, heads * d * ldp),
-                    c_strides=(d, p_len * heads * d))
+        ops.gemm_tn(pt, qkv[:, 2 * d:], p_len, d, p_len, ldp, ldq, o, heads * d, out_mode=1, batch=(heads, n),
+                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(3 * d, p_len * ldq),
+                    c_strides=(d, p_len * heads * d), code=code)
         if out is None:
             out = torch.empty((n, hh, ww, c), dtype=dt, device=dev)
         ops.gemm_nt(o, wo, n * p_len, c, heads * d, heads * d, heads * d, out, out.stride(2), bias=blk.output.bias,
                     residual=x, ldr=ldx)
         if save is not None:
-            save.update(qkv=qkv, pm=pm, o=o, ldp=ldp)
+            save.update(qkv=qkv, pt=pt, o=o, ldp=ldp)
         return out
 
     def unet_block(self, blk, x, ctx, out):

@@ -530,7 +530,7 @@ class UNetTrainEngine(UNetEngine):
         rows = n * p_len
         dt, dev = x.dtype, x.device
         lay = self.layout
-        qkv, pm, o, ldp = saved["qkv"], saved["pm"], saved["o"], saved["ldp"]
+        qkv, pt, o, ldp = saved["qkv"], saved["pt"], saved["o"], saved["ldp"]
         ldd = dout.stride(2)
         # output projection: out = o Wo^T + bo + x
         ops.act(2, dout, None, None, lay.view(blk.output.bias), rows, c, ldd, 0, 0, code)
@@ -539,22 +539,32 @@ class UNetTrainEngine(UNetEngine):
         d_o = torch.empty((rows, hd), dtype=dt, device=dev)
         ops.gemm_nt(dout, wo_t, rows, hd, c, ldd, c, d_o, hd)
         dqkv = torch.empty((rows, ldq), dtype=dt, device=dev)
-        # dP = dO V^T (fp32), dV = P^T dO
-        dp = torch.empty((n, heads, p_len, p_len), dtype=torch.float32, device=dev)
-        ops.gemm_nt(d_o, qkv[:, 2 * d:], p_len, p_len, d, hd, ldq, dp, p_len, out_fp32=True, batch=(heads, n),
-                    a_strides=(d, p_len * hd), b_strides=(3 * d, p_len * ldq), c_strides=(p_len * p_len, heads * p_len * p_len))
-        ops.gemm_tn(pm, d_o, p_len, d, p_len, ldp, hd, dqkv[:, 2 * d:], ldq, out_mode=1, batch=(heads, n),
-                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(d, p_len * hd), c_strides=(3 * d, p_len * ldq))
-        ds = torch.empty((n, heads, p_len, ldp), dtype=dt, device=dev)
-        call("b2_softmax_query_axis_bwd", ptr(pm), ptr(dp), ptr(ds), n * heads, p_len, p_len, ldp, float(blk.scale), code, stream())
-        # dQ = dS K (needs K^T as the NT operand), dK = dS^T Q
-        kt = torch.empty((n, heads, d, ldp), dtype=dt, device=dev)
-        call("b2_transpose_batched", ptr(qkv[:, d:]), ldq, 3 * d, p_len * ldq, ptr(kt), ldp, d * ldp, heads * d * ldp,
-             p_len, d, heads, n, code, stream())
-        ops.gemm_nt(ds, kt, p_len, d, p_len, ldp, ldp, dqkv, ldq, batch=(heads, n),
-                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(d * ldp, heads * d * ldp), c_strides=(3 * d, p_len * ldq))
-        ops.gemm_tn(ds, qkv, p_len, d, p_len, ldp, ldq, dqkv[:, d:], ldq, out_mode=1, batch=(heads, n),
-                    a_strides=(p_len * ldp, heads * p_len * ldp), b_strides=(3 * d, p_len * ldq), c_strides=(3 * d, p_len * ldq))
+        pt_s, t_s = (p_len * ldp, heads * p_len * ldp), (d * ldp, heads * d * ldp)      # batch strides of P^T-shaped / transposed tensors
+        qkv_s = (3 * d, p_len * ldq)
+
+        def transposed(src, ld_src, src_strides):
+            """[P][d] slices -> [d][ldp] (K-major B operand of the NT kernel for contractions over the query index)."""
+            out_t = torch.empty((n, heads, d, ldp), dtype=dt, device=dev)
+            call("b2_transpose_batched", ptr(src), ld_src, src_strides[0], src_strides[1], ptr(out_t), ldp, t_s[0], t_s[1],
+                 p_len, d, heads, n, code, stream())
+            return out_t
+
+        # dV[j][c] = sum_i P^T[j][i] dO[i][c]
+        ops.gemm_nt(pt, transposed(d_o, hd, (d, p_len * hd)), p_len, d, p_len, ldp, ldp, dqkv[:, 2 * d:], ldq, batch=(heads, n),
+                    a_strides=pt_s, b_strides=t_s, c_strides=qkv_s, code=code)
+        # softmax backward needs sum_i P^T dP^T per key, which equals sum_c V[j][c] dV[j][c]: a row dot product
+        dot = torch.empty((rows, heads), dtype=torch.float32, device=dev)
+        call("b2_rowdot", ptr(qkv[:, 2 * d:]), ldq, ptr(dqkv[:, 2 * d:]), ldq, 3 * d, ptr(dot), rows, heads, d, code, stream())
+        # dS^T = scale * P^T .* (V dO^T - dot): GEMM + softmax backward in one kernel, dP never materialised
+        dst = torch.empty((n, heads, p_len, ldp), dtype=dt, device=dev)
+        call("b2_attn_scores_bwd", ptr(qkv[:, 2 * d:]), ldq, 3 * d, p_len * ldq, ptr(d_o), hd, d, p_len * hd, ptr(pt), ptr(dot),
+             ptr(dst), ldp, p_len, d, heads, n, float(blk.scale), code, stream())
+        # dQ[i][c] = sum_j dS^T[j][i] K[j][c]  (TN: contraction index = row index of both operands)
+        ops.gemm_tn(dst, qkv[:, d:], p_len, d, p_len, ldp, ldq, dqkv, ldq, out_mode=1, batch=(heads, n),
+                    a_strides=pt_s, b_strides=qkv_s, c_strides=qkv_s, code=code)
+        # dK[j][c] = sum_i dS^T[j][i] Q[i][c]
+        ops.gemm_nt(dst, transposed(qkv, ldq, qkv_s), p_len, d, p_len, ldp, ldp, dqkv[:, d:], ldq, batch=(heads, n),
+                    a_strides=pt_s, b_strides=t_s, c_strides=qkv_s, code=code)
         # input projection: qkv = x Wp^T + bp
         ops.act(2, dqkv, None, None, lay.view(blk.projection.bias), rows, ldq, ldq, 0, 0, code)
         ops.gemm_tn(dqkv, x, ldq, c, rows, ldq, ldx, lay.view(blk.projection.weight), c, code=code)

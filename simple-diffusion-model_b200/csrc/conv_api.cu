@@ -205,6 +205,86 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
     return launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream);
 }
 
+// ================================================================================================ attention scores
+namespace b2 {
+int launch_softmax_fixup(void* pt, long long ldp, const float* stats, long long rows, int P, int n_tiles, int tile_cols, int dtype,
+                         cudaStream_t st);
+}
+
+static int attn_bn(int P) { return P <= 64 ? 64 : (P <= 128 ? 128 : 256); }
+
+// Shared set-up of the two score kernels: rows = keys (A operand), columns = queries (B operand), both [P][d] slices
+// of the packed qkv / gradient tensors, batched over (head, image).
+static int attn_params(IgemmParams* p, CUtensorMap* ta, CUtensorMap* tb, const void* A, long long lda, long long a_sh,
+                       long long a_sn, const void* B, long long ldb, long long b_sh, long long b_sn, void* out, long long ldo,
+                       long long o_sh, long long o_sn, int P, int d, int heads, int N, int dtype, int bn) {
+    const int eb = dtype == 0 ? 2 : 4;
+    const int bk = 128 / eb;
+    if ((lda * eb) % 16 || (ldb * eb) % 16) return set_error("attention: row strides must be 16-byte multiples");
+    memset(p, 0, sizeof(*p));
+    p->W = P; p->H = heads; p->N = N;
+    p->wb = 128; p->hb = 1; p->nb = 1;
+    p->tiles_w = (P + 127) / 128; p->tiles_h = heads; p->tiles_n = N;
+    p->groups = 1; p->taps = 1; p->kb_per_tap = (d + bk - 1) / bk;
+    p->Cout = P;
+    p->out = out; p->oN = o_sn; p->oH = o_sh; p->oW = ldo; p->oC = 1;
+    const int ov = dtype == 1 ? 4 : 8;
+    p->vec_ok = ((ldo % ov == 0) && (o_sh % ov == 0) && (o_sn % ov == 0) && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
+    p->b_mode = 1;
+    p->n_tiles = (P + bn - 1) / bn;
+    {
+        uint64_t dims[4] = {(uint64_t)d, (uint64_t)P, (uint64_t)heads, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)lda * eb, (uint64_t)(heads > 1 ? a_sh : lda * P) * eb, (uint64_t)(N > 1 ? a_sn : lda * P * heads) * eb};
+        uint32_t box[4] = {(uint32_t)bk, 128, 1, 1};
+        if (make_tmap_4d(ta, A, eb, dims, str, box)) return 1;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)d, (uint64_t)P, (uint64_t)heads, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)ldb * eb, (uint64_t)(heads > 1 ? b_sh : ldb * P) * eb, (uint64_t)(N > 1 ? b_sn : ldb * P * heads) * eb};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)bn, 1, 1};
+        if (make_tmap_4d(tb, B, eb, dims, str, box)) return 1;
+    }
+    return 0;
+}
+
+// P^T[n][h][j][i] = softmax over the QUERY index i of scale * q_i . k_j  (custom_layers.py:144-147), computed
+// as S^T = K Q^T so that the softmax axis runs along the TMEM columns of one thread: the fp32 score matrix never
+// reaches memory.  k, q: [P][d] slices (row stride ld, head stride sh, image stride sn, elements).  pt: row stride ldp
+// (multiple of 8 elements).  work: 2 * N*heads*P * ceil(P/256) floats, only touched when P > 256.
+extern "C" int b2_attn_scores_softmax(const void* k, const void* q, long long ld, long long sh, long long sn, void* pt,
+                                      long long ldp, int P, int d, int heads, int N, float scale, float* work, int dtype,
+                                      void* stream) {
+    IgemmParams p; CUtensorMap ta, tb;
+    const int bn = attn_bn(P);
+    if (attn_params(&p, &ta, &tb, k, ld, sh, sn, q, ld, sh, sn, pt, ldp, (long long)P * ldp, (long long)heads * P * ldp, P, d, heads,
+                    N, dtype, bn)) return 1;
+    p.alpha = scale; p.act = 4;
+    if (p.n_tiles > 1) {
+        if (!work) return set_error("b2_attn_scores_softmax: P > 256 needs the stats workspace");
+        p.gn_stats = work;
+    }
+    if (launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;
+    if (p.n_tiles > 1)
+        return launch_softmax_fixup(pt, ldp, work, (long long)N * heads * P, P, p.n_tiles, bn, dtype, (cudaStream_t)stream);
+    return 0;
+}
+
+// dS^T[n][h][j][i] = scale * P^T[j][i] * (dP^T[j][i] - dot[n][h][j]),  dP^T = V dO^T  (backward of the softmax above;
+// dot[j] = sum_i P^T dP^T = sum_c V[j][c] dV[j][c], see b2_rowdot).  v: [P][d] slices of qkv, d_o: [P][d] slices with
+// row stride ldo_ / head stride d / image stride P*ldo_.
+extern "C" int b2_attn_scores_bwd(const void* v, long long ld, long long sh, long long sn, const void* d_o, long long ld_do,
+                                  long long do_sh, long long do_sn, const void* pt, const float* dot, void* dst, long long ldp,
+                                  int P, int d, int heads, int N, float scale, int dtype, void* stream) {
+    IgemmParams p; CUtensorMap ta, tb;
+    const int bn = attn_bn(P);
+    if (attn_params(&p, &ta, &tb, v, ld, sh, sn, d_o, ld_do, do_sh, do_sn, dst, ldp, (long long)P * ldp, (long long)heads * P * ldp,
+                    P, d, heads, N, dtype, bn)) return 1;
+    p.alpha = scale; p.act = 5;
+    p.residual = pt; p.rW = ldp; p.rH = (long long)P * ldp; p.rN = (long long)heads * P * ldp;
+    p.rowvec = dot; p.vW = heads; p.vH = 1; p.vN = (long long)heads * P;      // dot is [N*P][heads] (b2_rowdot's layout)
+    return launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream);
+}
+
 // ================================================================================================ TN GEMM launchers
 namespace b2 {
 int launch_gemm_tn(int dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int block_n, cudaStream_t st);

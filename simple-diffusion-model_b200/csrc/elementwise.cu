@@ -387,6 +387,65 @@ int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, i
 }  // namespace b2
 
 // ------------------------------------------------------------------------------------------------ attention helpers
+// Fix-up of the fused score kernel when a key row spans several 256-query tiles: tile t of row r holds
+// exp2(s - m_t) and stats (m_t, z_t); the normalised probability is that value times exp2(m_t - m) / Z with
+// m = max_t m_t, Z = sum_t z_t exp2(m_t - m).  One warp per row.
+template <typename T>
+__global__ void softmax_tiles_fixup_kernel(T* __restrict__ pt, long long ldp, const float* __restrict__ stats, long long rows,
+                                           int P, int n_tiles, int tile_cols) {
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* st = stats + row * n_tiles * 2;
+    float m = -INFINITY;
+    for (int t = 0; t < n_tiles; ++t) m = fmaxf(m, st[2 * t]);
+    float z = 0.f;
+    for (int t = 0; t < n_tiles; ++t) z += st[2 * t + 1] * exp2f(st[2 * t] - m);
+    const float inv = 1.0f / z;
+    T* o = pt + row * ldp;
+    for (int c = lane; c < P; c += 32) {
+        const float f = exp2f(st[2 * (c / tile_cols)] - m) * inv;
+        o[c] = from_f<T>(to_f<T>(o[c]) * f);
+    }
+}
+// dot[r][h] = sum_c a[r][h*hs + c] * b[r][h*hs + c], c < d  (softmax backward: sum_i P dP == sum_c V dV per key).
+template <typename T>
+__global__ void rowdot_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, long long hs,
+                              float* __restrict__ out, long long rows, int heads, int d) {
+    const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= rows * heads) return;
+    const long long r = item / heads;
+    const int h = (int)(item % heads);
+    const T* pa = a + r * lda + h * hs;
+    const T* pb = b + r * ldb + h * hs;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc = fmaf(to_f<T>(pa[c]), to_f<T>(pb[c]), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[item] = acc;
+}
+namespace b2 {
+int launch_softmax_fixup(void* pt, long long ldp, const float* stats, long long rows, int P, int n_tiles, int tile_cols, int dtype,
+                         cudaStream_t st) {
+    const long long threads = rows * 32;
+    const int blocks = (int)((threads + 255) / 256);
+    if (dtype == 0) softmax_tiles_fixup_kernel<bf16><<<blocks, 256, 0, st>>>((bf16*)pt, ldp, stats, rows, P, n_tiles, tile_cols);
+    else softmax_tiles_fixup_kernel<float><<<blocks, 256, 0, st>>>((float*)pt, ldp, stats, rows, P, n_tiles, tile_cols);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("softmax fix-up: %s", cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace b2
+extern "C" int b2_rowdot(const void* a, long long lda, const void* b, long long ldb, long long head_stride, float* out,
+                         long long rows, int heads, int d, int dtype, void* stream) {
+    const long long threads = rows * heads * 32;
+    const int blocks = (int)((threads + 255) / 256);
+    if (dtype == 0) rowdot_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, head_stride, out, rows, heads, d);
+    else rowdot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, (const float*)b, ldb, head_stride, out, rows, heads, d);
+    LAUNCH_CHECK("b2_rowdot");
+}
+
 // Query-axis softmax (custom_layers.py:147): S[b][i][j] fp32 (already scaled) -> P[b][i][j] = exp(S - max_i) / sum_i.
 // One thread owns one key column j (coalesced across the warp), walking the query axis twice.
 template <typename T>

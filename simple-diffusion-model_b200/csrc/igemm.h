@@ -30,7 +30,12 @@ struct IgemmParams {
     long long rN, rH, rW;
     const float* bias;           // optional [Cout]
     float alpha;                 // acc *= alpha before bias
-    int act;                     // 0 none, 1 swish, 2 tanh, 3 none but GN stats of swish(value)
+    int act;                     // 0 none, 1 swish, 2 tanh, 3 none but GN stats of swish(value),
+                                 // 4 softmax over the valid columns of each row (attention: rows = keys, columns = queries;
+                                 //   gn_stats then receives per-(row, n-tile) (max, sum) when a row spans several tiles),
+                                 // 5 out = alpha * residual[row][col] * (acc - rowvec[row])  (softmax backward)
+    const float* rowvec;         // act 5: one value per output row, index n*vN + h*vH + w*vW
+    long long vN, vH, vW;
     float* gn_stats;             // optional [N][Cout/cpg][2] (sum, sum of squares), accumulated atomically
     int cpg;                     // channels per GroupNorm group
 };

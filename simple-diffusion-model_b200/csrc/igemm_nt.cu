@@ -206,6 +206,70 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
+            if (p.act == 4) {
+                // ---- attention scores: each thread owns one key row of S^T (columns = queries), so the reference's
+                // softmax over the QUERY axis (custom_layers.py:147) is a purely in-thread reduction over TMEM columns.
+                if (half == 0) {
+                    const int ncols_tile = min(BLOCK_N, p.Cout - tc.nt * BLOCK_N);
+                    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+                    const float sc = p.alpha * 1.4426950408889634f;          // exp(x) = exp2(x * log2 e)
+                    float mx = -INFINITY;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < ncols_tile; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(trow + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) mx = fmaxf(mx, __uint_as_float(r[i]) * sc);
+                    }
+                    float z = 0.f;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < ncols_tile; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(trow + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) z += exp2f(__uint_as_float(r[i]) * sc - mx);
+                    }
+                    const float inv = p.n_tiles == 1 ? 1.0f / z : 1.0f;       // several tiles per row: normalised by the fix-up pass
+#pragma unroll 1
+                    for (int c0 = 0; c0 < ncols_tile; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(trow + c0, r);
+                        tmem_ld_wait();
+                        if (!valid) continue;
+                        const int col0 = tc.nt * BLOCK_N + c0;
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = exp2f(__uint_as_float(r[i]) * sc - mx) * inv;
+                        const bool full = p.vec_ok && (c0 + 32 <= ncols_tile);
+                        if (f32out) {
+                            float* o = reinterpret_cast<float*>(p.out) + o_off + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) o[i] = kTF32 ? round_tf32(v[i]) : v[i];
+                        } else {
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_off + col0;
+                            if (full) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    uint4 x;
+                                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+                                    reinterpret_cast<uint4*>(o)[i] = x;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) o[i] = __float2bfloat16(v[i]);
+                            }
+                        }
+                    }
+                    if (valid && p.n_tiles > 1) {
+                        float* st = p.gn_stats + ((((long long)n * p.H + h) * p.W + w) * p.n_tiles + tc.nt) * 2;
+                        st[0] = mx; st[1] = z;
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
                 const int col0 = tc.nt * BLOCK_N + ch * 32;
@@ -232,7 +296,21 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
                 }
-                if (p.gn_stats && ncols == 32) {
+                if (p.act == 5) {       // softmax backward: dS^T = alpha * P^T .* (dP^T - dot[row]); P^T arrives as `residual`
+                    const float rv = valid ? __ldg(p.rowvec + n * p.vN + h * p.vH + w * p.vW) : 0.f;
+                    if (valid) {
+                        if (kTF32) {
+                            const float* ms = reinterpret_cast<const float*>(p.residual) + r_off + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) v[i] = (v[i] - p.alpha * rv) * ms[i];
+                        } else {
+                            const __nv_bfloat16* ms = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) v[i] = (v[i] - p.alpha * rv) * __bfloat162float(ms[i]);
+                        }
+                    }
+                }
+                if (p.gn_stats && ncols == 32 && p.act != 5) {
                     float* srow = p.gn_stats + static_cast<long long>(uniform ? n_lane0 : (valid ? n : 0)) * G * 2;
                     const int cpg = p.cpg;
                     if (p.act == 3) {       // training: store the pre-activation, normalise Swish(z) later -> stats of Swish(z)
@@ -253,7 +331,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (valid) {
                     if (f32out) {
                         float* o = reinterpret_cast<float*>(p.out) + o_off + col0 * p.oC;
-                        if (p.residual) {
+                        if (p.residual && p.act != 5) {
                             const float* rs = reinterpret_cast<const float*>(p.residual) + r_off + col0;
                             if (vec) {
 #pragma unroll
@@ -280,7 +358,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     } else {
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_off + col0 * p.oC;
-                        if (p.residual) {
+                        if (p.residual && p.act != 5) {
                             const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0;
                             if (vec) {
 #pragma unroll
