@@ -23,6 +23,12 @@ extern "C" {
 const char* b2_last_error(void);
 int b2_version(void);
 
+/* Optional split-K workspace for the tensor-core kernels: a device buffer (256-byte aligned, >= 1 MiB, first 4 KiB
+ * ZEROED: per-tile arrival counters; 32 MiB covers every layer of the reference's configurations) owned by the caller.
+ * Layers whose output tiles cannot fill the 148 SMs then split their K loop; counters are handed back zeroed.  One buffer serves one
+ * stream at a time.  Passing NULL disables split-K. */
+int b2_set_workspace(void* ws, long long bytes);
+
 /* ---- dense contractions (tcgen05 implicit GEMM) ------------------------------------------------------- */
 
 /* mode 0: Conv2d 3x3 stride 1 pad 1            (custom_layers.py:224-228), x = [N][H][W][Cin]

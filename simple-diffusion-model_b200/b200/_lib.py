@@ -16,6 +16,7 @@ _P, _I, _L, _F, _U, _D = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctyp
 
 # name -> argument ctypes, in the order of include/sdm_b200.h
 SIGNATURES = {
+    "b2_set_workspace": [_P, _L],
     "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
     "b2_gemm_nt": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P, _F, _I, _P, _L, _I, _I, _P],
     "b2_attn_scores_softmax": [_P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P],
@@ -83,9 +84,28 @@ def set_launch_hook(hook):
     _HOOK = hook
 
 
+_WORKSPACE = {}       # device index -> zeroed split-K workspace registered with the library (b2_set_workspace)
+WORKSPACE_BYTES = 32 << 20
+
+
+def _ensure_workspace():
+    """The split-K workspace belongs to the caller (PyTorch's allocator), one per device, registered on first use."""
+    dev = torch.cuda.current_device()
+    if dev not in _WORKSPACE and os.environ.get("SDM_B200_SPLIT_K", "1") != "0":
+        if torch.cuda.is_current_stream_capturing():
+            return                              # never allocate inside a capture; eager warm-up registers it first
+        buf = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=f"cuda:{dev}")
+        rc = lib().b2_set_workspace(buf.data_ptr(), WORKSPACE_BYTES)
+        if rc != 0:
+            raise B200Error(f"b2_set_workspace: {lib().b2_last_error().decode()}")
+        _WORKSPACE[dev] = buf
+
+
 def call(name, *args):
     global LAUNCHES
     handle = lib()
+    if name in ("b2_conv2d_nhwc", "b2_gemm_nt") and not _WORKSPACE:
+        _ensure_workspace()
     LAUNCHES += 1
     if _HOOK is not None:
         with _HOOK(name, args):

@@ -3,6 +3,8 @@
 #include "host_util.h"
 #include "igemm.h"
 #include "sdm_b200.h"
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2 {
@@ -12,16 +14,68 @@ int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, i
 }
 using namespace b2;
 
-static int pick_block_n(int cout, long long m_tiles, int groups) {
+// ---- tiling: N tile width and split-K factor -------------------------------------------------------------------
+// Workspace for split-K partial sums, registered once by the host side (b2_set_workspace): [1024 int counters | fp32].
+static float* g_ws = nullptr;
+static int* g_ws_counters = nullptr;
+static long long g_ws_floats = 0;
+
+extern "C" int b2_set_workspace(void* ws, long long bytes) {
+    if (!ws || bytes < (1 << 20)) { g_ws = nullptr; g_ws_counters = nullptr; g_ws_floats = 0; return 0; }
+    if ((uintptr_t)ws % 256) return set_error("b2_set_workspace: pointer must be 256-byte aligned");
+    g_ws_counters = reinterpret_cast<int*>(ws);
+    g_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
+    g_ws_floats = (bytes - 4096) / 4;
+    return 0;
+}
+
+// Picks the N tile (256 / 128 / 64 accumulator columns) and, for layers whose few output tiles cannot occupy the 148
+// SMs (deep U-Net levels: 2x2 ... 8x8 pixels per image), a split of the K loop, by minimising a small cost model
+// calibrated on B200 with tools/sweep_tiling.py (profiles/r01d_tiling_sweep_*.log):
+//   T = launch/pipeline latency + waves * k_iters/splits * t_iter(bn, machine fill) [+ split hand-off + per-slice read-back]
+// One K step (64 channels of one tap) costs 0.18 / 0.30 / 0.33 us on a lightly loaded machine (TMA-latency bound:
+// 8 / 6 / 4 pipeline stages) and 0.27 / 0.33 / 0.41 us with all SMs streaming (L2 bound).  The split hand-off is a
+// store + fence + counter round trip (~5 us) and the last split reads every partial slice back (cost ~ slice size),
+// so splitting only pays with narrow tiles.
+static void pick_tiling(int cout, long long m_tiles, int groups, int k_iters, bool allow_split, int* bn_out, int* splits_out) {
     const int sms = device_sm_count();
     const int cands[3] = {256, 128, 64};
+    const double t_light[3] = {0.33, 0.30, 0.18}, t_full[3] = {0.41, 0.33, 0.27}, slice_us[3] = {9.0, 1.5, 0.6};
+    const int split_cands[8] = {1, 2, 3, 4, 6, 8, 12, 16};
+    double best = 1e30;
+    int best_bn = 64, best_s = 1;
     for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
-        if (cout < bn && i < 2) continue;
+        if (cout < bn && i < 2 && cout <= cands[i + 1]) continue;           // a narrower tile already covers all columns
         const long long tiles = m_tiles * ((cout + bn - 1) / bn) * groups;
-        if (tiles >= sms || i == 2) return bn;
+        for (int j = 0; j < 8; ++j) {
+            const int sp = split_cands[j];
+            if (sp > 1) {
+                if (!allow_split || !g_ws || bn == 256 || k_iters / sp < 4 || tiles > 1024) break;
+                if (tiles * sp * 128LL * bn > g_ws_floats) break;
+                if (tiles * (sp - 1) >= sms) break;                              // the machine is full already
+            }
+            const long long items = tiles * sp;
+            const long long waves = (items + sms - 1) / sms;
+            const double fill = items >= sms ? 1.0 : (double)items / sms;
+            const double t_iter = t_light[i] + (t_full[i] - t_light[i]) * fill;
+            double t = 12.0 + (double)waves * ((double)k_iters / sp) * t_iter;
+            if (waves > 1) t += (double)(waves - 1) * 1.5;                       // per-tile epilogue tail that is not hidden
+            if (sp > 1) t += 5.0 + sp * slice_us[i];
+            if (t < best) { best = t; best_bn = bn; best_s = sp; }
+        }
     }
-    return 64;
+    *bn_out = best_bn;
+    *splits_out = best_s;
+    // tuning hook (tools/sweep_tiling.py): SDM_B200_FORCE_TILING="<bn>,<splits>" overrides the choice where it is legal
+    if (const char* force = getenv("SDM_B200_FORCE_TILING")) {
+        int fbn = 0, fs = 0;
+        if (sscanf(force, "%d,%d", &fbn, &fs) == 2 && (fbn == 64 || fbn == 128 || fbn == 256) && fs >= 1) {
+            const long long tiles = m_tiles * ((cout + fbn - 1) / fbn) * groups;
+            const bool split_ok = fs == 1 || (allow_split && g_ws && k_iters / fs >= 1 && tiles <= 1024 && tiles * fs * 128LL * fbn <= g_ws_floats);
+            if (split_ok) { *bn_out = fbn; *splits_out = fs; }
+        }
+    }
 }
 
 // Spatial box of <=128 output pixels: full rows first, then rows, then images.
@@ -134,9 +188,11 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         p.vec_ok = ok ? 1 : 0;
     }
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
-    const int bn = pick_block_n(Cout, m_tiles, p.groups);
+    int bn, splits;
+    pick_tiling(Cout, m_tiles, p.groups, p.taps * p.kb_per_tap, true, &bn, &splits);
     p.n_tiles = (Cout + bn - 1) / bn;
     p.b_mode = 0;
+    p.splits = splits; p.ws = g_ws; p.ws_counters = g_ws_counters;
 
     CUtensorMap ta, tb;
     {
@@ -185,8 +241,10 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
     p.bias = bias; p.alpha = alpha; p.act = act; p.out_fp32 = out_fp32;
     const bool batched = (batch1 > 1 || batch2 > 1);
     p.b_mode = batched ? 1 : 0;
-    const int bn = pick_block_n(Ncols, (long long)p.tiles_w * batch1 * batch2, 1);
+    int bn, splits;
+    pick_tiling(Ncols, (long long)p.tiles_w * batch1 * batch2, 1, p.kb_per_tap, !batched, &bn, &splits);
     p.n_tiles = (Ncols + bn - 1) / bn;
+    p.splits = splits; p.ws = g_ws; p.ws_counters = g_ws_counters;
     CUtensorMap ta, tb;
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch1, (uint64_t)batch2};
@@ -231,6 +289,7 @@ static int attn_params(IgemmParams* p, CUtensorMap* ta, CUtensorMap* tb, const v
     const int ov = dtype == 1 ? 4 : 8;
     p->vec_ok = ((ldo % ov == 0) && (o_sh % ov == 0) && (o_sn % ov == 0) && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
     p->b_mode = 1;
+    p->splits = 1;
     p->n_tiles = (P + bn - 1) / bn;
     {
         uint64_t dims[4] = {(uint64_t)d, (uint64_t)P, (uint64_t)heads, (uint64_t)N};

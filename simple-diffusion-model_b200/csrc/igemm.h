@@ -34,6 +34,12 @@ struct IgemmParams {
                                  // 4 softmax over the valid columns of each row (attention: rows = keys, columns = queries;
                                  //   gn_stats then receives per-(row, n-tile) (max, sum) when a row spans several tiles),
                                  // 5 out = alpha * residual[row][col] * (acc - rowvec[row])  (softmax backward)
+    // split-K (small-M layers whose few output tiles cannot fill 148 SMs): a work item is (tile, split); every split
+    // stores its fp32 partial tile into `ws` ([tile][split][128][BLOCK_N]); the split that arrives last (per-tile counter,
+    // self-resetting) sums the slices in split order -- deterministic -- and runs the normal epilogue.
+    int splits;
+    float* ws;
+    int* ws_counters;
     const float* rowvec;         // act 5: one value per output row, index n*vN + h*vH + w*vW
     long long vN, vH, vW;
     float* gn_stats;             // optional [N][Cout/cpg][2] (sum, sum of squares), accumulated atomically

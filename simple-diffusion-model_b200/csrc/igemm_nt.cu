@@ -102,6 +102,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+    volatile int* flag_s = reinterpret_cast<volatile int*>(tmem_holder + 1);      // split-K: arrival order of this CTA's split
     float* bias_s = reinterpret_cast<float*>(smem + S::BIAS_OFF);
 
     const int warp = threadIdx.x >> 5;
@@ -120,7 +121,8 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int splits = p.splits;
+    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * splits;     // work items
     const int k_iters = p.taps * p.kb_per_tap;
     constexpr int BK_ELEMS = 128 / sizeof(T);
     const uint32_t a_bytes = static_cast<uint32_t>(p.wb * p.hb * p.nb) * 128u;
@@ -129,22 +131,23 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(p, tile);
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+                const int split = item % splits;
+                const TileCoord tc = decode_tile(p, item / splits);
                 const int bb2 = p.b_mode ? tc.h0 : tc.g;
                 const int bb3 = p.b_mode ? tc.n0 : 0;
-                for (int t = 0; t < p.taps; ++t) {
+                const int it0 = (int)(((long long)k_iters * split) / splits), it1 = (int)(((long long)k_iters * (split + 1)) / splits);
+                for (int it = it0; it < it1; ++it) {
+                    const int t = it / p.kb_per_tap, kb = it - t * p.kb_per_tap;
                     const int ti = tc.g * p.taps + t;
                     const int aw = tc.w0 + p.tap_dw[ti], ah = tc.h0 + p.tap_dh[ti], an = tc.n0 + p.tap_dn[ti];
-                    for (int kb = 0; kb < p.kb_per_tap; ++kb) {
-                        mbar_wait(&empty[s], ph ^ 1);
-                        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-                        uint8_t* b_dst = a_dst + S::A_BYTES;
-                        mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
-                        tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
-                        tma_load_4d(b_dst, &tmB, &full[s], (t * p.kb_per_tap + kb) * BK_ELEMS, tc.nt * BLOCK_N, bb2, bb3);
-                        if (++s == STAGES) { s = 0; ph ^= 1; }
-                    }
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + S::A_BYTES;
+                    mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
+                    tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
+                    tma_load_4d(b_dst, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N, bb2, bb3);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -154,11 +157,13 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, 0);
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+                const int split = item % splits;
+                const int it0 = (int)(((long long)k_iters * split) / splits), it1 = (int)(((long long)k_iters * (split + 1)) / splits);
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int it = 0; it < k_iters; ++it) {
+                for (int it = it0; it < it1; ++it) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
@@ -167,7 +172,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_ss<kTF32>(d_tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+                        umma_ss<kTF32>(d_tmem, ad, bd, idesc, (it > it0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&empty[s]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -188,7 +193,8 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int G = p.gn_stats ? (p.Cout / p.cpg) : 0;
         const bool f32out = kTF32 || p.out_fp32;
         int acc = 0; uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+            const int tile = item / splits;
             const TileCoord tc = decode_tile(p, tile);
             const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
             const bool valid = (n_in < p.nb) && (w < p.W) && (h < p.H) && (n < p.N);
@@ -206,6 +212,41 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
+            bool from_ws = false;
+            float* ws_row = nullptr;
+            if (splits > 1) {
+                // ---- split-K: publish this split's partial sums, then only the last split to arrive runs the epilogue
+                ws_row = p.ws + (((long long)tile * splits) * 128 + row) * BLOCK_N;          // slice of split 0; split s is s*128*BLOCK_N further
+                float* mine = ws_row + (long long)(item % splits) * 128 * BLOCK_N;
+#pragma unroll 1
+                for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
+                    if (tc.nt * BLOCK_N + ch * 32 >= p.Cout) break;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            __stcg(reinterpret_cast<float4*>(mine + ch * 32) + i,
+                                   make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+                    }
+                }
+                tc_fence_before();
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                if (epi_tid == 0) {
+                    mbar_arrive_n(&tempty[acc], kEpiWarps);           // the accumulator stage is free again
+                    *flag_s = atomicAdd(p.ws_counters + tile, 1);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                const bool last = (*flag_s == splits - 1);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                if (!last) continue;
+                __threadfence();
+                from_ws = true;
+                if (epi_tid == 0) p.ws_counters[tile] = 0;
+            }
             if (p.act == 4) {
                 // ---- attention scores: each thread owns one key row of S^T (columns = queries), so the reference's
                 // softmax over the QUERY axis (custom_layers.py:147) is a purely in-thread reduction over TMEM columns.
@@ -275,8 +316,29 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int col0 = tc.nt * BLOCK_N + ch * 32;
                 if (col0 >= p.Cout) break;
                 uint32_t r[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
-                tmem_ld_wait();
+                if (from_ws) {          // sum the partial tiles of all splits (plain L2 reads, fixed order: deterministic)
+                    float4 a4[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) {
+                        for (int sp = 0; sp < splits; ++sp) {
+                            const float4* src = reinterpret_cast<const float4*>(ws_row + (long long)sp * 128 * BLOCK_N + ch * 32);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 x = __ldcg(src + i);
+                                a4[i].x += x.x; a4[i].y += x.y; a4[i].z += x.z; a4[i].w += x.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        r[4 * i] = __float_as_uint(a4[i].x); r[4 * i + 1] = __float_as_uint(a4[i].y);
+                        r[4 * i + 2] = __float_as_uint(a4[i].z); r[4 * i + 3] = __float_as_uint(a4[i].w);
+                    }
+                } else {
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                    tmem_ld_wait();
+                }
                 const int ncols = min(32, p.Cout - col0);
                 const bool vec = p.vec_ok && ncols == 32;
                 float v[32];
@@ -392,6 +454,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             }
+            if (splits > 1) continue;                 // accumulator already released right after the partials were published
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -418,7 +481,7 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmPar
         if (e != cudaSuccess) return set_error("igemm_nt: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.splits;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     kern<<<grid, kThreads, S::TOTAL, st>>>(a, b, p);
     cudaError_t e = cudaGetLastError();
