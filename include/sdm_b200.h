@@ -74,14 +74,15 @@ int b2_rowdot(const void* a, long long lda, const void* b, long long ldb, long l
 
 /* ---- gradients of the dense contractions (tcgen05 "TN" GEMM: contraction over pixel / sequence rows) -------- */
 
-/* Weight gradient of b2_conv2d_nhwc's three modes (autograd's convolution_backward in the reference), accumulated
- * with fp32 atomics into a ZEROED buffer in kernel layout: mode 0/1 [Cout][9][Cin], mode 2 [4][Cout][4][Cin].
+/* Weight gradient of b2_conv2d_nhwc's three modes (autograd's convolution_backward in the reference), written (plain
+ * stores when one work item owns a tile, fp32 atomics under split-K) into a ZEROED buffer in kernel layout: mode 0/1 [Cout][9][Cin], mode 2 [4][Cout][4][Cin].
  * x: forward input (mode 1: its parity planes); dz: gradient w.r.t. the conv pre-activation output
  * (mode 2: [N][2H][2W][Cout]); (H, W) as in b2_conv2d_nhwc. */
 int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* dz, int Cout,
                     long long lddz, float* grad_packed, int dtype, void* stream);
 /* C (+)= alpha * A^T . B with A [K][M], B [K][Ncols] (rows = contraction index), optionally batched.
- * out_mode 0: fp32 atomic accumulate (Linear weight grads); out_mode 1: store in `dtype` (attention dV, dK). */
+ * out_mode 0: fp32 result added into a ZEROED C (Linear weight grads; atomics only under split-K);
+ * out_mode 1: store in `dtype` (attention products). */
 int b2_gemm_tn(const void* A, long long lda, long long a_s1, long long a_s2, const void* B, long long ldb,
                long long b_s1, long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2, int M,
                int Ncols, int K, int batch1, int batch2, float alpha, int out_mode, int dtype, void* stream);

@@ -383,17 +383,26 @@ static int tn_block_n(int ncols, int dtype) {
     return ncols >= 128 ? 128 : (ncols >= 64 ? 64 : 32);
 }
 
+// Split-K factor of the TN kernel: work items = tiles x splits run in waves of (#SMs) persistent CTAs; a split costs
+// an fp32 atomic pass over the tile instead of plain stores.  Pick the factor with the least (waves x K boxes per item),
+// charging each extra split a few K boxes for the atomics, and prefer no split when the tiles alone fill the machine.
 static void tn_pick_splits(GemmTnParams* p, int batches) {
     const int sms = device_sm_count();
     const long long base = (long long)p->m_tiles * p->n_tiles * p->taps * batches;
     const int k_boxes = p->kt_w * p->kt_h * p->kt_n;
-    int splits = 1;
-    if (p->out_mode == 0 && base < 2LL * sms) {
-        splits = (int)((2LL * sms + base - 1) / base);
+    int best_s = 1;
+    if (p->out_mode == 0) {
+        double best = 1e30;
         const int cap = k_boxes / 4 > 1 ? k_boxes / 4 : 1;
-        if (splits > cap) splits = cap;
+        for (int s = 1; s <= cap && s <= 64; ++s) {
+            const long long items = base * s;
+            const long long waves = (items + sms - 1) / sms;
+            const double cost = (double)waves * ((k_boxes + s - 1) / s + 6.0) + (s > 1 ? 8.0 + 2.0 * s : 0.0);
+            if (cost < best) { best = cost; best_s = s; }
+            if (items >= 4LL * sms) break;
+        }
     }
-    p->splits = splits < 1 ? 1 : splits;
+    p->splits = best_s;
 }
 
 // Weight gradient of the three convolution flavours, accumulated (fp32 atomics) into a zero-initialised buffer in

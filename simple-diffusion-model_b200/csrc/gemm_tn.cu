@@ -14,7 +14,7 @@
 namespace b2 {
 
 constexpr int kTnEpiWarps = 8;
-constexpr int kTnThreads = 64 + kTnEpiWarps * 32;
+constexpr int kTnThreads = 64 + kTnEpiWarps * 32 + 32;     // + a second TMA producer warp (warp 10)
 constexpr int kTnBK = 64;     // pixel rows per pipeline stage
 
 template <int BLOCK_N, int STAGES>
@@ -82,7 +82,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int k_boxes = p.kt_w * p.kt_h * p.kt_n;
     const uint32_t box_rows = static_cast<uint32_t>(p.wb * p.hb * p.nb);
 
-    if (warp == 0) {
+    if (warp == 0 || warp == kTnThreads / 32 - 1) {
+        // Two TMA producer warps: a stage is 2 + BLOCK_N/64 slab loads (one 128-byte-wide box each: the SWIZZLE_128B limit),
+        // and a single thread could not issue them fast enough to keep the 4-stage ring full (ncu: the producer sat on
+        // UTMALDG while the MMA warp starved).  Producer 0 takes the even slabs and posts the byte count, producer 1 the odd.
+        const int prod = warp == 0 ? 0 : 1;
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -98,16 +102,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
                     uint8_t* b_dst = a_dst + A_BYTES;
-                    mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
-#pragma unroll
-                    for (int sl = 0; sl < A_SLABS; ++sl)
-                        tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
+                    if (prod == 0) mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
                     const int bw = w0 + p.tap_dw[wk.tap];
                     const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
                     const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
 #pragma unroll
-                    for (int sl = 0; sl < B_SLABS; ++sl)
-                        tma_load_4d(b_dst + sl * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + sl * SLAB, bw, bh, bn);
+                    for (int sl = 0; sl < A_SLABS + B_SLABS; ++sl) {
+                        if ((sl & 1) != prod) continue;
+                        if (sl < A_SLABS)
+                            tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
+                        else
+                            tma_load_4d(b_dst + (sl - A_SLABS) * SLAB_BYTES, &tmB, &full[s],
+                                        wk.nt_in_tap * BLOCK_N + (sl - A_SLABS) * SLAB, bw, bh, bn);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -166,7 +173,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld_wait();
                     const int ncols = min(32, p.Ncols - col0);
                     if (!valid) continue;
-                    if (p.out_mode == 0) {
+                    if (p.out_mode == 0 && p.splits == 1) {
+                        // one work item owns this output tile: the buffer is zero on entry (ABI), so a plain store IS the
+                        // accumulation -- no atomics (they throttled the epilogue below the main loop's pace)
+                        float* o = reinterpret_cast<float*>(p.out) + off + col0;
+                        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(o)[i] =
+                                    make_float4(__uint_as_float(r[4 * i]) * p.alpha, __uint_as_float(r[4 * i + 1]) * p.alpha,
+                                                __uint_as_float(r[4 * i + 2]) * p.alpha, __uint_as_float(r[4 * i + 3]) * p.alpha);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = __uint_as_float(r[i]) * p.alpha;
+                        }
+                    } else if (p.out_mode == 0) {
                         float* o = reinterpret_cast<float*>(p.out) + off + col0;
                         if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
