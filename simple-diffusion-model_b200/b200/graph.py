@@ -175,6 +175,7 @@ class GraphedUNet:
         if cond is not None:
             entry["cond"].copy_(cond, non_blocking=True)
         entry["graph"].replay()
+        _lib.LAUNCHES += entry["launches"]
         return entry["out"]
 
     def _capture(self, x, t, cond, wkey):
@@ -190,7 +191,9 @@ class GraphedUNet:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
         with torch.cuda.graph(g, capture_error_mode="thread_local"), torch.no_grad():
             st["out"] = eng.forward(st["x"], st["t"], st["cond"])
+        st["launches"] = _lib.LAUNCHES - l0
         st["graph"] = g
         return st

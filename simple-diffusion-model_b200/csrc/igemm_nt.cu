@@ -253,7 +253,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (half == 0) {
                     const int ncols_tile = min(BLOCK_N, p.Cout - tc.nt * BLOCK_N);
                     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-                    const float sc = p.alpha * 1.4426950408889634f;          // exp(x) = exp2(x * log2 e)
+                    // exp(x) = exp2(x * log2 e).  The scaled score is rounded ONCE (__fmul_rn, never contracted into an FMA
+                    // with the subtraction): the row maximum must map to exactly exp2(0) even for logits of 1e14, which
+                    // the first DDIM steps of the cosine schedule produce on an untrained net (1/sqrt(abar_T) = 2e7).
+                    const float sc = p.alpha * 1.4426950408889634f;
                     float mx = -INFINITY;
 #pragma unroll 1
                     for (int c0 = 0; c0 < ncols_tile; c0 += 32) {
@@ -261,7 +264,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tmem_ld32(trow + c0, r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) mx = fmaxf(mx, __uint_as_float(r[i]) * sc);
+                        for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) mx = fmaxf(mx, __fmul_rn(__uint_as_float(r[i]), sc));
                     }
                     float z = 0.f;
 #pragma unroll 1
@@ -270,7 +273,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tmem_ld32(trow + c0, r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) z += exp2f(__uint_as_float(r[i]) * sc - mx);
+                        for (int i = 0; i < 32; ++i) if (c0 + i < ncols_tile) z += exp2f(__fsub_rn(__fmul_rn(__uint_as_float(r[i]), sc), mx));
                     }
                     const float inv = p.n_tiles == 1 ? 1.0f / z : 1.0f;       // several tiles per row: normalised by the fix-up pass
 #pragma unroll 1
@@ -282,7 +285,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const int col0 = tc.nt * BLOCK_N + c0;
                         float v[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = exp2f(__uint_as_float(r[i]) * sc - mx) * inv;
+                        for (int i = 0; i < 32; ++i) v[i] = exp2f(__fsub_rn(__fmul_rn(__uint_as_float(r[i]), sc), mx)) * inv;
                         const bool full = p.vec_ok && (c0 + 32 <= ncols_tile);
                         if (f32out) {
                             float* o = reinterpret_cast<float*>(p.out) + o_off + col0;
