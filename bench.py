@@ -376,7 +376,10 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     achieved_tf = flops_step / (kern_ms / 1000.0) / 1e12 if kern_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "igemm_nt_kernel / gemm_tn_kernel (tcgen05 implicit GEMM: conv3x3/convT/linear/softmax(QK^T)/PV)",
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the family's heaviest shape (conv3x3 N256 16x16
+                # C1024, 1237 GFLOP, algorithmic bytes 287e6) from profiles/r01d_ncu_conv_b256.md (ncu --set full)
+                "traffic": 253.9e6 if batch == BATCH else None, "traffic_unit": "bytes/launch (heaviest shape)",
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": n_kern, "avg_launch_ms": kern_ms / max(n_kern, 1),
                 "kernel_share_of_step": kern_ms / ms_eager if ms_eager else None,
