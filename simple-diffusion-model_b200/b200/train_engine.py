@@ -177,6 +177,16 @@ class UNetTrainEngine(UNetEngine):
     def __init__(self, net):
         super().__init__(net)
         self.layout = None
+        # Weight gradients do not feed the backward chain, so they CAN run on a second stream next to the data-gradient /
+        # normalisation kernels of the following layers (fork/join with stream events, kept by CUDA-graph capture).
+        # Measured on B200 (tools/bench_train.py, batch 32 @64x64 and batch 16 @128x128): within +-1 % of the single-stream
+        # schedule -- both GEMM kernels are persistent 1-CTA-per-SM grids with ~200 KB of shared memory, so two of them
+        # cannot share an SM -- hence off by default (SDM_B200_OVERLAP_WGRAD=1 enables it).
+        import os
+        self.overlap_wgrad = os.environ.get("SDM_B200_OVERLAP_WGRAD", "0") == "1"
+        self._side_stream = None
+        self._side_busy = False
+        self._side_keep = []               # operands of in-flight side-stream kernels (kept alive until the join)
         self.post_backward = None          # optional callable(layout), runs when every gradient is complete
         self.on_grads_ready = None         # optional callable(layout, lo, hi): flat range [lo, hi) is final (DP buckets)
 
@@ -390,11 +400,30 @@ class UNetTrainEngine(UNetEngine):
         cin_pad = x.shape[3]
         if self.layout.is_cl(conv.weight) and cin_pad == cin:
             # channels-last stored weight: the flat gradient slice IS the kernel layout (zeroed at the start of backward)
-            ops.conv2d_wgrad(mode, x, dz, cout, self.layout.raw_grad(conv.weight))
+            grad = self.layout.raw_grad(conv.weight)
+            if not self.overlap_wgrad:
+                ops.conv2d_wgrad(mode, x, dz, cout, grad)
+                return
+            main = torch.cuda.current_stream(x.device)
+            if self._side_stream is None or self._side_stream.device != x.device:
+                self._side_stream = torch.cuda.Stream(device=x.device)
+            side = self._side_stream
+            side.wait_stream(main)                      # dz (and the zeroed gradient buffer) are ready
+            with torch.cuda.stream(side):
+                ops.conv2d_wgrad(mode, x, dz, cout, grad)
+            self._side_busy = True
+            self._side_keep.append((x, dz))
             return
         packed = self._scratch(cout * 9 * cin_pad, x.device)
         ops.conv2d_wgrad(mode, x, dz, cout, packed)
         call("b2_unpack_weight_grad", 0, ptr(packed), ptr(self.layout.view(conv.weight)), cout, cin, cin_pad, 0, stream())
+
+    def _join_side(self):
+        """Main stream waits for the weight-gradient stream (before gradients are consumed: all-reduce, optimiser)."""
+        if self._side_busy:
+            torch.cuda.current_stream(self._side_stream.device).wait_stream(self._side_stream)
+            self._side_busy = False
+        self._side_keep.clear()
 
     def _dgrad_s1(self, conv, dz, residual=None, out=None):
         code = ops.code_of(dz)
@@ -505,7 +534,9 @@ class UNetTrainEngine(UNetEngine):
             elif kind == "mark" and self.on_grads_ready is not None:
                 lo, hi = lay.module_range(entry[1])
                 if hi > lo:
+                    self._join_side()
                     self.on_grads_ready(lay, lo, hi)
+        self._join_side()
         for p in lay.params:
             v = lay.view(p)
             if p.grad is None or p.grad.data_ptr() == v.data_ptr():
