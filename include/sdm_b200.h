@@ -128,7 +128,7 @@ int b2_small_gemm(const float* A, long long lda, int ta, const float* B, long lo
 /* Backward of Conv -> Swish -> AdaGN (custom_layers.py:240-245, :35-45) from dout to the conv pre-activation:
  * dz = rstd*(s*gamma*dout - m1 - xh*m2) * swish'(z).  Also accumulates ds (gradient of the AdaGN scale vector, row
  * stride ds_bstride, 0 = embedding broadcast over the batch), dgamma, dbeta, dbias (+=, fp32).  z: pre-activation
- * saved by the forward; stats: the forward's (sum, sumsq); work: >= 2*N*C + 2*N*groups floats of scratch. */
+ * saved by the forward; stats: the forward's (sum, sumsq); work: 2*N*C floats of scratch, ZEROED by the caller. */
 int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats, const float* gamma,
                  const float* beta, const float* s, long long s_bstride, float* work, float* ds, long long ds_bstride,
                  float* dgamma, float* dbeta, void* dz, long long lddz, float* dbias, int N, int HW, int C, int groups,

@@ -425,6 +425,16 @@ class UNetTrainEngine(UNetEngine):
             self._side_busy = False
         self._side_keep.clear()
 
+    def _bwd_work(self, numel, device):
+        """Zeroed fp32 scratch for one AdaGN backward, carved from an arena that is cleared ONCE per backward pass."""
+        arena = getattr(self, "_work_arena", None)
+        if arena is None or self._work_used + numel > arena.numel():
+            arena = torch.zeros((max(numel, 1 << 20),), dtype=torch.float32, device=device)     # only for standalone block runs
+            self._work_arena, self._work_used = arena, 0
+        out = arena[self._work_used:self._work_used + numel]
+        self._work_used += (numel + 3) // 4 * 4
+        return out
+
     def _dgrad_s1(self, conv, dz, residual=None, out=None):
         code = ops.code_of(dz)
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
@@ -437,7 +447,7 @@ class UNetTrainEngine(UNetEngine):
         code = ops.code_of(z)
         n, hh, ww, c = z.shape
         lay = self.layout
-        work = torch.empty((2 * n * c + 2 * n * gn.num_groups,), dtype=torch.float32, device=z.device)
+        work = self._bwd_work(2 * n * c, z.device)
         dz = torch.empty((n, hh, ww, c), dtype=z.dtype, device=z.device)
         s = ctx["s_all"][:, off:off + c]
         ds = ctx["ds_all"][:, off:off + c]
@@ -463,6 +473,9 @@ class UNetTrainEngine(UNetEngine):
         dev = dout.device
         lay = self.grad_layout(dev)
         lay.flat.zero_()
+        need = sum(2 * e[2][2].shape[0] * e[2][2].shape[3] + 2 * e[1][2].shape[0] * e[1][2].shape[3] + 8
+                   for e in tape if e[0] == "res")
+        self._work_arena, self._work_used = torch.zeros((max(need, 4),), dtype=torch.float32, device=dev), 0
         code = self._code()
         kal = ops.K_ALIGN[code]
         ctx = None

@@ -1,5 +1,5 @@
 // Memory-bound kernels of the backward pass (the reference gets these from autograd): GroupNorm x AdaGN backward
-// (two streaming passes + a tiny per-image finalize), Swish / tanh backward with fused bias gradients, query-axis
+// (two streaming passes; the per-image finalize is folded into the second), Swish / tanh backward with fused bias gradients, query-axis
 // softmax backward, column sums, and the kernel-layout -> parameter-layout gradient unpack.
 #include "host_util.h"
 #include "ptx.cuh"
@@ -108,44 +108,41 @@ __global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ld
     block_colsum_atomic<V>(s2, red, C, c0, prow, rows_per_block, a2 + (long long)n * C);
 }
 
-// Finalize (one CTA per image): ds[n][c] += gamma*a2 + (beta+1)*a1; dgamma[c] += s*a2; dbeta[c] += s*a1;
-// m[n][g] = (sum_{c in g} s*gamma*a1, sum_{c in g} s*gamma*a2) / (cpg*HW).
-__global__ void adagn_bwd_finalize_kernel(const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ s,
-                                          long long s_bstride, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                          float* __restrict__ ds, long long ds_bstride, float* __restrict__ dgamma,
-                                          float* __restrict__ dbeta, float* __restrict__ m12, int HW, int C, int groups) {
-    extern __shared__ float gs[];      // [groups][2]
-    const int n = blockIdx.x;
-    const int cpg = C / groups;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gs[i] = 0.f;
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float x1 = a1[(long long)n * C + c], x2 = a2[(long long)n * C + c];
-        const float sc = s[(long long)n * s_bstride + c], ga = gamma[c];
-        atomicAdd(ds + (long long)n * ds_bstride + c, ga * x2 + (beta[c] + 1.0f) * x1);
-        atomicAdd(dgamma + c, sc * x2);
-        atomicAdd(dbeta + c, sc * x1);
-        atomicAdd(&gs[(c / cpg) * 2], sc * ga * x1);
-        atomicAdd(&gs[(c / cpg) * 2 + 1], sc * ga * x2);
-    }
-    __syncthreads();
-    const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) m12[(long long)n * groups * 2 + i] = gs[i] * inv_cnt;
-}
-
 // Pass 2: dz = rstd * (s*gamma*dout - m1 - xh*m2) * swish'(z);  dbias[c] += sum dz.
+// Every CTA first folds the per-channel sums of pass 1 into the group terms of its image,
+//   m[n][g] = (sum_{c in g} s*gamma*a1, sum_{c in g} s*gamma*a2) / (cpg*HW)          (C loads from L2, shared-memory adds),
+// and the first slab of each image also emits ds[n][c] += gamma*a2 + (beta+1)*a1, dgamma[c] += s*a2, dbeta[c] += s*a1 --
+// a separate finalize launch per layer (100 latency-bound launches per backward pass) is not needed.
 template <typename T>
 __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
-                                       const float* __restrict__ stats, const float* __restrict__ m12,
-                                       const float* __restrict__ s, long long s_bstride, const float* __restrict__ gamma,
+                                       const float* __restrict__ stats, const float* __restrict__ a1,
+                                       const float* __restrict__ a2, const float* __restrict__ s, long long s_bstride,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ds,
+                                       long long ds_bstride, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        T* __restrict__ dz, long long lddz, float* __restrict__ dbias, int HW, int C,
                                        int groups, float eps, int slabs, int rows_per_block) {
+    extern __shared__ float red[];
+    float* gs = red;                                  // [groups][2]; the same buffer serves the dbias reduction at the end
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
     const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
     const int cpg = C / groups;
     const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gs[i] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float x1 = a1[(long long)n * C + c], x2 = a2[(long long)n * C + c];
+        const float sc = __ldg(s + (long long)n * s_bstride + c), ga = __ldg(gamma + c);
+        if (slab == 0) {
+            atomicAdd(ds + (long long)n * ds_bstride + c, ga * x2 + (__ldg(beta + c) + 1.0f) * x1);
+            atomicAdd(dgamma + c, sc * x2);
+            atomicAdd(dbeta + c, sc * x1);
+        }
+        atomicAdd(&gs[(c / cpg) * 2], sc * ga * x1);
+        atomicAdd(&gs[(c / cpg) * 2 + 1], sc * ga * x2);
+    }
+    __syncthreads();
     float mean[V], rstd[V], sg[V], m1[V], m2[V], db[V];
     gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
     {
@@ -156,10 +153,11 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
         for (int j = 0; j < V; ++j) {
             const int g = (c0 + j) / cpg;
             sg[j] = sc[j] * ga[j];
-            m1[j] = m12[((long long)n * groups + g) * 2]; m2[j] = m12[((long long)n * groups + g) * 2 + 1];
+            m1[j] = gs[g * 2] * inv_cnt; m2[j] = gs[g * 2 + 1] * inv_cnt;
             db[j] = 0.f;
         }
     }
+    __syncthreads();                                  // gs is dead from here on: `red` may be reused
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
@@ -196,10 +194,7 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
         }
     };
     pipelined_rows<Buf>(p0 + prow, p1, U * k, load, proc);
-    if (dbias) {
-        extern __shared__ float red[];
-        block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
-    }
+    if (dbias) block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
 }
 
 extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
@@ -212,23 +207,20 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
     const int cv = C / V;
     if (cv > 1024) return set_error("b2_adagn_bwd: C too large");
     cudaStream_t st = (cudaStream_t)stream;
-    // work: [2][N][C] (a1, a2) + [N][groups][2] (m1, m2), all fp32
+    // work: [2][N][C] fp32 (a1, a2), zeroed by the caller
     float* a1 = work;
     float* a2 = work + (long long)N * C;
-    float* m12 = work + 2LL * N * C;
-    cudaError_t e = cudaMemsetAsync(work, 0, 2LL * N * C * sizeof(float), st);
-    if (e != cudaSuccess) return set_error("b2_adagn_bwd: memset: %s", cudaGetErrorString(e));
     const SlabLaunch sl = slab_launch(N, HW, cv);
-    const size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
+    size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
+    if (red_bytes < (size_t)groups * 2 * sizeof(float)) red_bytes = (size_t)groups * 2 * sizeof(float);
     if (dtype == 0)
         adagn_bwd_reduce_kernel<bf16><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     else
         adagn_bwd_reduce_kernel<float><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
-    adagn_bwd_finalize_kernel<<<N, 256, groups * 2 * sizeof(float), st>>>(a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, m12, HW, C, groups);
     if (dtype == 0)
-        adagn_bwd_apply_kernel<bf16><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, m12, s, s_bstride, gamma, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        adagn_bwd_apply_kernel<bf16><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     else
-        adagn_bwd_apply_kernel<float><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, m12, s, s_bstride, gamma, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        adagn_bwd_apply_kernel<float><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     LAUNCH_CHECK("b2_adagn_bwd");
 }
 
