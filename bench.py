@@ -26,7 +26,7 @@ import torch  # noqa: E402
 METRIC = "ddim50_sampled_images_per_s"
 UNIT = "img/s"
 IMG, BATCH, STEP_SIZE, T_MAX = 64, 256, 20, 1000
-TRAIN_IMG, TRAIN_BATCH, TRAIN_COND = 128, 16, 10        # BASELINE.json configs[2]: 128x128 label-conditioned, bf16, DP
+TRAIN_IMG, TRAIN_BATCH, TRAIN_COND = 128, 32, 10        # BASELINE.json configs[2]: 128x128 label-conditioned, bf16, DP
 
 
 def load_peaks():

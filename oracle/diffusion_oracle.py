@@ -31,7 +31,7 @@ def _lin(sd, key, x):
 def sinusoid(t, time_dim):
     """models/custom_layers.py:84-90: [sin(t f_k), cos(t f_k)], f_k = exp(-k ln(1e4)/(half-1))."""
     half = time_dim // 2
-    k = torch.arange(half, dtype=torch.float32)
+    k = torch.arange(half, dtype=torch.float32, device=t.device)   # device-agnostic: the GPU tests also run this restatement through torch eager
     freq = torch.exp(k * -(math.log(10_000) / (half - 1)))
     arg = t[:, None] * freq[None, :]
     return torch.cat((arg.sin(), arg.cos()), dim=1)
