@@ -63,6 +63,8 @@ template <typename T>
 __global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
                                         const float* __restrict__ stats, float* __restrict__ a1, float* __restrict__ a2,
                                         int HW, int C, int groups, float eps, int slabs, int rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
@@ -121,6 +123,8 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
                                        long long ds_bstride, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        T* __restrict__ dz, long long lddz, float* __restrict__ dbias, int HW, int C,
                                        int groups, float eps, int slabs, int rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float red[];
     float* gs = red;                                  // [groups][2]; the same buffer serves the dbias reduction at the end
     constexpr int V = V16<T>::N;
@@ -214,13 +218,13 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
     size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
     if (red_bytes < (size_t)groups * 2 * sizeof(float)) red_bytes = (size_t)groups * 2 * sizeof(float);
     if (dtype == 0)
-        adagn_bwd_reduce_kernel<bf16><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        B2_LAUNCH((adagn_bwd_reduce_kernel<bf16>), N * sl.slabs, sl.threads, red_bytes, st, (const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     else
-        adagn_bwd_reduce_kernel<float><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        B2_LAUNCH((adagn_bwd_reduce_kernel<float>), N * sl.slabs, sl.threads, red_bytes, st, (const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     if (dtype == 0)
-        adagn_bwd_apply_kernel<bf16><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        B2_LAUNCH((adagn_bwd_apply_kernel<bf16>), N * sl.slabs, sl.threads, red_bytes, st, (const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     else
-        adagn_bwd_apply_kernel<float><<<N * sl.slabs, sl.threads, red_bytes, st>>>((const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        B2_LAUNCH((adagn_bwd_apply_kernel<float>), N * sl.slabs, sl.threads, red_bytes, st, (const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     LAUNCH_CHECK("b2_adagn_bwd");
 }
 
@@ -231,6 +235,8 @@ template <typename T>
 __global__ void act_kernel(int mode, const T* __restrict__ a, long long lda, const T* __restrict__ z, long long ldz,
                            T* __restrict__ out, long long ldo, float* __restrict__ dbias, long long rows, int C,
                            int rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
@@ -297,13 +303,15 @@ extern "C" int b2_act(int mode, const void* a, long long lda, const void* z, lon
     const long long cap = 8LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (dtype == 0) act_kernel<bf16><<<(int)blocks, cv * k, (size_t)k * C * sizeof(float), (cudaStream_t)stream>>>(mode, (const bf16*)a, lda, (const bf16*)z, ldz, (bf16*)out, ldo, dbias, rows, C, k);
-    else act_kernel<float><<<(int)blocks, cv * k, (size_t)k * C * sizeof(float), (cudaStream_t)stream>>>(mode, (const float*)a, lda, (const float*)z, ldz, (float*)out, ldo, dbias, rows, C, k);
+    if (dtype == 0) B2_LAUNCH((act_kernel<bf16>), (int)blocks, cv * k, (size_t)k * C * sizeof(float), (cudaStream_t)stream, mode, (const bf16*)a, lda, (const bf16*)z, ldz, (bf16*)out, ldo, dbias, rows, C, k);
+    else B2_LAUNCH((act_kernel<float>), (int)blocks, cv * k, (size_t)k * C * sizeof(float), (cudaStream_t)stream, mode, (const float*)a, lda, (const float*)z, ldz, (float*)out, ldo, dbias, rows, C, k);
     LAUNCH_CHECK("b2_act");
 }
 
 // fp32 elementwise helpers for the tiny embedding MLPs: mode 0 y = swish(z); mode 1 dz = dy * swish'(z); mode 2 d *= 1 - y^2 (tanh).
 __global__ void f32_act_kernel(int mode, const float* __restrict__ a, const float* __restrict__ z, float* __restrict__ out, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         if (mode == 0) out[i] = swishf(z[i]);
         else if (mode == 1) out[i] = a[i] * swish_grad(z[i]);
@@ -315,7 +323,7 @@ extern "C" int b2_f32_act(int mode, const float* a, const float* z, float* out, 
     const long long cap = 8LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    f32_act_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mode, a, z, out, n);
+    B2_LAUNCH((f32_act_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, mode, a, z, out, n);
     LAUNCH_CHECK("b2_f32_act");
 }
 
@@ -324,6 +332,8 @@ extern "C" int b2_f32_act(int mode, const float* a, const float* z, float* out, 
 template <typename T>
 __global__ void softmax_query_axis_bwd_kernel(const T* __restrict__ P, const float* __restrict__ dP, T* __restrict__ dS,
                                               int B, int Pq, int Pk, long long ldp, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)B * Pk;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx % Pk);
@@ -345,8 +355,8 @@ extern "C" int b2_softmax_query_axis_bwd(const void* P, const float* dP, void* d
     const long long cap = 8LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (dtype == 0) softmax_query_axis_bwd_kernel<bf16><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>((const bf16*)P, dP, (bf16*)dS, B, Pq, Pk, ldp, scale);
-    else softmax_query_axis_bwd_kernel<float><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>((const float*)P, dP, (float*)dS, B, Pq, Pk, ldp, scale);
+    if (dtype == 0) B2_LAUNCH((softmax_query_axis_bwd_kernel<bf16>), (int)blocks, 128, 0, (cudaStream_t)stream, (const bf16*)P, dP, (bf16*)dS, B, Pq, Pk, ldp, scale);
+    else B2_LAUNCH((softmax_query_axis_bwd_kernel<float>), (int)blocks, 128, 0, (cudaStream_t)stream, (const float*)P, dP, (float*)dS, B, Pq, Pk, ldp, scale);
     LAUNCH_CHECK("b2_softmax_query_axis_bwd");
 }
 
@@ -354,6 +364,8 @@ extern "C" int b2_softmax_query_axis_bwd(const void* P, const float* dP, void* d
 // kind 0: packed [Cout][9][Cin_pad] -> grad [Cout][Cin][3][3];  kind 2: packed [4][Cout][4][Cin] -> grad [Cin][Cout][4][4].
 __global__ void unpack_weight_grad_kernel(int kind, const float* __restrict__ packed, float* __restrict__ grad, int Cout, int Cin,
                                           int Cin_pad, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = kind == 0 ? (long long)Cout * Cin * 9 : (long long)Cin * Cout * 16;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         float v;
@@ -376,7 +388,7 @@ extern "C" int b2_unpack_weight_grad(int kind, const float* packed, float* grad,
     long long blocks = (total + 255) / 256;
     const long long cap = 16LL * device_sm_count();
     if (blocks > cap) blocks = cap;
-    unpack_weight_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(kind, packed, grad, Cout, Cin, Cin_pad, accumulate);
+    B2_LAUNCH((unpack_weight_grad_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, kind, packed, grad, Cout, Cin, Cin_pad, accumulate);
     LAUNCH_CHECK("b2_unpack_weight_grad");
 }
 
@@ -384,6 +396,8 @@ extern "C" int b2_unpack_weight_grad(int kind, const float* packed, float* grad,
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, T* __restrict__ out,
                            long long ldo, long long rows, int cv) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int V = V16<T>::N;
     const long long total = rows * cv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -404,7 +418,7 @@ extern "C" int b2_add(const void* a, long long lda, const void* b, long long ldb
     const long long cap = 8LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (dtype == 0) add_kernel<bf16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out, ldo, rows, C / V);
-    else add_kernel<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, (const float*)b, ldb, (float*)out, ldo, rows, C / V);
+    if (dtype == 0) B2_LAUNCH((add_kernel<bf16>), (int)blocks, 256, 0, (cudaStream_t)stream, (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out, ldo, rows, C / V);
+    else B2_LAUNCH((add_kernel<float>), (int)blocks, 256, 0, (cudaStream_t)stream, (const float*)a, lda, (const float*)b, ldb, (float*)out, ldo, rows, C / V);
     LAUNCH_CHECK("b2_add");
 }

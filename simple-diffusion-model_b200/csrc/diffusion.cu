@@ -52,6 +52,8 @@ __device__ __forceinline__ float4 philox_normal4(const Philox& ph, unsigned long
 
 __global__ void philox_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
                                      long long first_elem) {
+    pdl_launch_dependents();
+    pdl_wait();
     const Philox ph(seed);
     const long long nv = (n + 3) / 4;
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nv; v += (long long)gridDim.x * blockDim.x) {
@@ -64,7 +66,7 @@ __global__ void philox_normal_kernel(float* __restrict__ out, long long n, unsig
 extern "C" int b2_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset,
                                 long long first_elem, void* stream) {
     if (first_elem % 4) return set_error("b2_philox_normal: first_elem must be a multiple of 4");
-    philox_normal_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, first_elem);
+    B2_LAUNCH((philox_normal_kernel), ew_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream, out, n, seed, offset, first_elem);
     LAUNCH_CHECK("b2_philox_normal");
 }
 
@@ -79,6 +81,8 @@ __device__ __forceinline__ float cosine_abar(float t, float T) {
 __global__ void qsample_kernel(const float* __restrict__ img, const float* __restrict__ eps, float* __restrict__ out,
                                const long long* __restrict__ steps, int steps_count, const float* __restrict__ abar_table,
                                int max_step, long long per_image, int vec_per_image_blocks) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = blockIdx.x / vec_per_image_blocks, blk = blockIdx.x % vec_per_image_blocks;
     const long long t = steps[steps_count == 1 ? 0 : n];
     const float abar = abar_table ? abar_table[t] : cosine_abar((float)t, (float)max_step);
@@ -103,7 +107,7 @@ extern "C" int b2_qsample(const float* img, const float* eps, float* out, const 
     const int cap = (device_sm_count() * 16 + N - 1) / N;
     if (bpi > cap) bpi = cap;
     if (bpi < 1) bpi = 1;
-    qsample_kernel<<<N * bpi, 256, 0, (cudaStream_t)stream>>>(img, eps, out, steps, steps_count, abar_table, max_step, per_image, bpi);
+    B2_LAUNCH((qsample_kernel), N * bpi, 256, 0, (cudaStream_t)stream, img, eps, out, steps, steps_count, abar_table, max_step, per_image, bpi);
     LAUNCH_CHECK("b2_qsample");
 }
 
@@ -112,6 +116,8 @@ extern "C" int b2_qsample(const float* img, const float* eps, float* out, const 
 __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ noise,
                                  float* __restrict__ x_out, float* __restrict__ x0_out, long long n, float c_scale, float c_s,
                                  float c_an, float c_dir, float sigma, int last) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long nv = n / 4;
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nv; v += (long long)gridDim.x * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + v), b = __ldg(reinterpret_cast<const float4*>(e) + v);
@@ -133,7 +139,7 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
 extern "C" int b2_ddim_step(const float* x_t, const float* eps_hat, const float* noise, float* x_out, float* x0_out,
                             long long n, float c_scale, float c_s, float c_an, float c_dir, float sigma, int last, void* stream) {
     if (n % 4) return set_error("b2_ddim_step: element count must be a multiple of 4");
-    ddim_step_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x_t, eps_hat, noise, x_out, x0_out, n, c_scale, c_s, c_an, c_dir, sigma, last);
+    B2_LAUNCH((ddim_step_kernel), ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, x_t, eps_hat, noise, x_out, x0_out, n, c_scale, c_s, c_an, c_dir, sigma, last);
     LAUNCH_CHECK("b2_ddim_step");
 }
 
@@ -141,6 +147,8 @@ extern "C" int b2_ddim_step(const float* x_t, const float* eps_hat, const float*
 __global__ void ddpm_step_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ z_in,
                                  float* __restrict__ out, long long n, float scale1, float scale2, float sigma, int use_philox,
                                  unsigned long long seed, unsigned long long offset, long long first_elem) {
+    pdl_launch_dependents();
+    pdl_wait();
     const Philox ph(seed);
     const long long nv = n / 4;
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nv; v += (long long)gridDim.x * blockDim.x) {
@@ -160,13 +168,15 @@ extern "C" int b2_ddpm_step(const float* x_t, const float* eps_hat, const float*
                             float scale2, float sigma, int use_philox, unsigned long long seed, unsigned long long offset,
                             long long first_elem, void* stream) {
     if (n % 4 || first_elem % 4) return set_error("b2_ddpm_step: element counts must be multiples of 4");
-    ddpm_step_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x_t, eps_hat, z, out, n, scale1, scale2, sigma, use_philox, seed, offset, first_elem);
+    B2_LAUNCH((ddpm_step_kernel), ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, x_t, eps_hat, z, out, n, scale1, scale2, sigma, use_philox, seed, offset, first_elem);
     LAUNCH_CHECK("b2_ddpm_step");
 }
 
 // Cold diffusion (diffusion_sampling_algorithms.py:193-208): x' = x - D(x0, t) + D(x0, t'),  D(x0, t) = a_t*x0 + b_t*noise
 __global__ void cold_step_kernel(const float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ noise,
                                  float* __restrict__ out, long long n, float a_t, float b_t, float a_n, float b_n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long nv = n / 4;
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nv; v += (long long)gridDim.x * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + v), r = __ldg(reinterpret_cast<const float4*>(x0) + v),
@@ -182,7 +192,7 @@ __global__ void cold_step_kernel(const float* __restrict__ x, const float* __res
 extern "C" int b2_cold_step(const float* x_t, const float* x0_hat, const float* noise, float* out, long long n, float a_t,
                             float b_t, float a_n, float b_n, void* stream) {
     if (n % 4) return set_error("b2_cold_step: element count must be a multiple of 4");
-    cold_step_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x_t, x0_hat, noise, out, n, a_t, b_t, a_n, b_n);
+    B2_LAUNCH((cold_step_kernel), ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, x_t, x0_hat, noise, out, n, a_t, b_t, a_n, b_n);
     LAUNCH_CHECK("b2_cold_step");
 }
 
@@ -190,6 +200,8 @@ extern "C" int b2_cold_step(const float* x_t, const float* x0_hat, const float* 
 // loss += sum((p - t)^2) * inv_n ; grad = 2 (p - t) * inv_n * grad_scale        (train_diffusion.py:350)
 __global__ void mse_loss_grad_kernel(const float* __restrict__ p, const float* __restrict__ t, float* __restrict__ grad,
                                      float* __restrict__ loss, long long n, float inv_n, float grad_scale) {
+    pdl_launch_dependents();
+    pdl_wait();
     float acc = 0.f;
     const long long nv = n / 4;
     const float gs = 2.0f * inv_n * grad_scale;
@@ -215,7 +227,7 @@ extern "C" int b2_mse_loss_grad(const float* pred, const float* target, float* g
     if (n % 4) return set_error("b2_mse_loss_grad: element count must be a multiple of 4");
     cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error("b2_mse_loss_grad: memset: %s", cudaGetErrorString(e));
-    mse_loss_grad_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(pred, target, grad, loss, n, 1.0f / (float)n, grad_scale);
+    B2_LAUNCH((mse_loss_grad_kernel), ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, pred, target, grad, loss, n, 1.0f / (float)n, grad_scale);
     LAUNCH_CHECK("b2_mse_loss_grad");
 }
 
@@ -224,6 +236,8 @@ extern "C" int b2_mse_loss_grad(const float* pred, const float* target, float* g
 // out[o] = mean of in[floor(o*I/O) .. ceil((o+1)*I/O)) per axis.  Integer down-scaling averages k x k windows, integer
 // up-scaling replicates.  fp32 NCHW planes; one thread per output element (consecutive threads walk the output row).
 __global__ void area_resample_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int H, int W, int OH, int OW) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = planes * OH * OW;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ow = (int)(i % OW), oh = (int)((i / OW) % OH);
@@ -239,6 +253,6 @@ __global__ void area_resample_kernel(const float* __restrict__ x, float* __restr
 }
 extern "C" int b2_area_resample(const float* x, float* y, long long planes, int H, int W, int OH, int OW, void* stream) {
     if (H < 1 || W < 1 || OH < 1 || OW < 1) return set_error("b2_area_resample: bad sizes");
-    area_resample_kernel<<<ew_grid(planes * OH * OW, 256), 256, 0, (cudaStream_t)stream>>>(x, y, planes, H, W, OH, OW);
+    B2_LAUNCH((area_resample_kernel), ew_grid(planes * OH * OW, 256), 256, 0, (cudaStream_t)stream, x, y, planes, H, W, OH, OW);
     LAUNCH_CHECK("b2_area_resample");
 }

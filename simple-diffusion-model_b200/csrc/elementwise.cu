@@ -62,6 +62,8 @@ static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
 // x fp32 NCHW [N][C][H][W]  ->  y T NHWC [N][H][W][Cpad] (channels >= C zero-filled).
 template <typename T>
 __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int HW, int Cpad) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)N * HW * (Cpad / 8);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int cv = (int)(i % (Cpad / 8));
@@ -79,14 +81,16 @@ extern "C" int b2_nchw_to_nhwc_pad(const float* x, void* y, int N, int C, int H,
     if (Cpad % 8) return set_error("b2_nchw_to_nhwc_pad: Cpad must be a multiple of 8");
     const long long total = (long long)N * H * W * (Cpad / 8);
     const int g = grid_for(total, 256);
-    if (dtype == 0) nchw_to_nhwc_pad_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, N, C, H * W, Cpad);
-    else nchw_to_nhwc_pad_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, N, C, H * W, Cpad);
+    if (dtype == 0) B2_LAUNCH((nchw_to_nhwc_pad_kernel<bf16>), g, 256, 0, (cudaStream_t)stream, x, (bf16*)y, N, C, H * W, Cpad);
+    else B2_LAUNCH((nchw_to_nhwc_pad_kernel<float>), g, 256, 0, (cudaStream_t)stream, x, (float*)y, N, C, H * W, Cpad);
     LAUNCH_CHECK("b2_nchw_to_nhwc_pad");
 }
 
 // x T NHWC (ld) [N][H][W][C] -> y fp32 NCHW.
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ y, int N, int C, int HW) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)N * C * HW;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i % HW);
@@ -97,14 +101,16 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, long long ldx, floa
 }
 extern "C" int b2_nhwc_to_nchw(const void* x, long long ldx, float* y, int N, int C, int H, int W, int dtype, void* stream) {
     const int g = grid_for((long long)N * C * H * W, 256);
-    if (dtype == 0) nhwc_to_nchw_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, y, N, C, H * W);
-    else nhwc_to_nchw_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, y, N, C, H * W);
+    if (dtype == 0) B2_LAUNCH((nhwc_to_nchw_kernel<bf16>), g, 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, y, N, C, H * W);
+    else B2_LAUNCH((nhwc_to_nchw_kernel<float>), g, 256, 0, (cudaStream_t)stream, (const float*)x, ldx, y, N, C, H * W);
     LAUNCH_CHECK("b2_nhwc_to_nchw");
 }
 
 // Parity planes for the stride-2 conv: planes[pr][pc][n][i][j][:] = x[n][2i+pr][2j+pc][:].
 template <typename T>
 __global__ void space_to_depth2_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ planes, int N, int H, int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int V = Vec16<T>::N;
     const int cv = C / V, OH = H / 2, OW = W / 2;
     const long long total = (long long)N * H * W * cv;
@@ -124,8 +130,8 @@ extern "C" int b2_space_to_depth2(const void* x, long long ldx, void* planes, in
     const int V = dtype == 0 ? 8 : 4;
     if (C % V || ldx % V || (H & 1) || (W & 1)) return set_error("b2_space_to_depth2: C/ld must be vector aligned, H/W even");
     const int g = grid_for((long long)N * H * W * (C / V), 256);
-    if (dtype == 0) space_to_depth2_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)planes, N, H, W, C);
-    else space_to_depth2_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, (float*)planes, N, H, W, C);
+    if (dtype == 0) B2_LAUNCH((space_to_depth2_kernel<bf16>), g, 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, (bf16*)planes, N, H, W, C);
+    else B2_LAUNCH((space_to_depth2_kernel<float>), g, 256, 0, (cudaStream_t)stream, (const float*)x, ldx, (float*)planes, N, H, W, C);
     LAUNCH_CHECK("b2_space_to_depth2");
 }
 
@@ -145,6 +151,8 @@ template <> __device__ __forceinline__ float pack_val<float>(float v) { return r
 template <typename T>
 __global__ void pack_weight_kernel(int kind, const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int k_pad,
                                    long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         float v = 0.f;
         if (kind == 0) {
@@ -197,14 +205,16 @@ extern "C" int b2_pack_weight(int kind, const float* w, void* out, int Cout, int
     if (kind < 0 || kind > 6) return set_error("b2_pack_weight: bad kind");
     const long long total = pack_total(kind, Cout, Cin, k_pad);
     const int g = grid_for(total, 256);
-    if (dtype == 0) pack_weight_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (bf16*)out, Cout, Cin, k_pad, total);
-    else pack_weight_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(kind, w, (float*)out, Cout, Cin, k_pad, total);
+    if (dtype == 0) B2_LAUNCH((pack_weight_kernel<bf16>), g, 256, 0, (cudaStream_t)stream, kind, w, (bf16*)out, Cout, Cin, k_pad, total);
+    else B2_LAUNCH((pack_weight_kernel<float>), g, 256, 0, (cudaStream_t)stream, kind, w, (float*)out, Cout, Cin, k_pad, total);
     LAUNCH_CHECK("b2_pack_weight");
 }
 
 // Data-gradient weights of a 3x3/s1 conv straight from the bf16 "channels-last" copy the optimiser maintains:
 // in [Cout][9][Cin] -> out [Cin][9 flipped][Cout].  64x64 tiles through shared memory, 128-byte rows on both sides.
 __global__ void transpose_weight_cl_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int Cout, int Cin) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ bf16 tile[64][64 + 8];
     const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
     const int t = threadIdx.x;                       // 256 threads
@@ -230,7 +240,7 @@ __global__ void transpose_weight_cl_kernel(const bf16* __restrict__ in, bf16* __
 extern "C" int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int Cin, void* stream) {
     if (Cout % 64 || Cin % 64) return set_error("b2_transpose_weight_cl: Cout and Cin must be multiples of 64");
     dim3 grid(Cin / 64, Cout / 64, 9);
-    transpose_weight_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)w_cl, (bf16*)out, Cout, Cin);
+    B2_LAUNCH((transpose_weight_cl_kernel), grid, 256, 0, (cudaStream_t)stream, (const bf16*)w_cl, (bf16*)out, Cout, Cin);
     LAUNCH_CHECK("b2_transpose_weight_cl");
 }
 
@@ -244,6 +254,8 @@ __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const
                                    const float* __restrict__ s, long long s_bstride, const T* __restrict__ res, long long ldr,
                                    T* __restrict__ out, long long ldo, int HW, int C, int groups, float eps, int slabs,
                                    int rows_per_block, int pre_swish) {
+    pdl_launch_dependents();
+    pdl_wait();
     // each thread owns one 16-byte channel vector (its folded affine lives in registers) and walks the pixels of its
     // slab with U independent 16-byte loads in flight
     constexpr int V = V16<T>::N;
@@ -323,10 +335,10 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
     if (dtype == 0)
-        adagn_apply_kernel<bf16><<<N * slabs, cv * k, 0, (cudaStream_t)stream>>>((const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
+        B2_LAUNCH((adagn_apply_kernel<bf16>), N * slabs, cv * k, 0, (cudaStream_t)stream, (const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
                                                                                   (const bf16*)residual, ldr, (bf16*)out, ldo, HW, C, groups, eps, slabs, k, pre_swish);
     else
-        adagn_apply_kernel<float><<<N * slabs, cv * k, 0, (cudaStream_t)stream>>>((const float*)y, ldy, stats, gamma, beta, s, s_bstride,
+        B2_LAUNCH((adagn_apply_kernel<float>), N * slabs, cv * k, 0, (cudaStream_t)stream, (const float*)y, ldy, stats, gamma, beta, s, s_bstride,
                                                                                    (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs, k, pre_swish);
     LAUNCH_CHECK("b2_adagn_apply");
 }
@@ -336,6 +348,8 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ y, long long ldy, float* __restrict__ stats, int HW, int C, int groups,
                                 int slabs, int rows_per_block, int pre_swish) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float gsum[];                  // [groups][2]
     constexpr int V = V16<T>::N;
     const int cv = C / V;
@@ -378,8 +392,8 @@ int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, i
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
     const size_t smem = (size_t)groups * 2 * sizeof(float);
-    if (dtype == 0) gn_stats_kernel<bf16><<<N * slabs, cv * k, smem, st>>>((const bf16*)y, ldy, stats, HW, C, groups, slabs, k, pre_swish);
-    else gn_stats_kernel<float><<<N * slabs, cv * k, smem, st>>>((const float*)y, ldy, stats, HW, C, groups, slabs, k, pre_swish);
+    if (dtype == 0) B2_LAUNCH((gn_stats_kernel<bf16>), N * slabs, cv * k, smem, st, (const bf16*)y, ldy, stats, HW, C, groups, slabs, k, pre_swish);
+    else B2_LAUNCH((gn_stats_kernel<float>), N * slabs, cv * k, smem, st, (const float*)y, ldy, stats, HW, C, groups, slabs, k, pre_swish);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("gn_stats: %s", cudaGetErrorString(e));
     return 0;
@@ -393,6 +407,8 @@ int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, i
 template <typename T>
 __global__ void softmax_tiles_fixup_kernel(T* __restrict__ pt, long long ldp, const float* __restrict__ stats, long long rows,
                                            int P, int n_tiles, int tile_cols) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -412,6 +428,8 @@ __global__ void softmax_tiles_fixup_kernel(T* __restrict__ pt, long long ldp, co
 template <typename T>
 __global__ void rowdot_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, long long hs,
                               float* __restrict__ out, long long rows, int heads, int d) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (item >= rows * heads) return;
@@ -430,8 +448,8 @@ int launch_softmax_fixup(void* pt, long long ldp, const float* stats, long long 
                          cudaStream_t st) {
     const long long threads = rows * 32;
     const int blocks = (int)((threads + 255) / 256);
-    if (dtype == 0) softmax_tiles_fixup_kernel<bf16><<<blocks, 256, 0, st>>>((bf16*)pt, ldp, stats, rows, P, n_tiles, tile_cols);
-    else softmax_tiles_fixup_kernel<float><<<blocks, 256, 0, st>>>((float*)pt, ldp, stats, rows, P, n_tiles, tile_cols);
+    if (dtype == 0) B2_LAUNCH((softmax_tiles_fixup_kernel<bf16>), blocks, 256, 0, st, (bf16*)pt, ldp, stats, rows, P, n_tiles, tile_cols);
+    else B2_LAUNCH((softmax_tiles_fixup_kernel<float>), blocks, 256, 0, st, (float*)pt, ldp, stats, rows, P, n_tiles, tile_cols);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("softmax fix-up: %s", cudaGetErrorString(e));
     return 0;
@@ -441,8 +459,8 @@ extern "C" int b2_rowdot(const void* a, long long lda, const void* b, long long 
                          long long rows, int heads, int d, int dtype, void* stream) {
     const long long threads = rows * heads * 32;
     const int blocks = (int)((threads + 255) / 256);
-    if (dtype == 0) rowdot_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, head_stride, out, rows, heads, d);
-    else rowdot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, (const float*)b, ldb, head_stride, out, rows, heads, d);
+    if (dtype == 0) B2_LAUNCH((rowdot_kernel<bf16>), blocks, 256, 0, (cudaStream_t)stream, (const bf16*)a, lda, (const bf16*)b, ldb, head_stride, out, rows, heads, d);
+    else B2_LAUNCH((rowdot_kernel<float>), blocks, 256, 0, (cudaStream_t)stream, (const float*)a, lda, (const float*)b, ldb, head_stride, out, rows, heads, d);
     LAUNCH_CHECK("b2_rowdot");
 }
 
@@ -450,6 +468,8 @@ extern "C" int b2_rowdot(const void* a, long long lda, const void* b, long long 
 // One thread owns one key column j (coalesced across the warp), walking the query axis twice.
 template <typename T>
 __global__ void softmax_query_axis_kernel(const float* __restrict__ S, T* __restrict__ P, int B, int Pq, int Pk, long long ldp) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)B * Pk;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx % Pk);
@@ -469,8 +489,8 @@ __global__ void softmax_query_axis_kernel(const float* __restrict__ S, T* __rest
 }
 extern "C" int b2_softmax_query_axis(const float* S, void* P, int B, int Pq, int Pk, long long ldp, int dtype, void* stream) {
     const int g = grid_for((long long)B * Pk, 128);
-    if (dtype == 0) softmax_query_axis_kernel<bf16><<<g, 128, 0, (cudaStream_t)stream>>>(S, (bf16*)P, B, Pq, Pk, ldp);
-    else softmax_query_axis_kernel<float><<<g, 128, 0, (cudaStream_t)stream>>>(S, (float*)P, B, Pq, Pk, ldp);
+    if (dtype == 0) B2_LAUNCH((softmax_query_axis_kernel<bf16>), g, 128, 0, (cudaStream_t)stream, S, (bf16*)P, B, Pq, Pk, ldp);
+    else B2_LAUNCH((softmax_query_axis_kernel<float>), g, 128, 0, (cudaStream_t)stream, S, (float*)P, B, Pq, Pk, ldp);
     LAUNCH_CHECK("b2_softmax_query_axis");
 }
 
@@ -479,6 +499,8 @@ template <typename T>
 __global__ void transpose_batched_kernel(const T* __restrict__ in, long long ld_in, long long in_s1, long long in_s2,
                                          T* __restrict__ out, long long ld_out, long long out_s1, long long out_s2,
                                          int R, int Ccols, int B1) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ T tile[32][33];
     const int b = blockIdx.z, b1 = b % B1, b2 = b / B1;
     const T* src = in + b1 * in_s1 + b2 * in_s2;
@@ -498,14 +520,16 @@ extern "C" int b2_transpose_batched(const void* in, long long ld_in, long long i
                                     long long out_s1, long long out_s2, int R, int Ccols, int B1, int B2, int dtype, void* stream) {
     dim3 grid((Ccols + 31) / 32, (R + 31) / 32, B1 * B2), block(32, 8);
     if (grid.y > 65535 || grid.z > 65535) return set_error("b2_transpose_batched: grid too large");
-    if (dtype == 0) transpose_batched_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)in, ld_in, in_s1, in_s2, (bf16*)out, ld_out, out_s1, out_s2, R, Ccols, B1);
-    else transpose_batched_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, in_s1, in_s2, (float*)out, ld_out, out_s1, out_s2, R, Ccols, B1);
+    if (dtype == 0) B2_LAUNCH((transpose_batched_kernel<bf16>), grid, block, 0, (cudaStream_t)stream, (const bf16*)in, ld_in, in_s1, in_s2, (bf16*)out, ld_out, out_s1, out_s2, R, Ccols, B1);
+    else B2_LAUNCH((transpose_batched_kernel<float>), grid, block, 0, (cudaStream_t)stream, (const float*)in, ld_in, in_s1, in_s2, (float*)out, ld_out, out_s1, out_s2, R, Ccols, B1);
     LAUNCH_CHECK("b2_transpose_batched");
 }
 
 // ------------------------------------------------------------------------------------------------ embedding + small linear
 // out[b][:] = [sin(t_b f_k), cos(t_b f_k)], f_k = exp(-k ln(1e4)/(half-1))        (custom_layers.py:84-90)
 __global__ void sinusoid_kernel(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -518,7 +542,7 @@ __global__ void sinusoid_kernel(const long long* __restrict__ t, float* __restri
 extern "C" int b2_sinusoid_embedding(const long long* t, float* out, int B, int dim, void* stream) {
     if (dim < 4 || dim % 2) return set_error("b2_sinusoid_embedding: time_dim must be even and >= 4");
     const int n = B * (dim / 2);
-    sinusoid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, out, B, dim);
+    B2_LAUNCH((sinusoid_kernel), (n + 127) / 128, 128, 0, (cudaStream_t)stream, t, out, B, dim);
     LAUNCH_CHECK("b2_sinusoid_embedding");
 }
 
@@ -527,6 +551,8 @@ extern "C" int b2_sinusoid_embedding(const long long* t, float* out, int B, int 
 __global__ void small_gemm_kernel(const float* __restrict__ A, long long lda, int ta, const float* __restrict__ Bm, long long ldb, int tb,
                                   float* __restrict__ C, long long ldc, int M, int N, int K, const float* __restrict__ bias, int act,
                                   int accumulate, int k_per_split) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float As[32][33], Bs[32][33];
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
@@ -597,6 +623,6 @@ extern "C" int b2_small_gemm(const float* A, long long lda, int ta, const float*
         if (e != cudaSuccess) return set_error("b2_small_gemm: memset: %s", cudaGetErrorString(e));
     }
     grid.z = splits;
-    small_gemm_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, bias, act, accumulate, k_per_split);
+    B2_LAUNCH((small_gemm_kernel), grid, block, 0, (cudaStream_t)stream, A, lda, ta, B, ldb, tb, C, ldc, M, N, K, bias, act, accumulate, k_per_split);
     LAUNCH_CHECK("b2_small_gemm");
 }

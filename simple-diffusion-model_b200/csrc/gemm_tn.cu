@@ -62,6 +62,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
 
+    pdl_launch_dependents();               // the next kernel may be scheduled (and run its prologue) while this one works
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -76,6 +77,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                            // everything above overlapped the previous kernel's tail; global memory from here on
 
     const int batches = p.batch_mode ? p.H * p.N : 1;
     const int total_items = p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
@@ -254,7 +256,7 @@ static int launch_tn_cfg(const CUtensorMap& a, const CUtensorMap& b, const GemmT
     const int batches = p.batch_mode ? p.H * p.N : 1;
     const long long items = (long long)p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
     const int grid = (int)(items < num_sms ? items : num_sms);
-    kern<<<grid, kTnThreads, total, st>>>(a, b, p);
+    B2_LAUNCH((kern), grid, kTnThreads, total, st, a, b, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("gemm_tn launch: %s", cudaGetErrorString(e));
     return 0;

@@ -1,4 +1,5 @@
 #include "host_util.h"
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -67,6 +68,15 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
                          (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
                          (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
     return 0;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SDM_B200_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 }  // namespace b2

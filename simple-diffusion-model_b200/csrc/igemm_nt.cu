@@ -105,6 +105,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     volatile int* flag_s = reinterpret_cast<volatile int*>(tmem_holder + 1);      // split-K: arrival order of this CTA's split
     float* bias_s = reinterpret_cast<float*>(smem + S::BIAS_OFF);
 
+    pdl_launch_dependents();               // the next kernel may be scheduled (and run its prologue) while this one works
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -120,6 +121,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                            // everything above overlapped the previous kernel's tail; global memory from here on
 
     const int splits = p.splits;
     const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * splits;     // work items
@@ -486,7 +488,7 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmPar
     }
     const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.splits;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    kern<<<grid, kThreads, S::TOTAL, st>>>(a, b, p);
+    B2_LAUNCH((kern), grid, kThreads, S::TOTAL, st, a, b, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("igemm_nt launch: %s", cudaGetErrorString(e));
     return 0;

@@ -1,6 +1,7 @@
 // Fused Adam over flat fp32 buffers (parameters, gradients, exp_avg, exp_avg_sq): one memory-bound pass of
 // 28 bytes per parameter instead of torch's multi-tensor foreach over ~760 tensors (train_diffusion.py:214-218,361).
 #include "host_util.h"
+#include "ptx.cuh"
 #include "sdm_b200.h"
 #include <cuda_bf16.h>
 
@@ -10,6 +11,8 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
                                  long long n, float beta1, float omb1, float beta2, float omb2, float eps, float step_size,
                                  float inv_bc2_sqrt, float grad_scale, const float* __restrict__ dev_state,
                                  __nv_bfloat16* __restrict__ shadow) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (dev_state) {          // CUDA-graph mode: the step-dependent scalars come from device memory (b2_adam_flat_graph)
         grad_scale = dev_state[2]; step_size = dev_state[3]; inv_bc2_sqrt = dev_state[4];
     }
@@ -57,7 +60,7 @@ extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long l
     const long long cap = 16LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale, nullptr, (__nv_bfloat16*)shadow_bf16);
+    B2_LAUNCH((adam_flat_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale, nullptr, (__nv_bfloat16*)shadow_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat: %s", cudaGetErrorString(e));
     return 0;
@@ -66,6 +69,8 @@ extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long l
 // state[0] = steps taken so far, state[1] = learning rate, state[2] = gradient scale; this kernel advances the step and
 // derives state[3] = lr / (1 - beta1^t), state[4] = 1 / sqrt(1 - beta2^t) in double precision (torch computes them on the host).
 __global__ void adam_advance_kernel(float* state, double beta1, double beta2) {
+    pdl_launch_dependents();
+    pdl_wait();
     const double t = (double)state[0] + 1.0;
     state[0] = (float)t;
     state[3] = (float)((double)state[1] / (1.0 - pow(beta1, t)));
@@ -80,8 +85,8 @@ extern "C" int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, 
     const long long cap = 16LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
-    adam_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, 0.f, 0.f, 0.f, state, (__nv_bfloat16*)shadow_bf16);
+    B2_LAUNCH((adam_advance_kernel), 1, 1, 0, (cudaStream_t)stream, state, beta1, beta2);
+    B2_LAUNCH((adam_flat_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, 0.f, 0.f, 0.f, state, (__nv_bfloat16*)shadow_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat_graph: %s", cudaGetErrorString(e));
     return 0;
