@@ -78,6 +78,22 @@ static void pick_tiling(int cout, long long m_tiles, int groups, int k_iters, bo
     }
 }
 
+// Cluster size for TMA multicast of the weight tile (igemm_nt.cu, CL): only worth it when the layer has several waves of
+// tiles (the main loop is then bound by L2 -> SM operand traffic); bf16 kernels only.  SDM_B200_CLUSTER=1|2|4 overrides.
+static int pick_cluster(int dtype, int bn, int splits, long long tiles, long long m_tiles) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("SDM_B200_CLUSTER");
+        forced = e ? atoi(e) : 0;
+    }
+    if (dtype != 0 || splits != 1 || bn < 128) return 1;
+    const int sms = device_sm_count();
+    int cl = forced > 0 ? forced : 2;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+    if (cl > 1 && (tiles < 2LL * sms || m_tiles < 8 * cl)) return 1;
+    return cl;
+}
+
 // Spatial box of <=128 output pixels: full rows first, then rows, then images.
 static void pick_box(int W, int H, int N, int* wb, int* hb, int* nb) {
     *wb = W < 128 ? W : 128;
@@ -193,6 +209,7 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
     p.n_tiles = (Cout + bn - 1) / bn;
     p.b_mode = 0;
     p.splits = splits; p.ws = g_ws; p.ws_counters = g_ws_counters;
+    p.cluster = pick_cluster(dtype, bn, splits, m_tiles * p.groups * p.n_tiles, m_tiles);
 
     CUtensorMap ta, tb;
     {
@@ -205,7 +222,7 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         const uint64_t ktot = (uint64_t)p.taps * Cin;
         uint64_t dims[4] = {ktot, (uint64_t)Cout, (uint64_t)p.groups, 1};
         uint64_t str[3] = {ktot * eb, ktot * Cout * eb, ktot * Cout * p.groups * eb};
-        uint32_t box[4] = {(uint32_t)bk, (uint32_t)bn, 1, 1};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)(bn / p.cluster), 1, 1};      // cluster mode: each CTA fetches 1/CL of the B tile
         if (make_tmap_4d(&tb, wpacked, eb, dims, str, box)) return 1;
     }
     if (launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;
@@ -245,6 +262,7 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
     pick_tiling(Ncols, (long long)p.tiles_w * batch1 * batch2, 1, p.kb_per_tap, !batched, &bn, &splits);
     p.n_tiles = (Ncols + bn - 1) / bn;
     p.splits = splits; p.ws = g_ws; p.ws_counters = g_ws_counters;
+    p.cluster = batched ? 1 : pick_cluster(dtype, bn, splits, (long long)p.tiles_w * p.n_tiles, p.tiles_w);
     CUtensorMap ta, tb;
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch1, (uint64_t)batch2};
@@ -257,7 +275,7 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)Ncols, (uint64_t)batch1, (uint64_t)batch2};
         uint64_t str[3] = {(uint64_t)ldb * eb, (uint64_t)(batch1 > 1 ? b_s1 : ldb * Ncols) * eb,
                            (uint64_t)(batch2 > 1 ? b_s2 : ldb * Ncols * batch1) * eb};
-        uint32_t box[4] = {(uint32_t)bk, (uint32_t)bn, 1, 1};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)(bn / p.cluster), 1, 1};
         if (make_tmap_4d(&tb, B, eb, dims, str, box)) return 1;
     }
     return launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream);
@@ -290,6 +308,7 @@ static int attn_params(IgemmParams* p, CUtensorMap* ta, CUtensorMap* tb, const v
     p->vec_ok = ((ldo % ov == 0) && (o_sh % ov == 0) && (o_sn % ov == 0) && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
     p->b_mode = 1;
     p->splits = 1;
+    p->cluster = 1;
     p->n_tiles = (P + bn - 1) / bn;
     {
         uint64_t dims[4] = {(uint64_t)d, (uint64_t)P, (uint64_t)heads, (uint64_t)N};

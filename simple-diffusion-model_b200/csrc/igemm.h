@@ -37,6 +37,7 @@ struct IgemmParams {
     // split-K (small-M layers whose few output tiles cannot fill 148 SMs): a work item is (tile, split); every split
     // stores its fp32 partial tile into `ws` ([tile][split][128][BLOCK_N]); the split that arrives last (per-tile counter,
     // self-resetting) sums the slices in split order -- deterministic -- and runs the normal epilogue.
+    int cluster;                 // 1, or CL = 2 / 4: CTAs of a cluster share the B tile through TMA multicast (needs splits == 1)
     int splits;
     float* ws;
     int* ws_counters;

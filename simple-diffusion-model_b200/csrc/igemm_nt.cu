@@ -37,6 +37,26 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
     return c;
 }
 
+// Cluster mode pads the M-tile count to a multiple of CL; a padded (dummy) tile decodes to an image index past the batch.
+template <int CL>
+__device__ __forceinline__ TileCoord decode_tile_cl(const IgemmParams& p, int tile, int m_groups) {
+    if constexpr (CL == 1) {
+        return decode_tile(p, tile);
+    } else {
+        TileCoord c;
+        c.nt = tile % p.n_tiles;  tile /= p.n_tiles;
+        const int m_pad = m_groups * CL;
+        int m = tile % m_pad;
+        c.g = tile / m_pad;
+        const int m_total = p.tiles_n * p.tiles_h * p.tiles_w;
+        if (m >= m_total) { c.w0 = 0; c.h0 = 0; c.n0 = p.tiles_n * p.nb; return c; }     // dummy: every row is out of range
+        c.w0 = (m % p.tiles_w) * p.wb;  m /= p.tiles_w;
+        c.h0 = (m % p.tiles_h) * p.hb;  m /= p.tiles_h;
+        c.n0 = m * p.nb;
+        return c;
+    }
+}
+
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int kThreads = 64 + kEpiWarps * 32;
 
@@ -85,7 +105,10 @@ __device__ __forceinline__ void gn_partial(const float (&v)[32], bool valid, boo
     }
 }
 
-template <typename T, int BLOCK_N, int STAGES>
+// CL > 1: thread-block cluster of CL CTAs that work on CL consecutive M tiles of the SAME N tile.  The B (weight) tile
+// of every K step is identical for them, so each CTA fetches 1/CL of it and TMA-multicasts that piece to all: the L2 -> SM
+// operand traffic per CTA drops from A + B to A + B/CL (the main loop is bound by exactly that traffic, not by the MMA).
+template <typename T, int BLOCK_N, int STAGES, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ IgemmParams p) {
@@ -112,19 +135,41 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        // a stage may be refilled (by multicasts from every CTA of the cluster) once ALL CL consumers released it
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_holder);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();          // peers' barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     pdl_wait();                            // everything above overlapped the previous kernel's tail; global memory from here on
 
     const int splits = p.splits;
-    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * splits;     // work items
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    // Work items.  CL == 1: (tile, split), CTA i takes items i, i + grid, ...  CL > 1 (no split-K): an item is a group of CL
+    // consecutive M tiles x one N tile; cluster c takes groups c, c + #clusters, ... and CTA `crank` the crank-th M tile of the
+    // group (tiles past the end are dummies: TMA zero-fills, the epilogue sees no valid row).
+    const int m_total = p.tiles_n * p.tiles_h * p.tiles_w;
+    const int m_groups = (m_total + CL - 1) / CL;
+    const int total_tiles = CL > 1 ? p.groups * m_groups * p.n_tiles
+                                   : p.groups * m_total * p.n_tiles * splits;
+    const int item0 = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    const int item_step = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
+    auto tile_of = [&](int item) -> int {              // linear tile index in decode_tile()'s order (N tile fastest)
+        if constexpr (CL > 1) {
+            const int nt = item % p.n_tiles;
+            const int rest = item / p.n_tiles;
+            const int mg = rest % m_groups, g = rest / m_groups;
+            return (g * (m_groups * CL) + mg * CL + crank) * p.n_tiles + nt;       // may exceed the real tile count: dummy
+        } else {
+            return item / splits;
+        }
+    };
     const int k_iters = p.taps * p.kb_per_tap;
     constexpr int BK_ELEMS = 128 / sizeof(T);
     const uint32_t a_bytes = static_cast<uint32_t>(p.wb * p.hb * p.nb) * 128u;
@@ -133,9 +178,9 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-                const int split = item % splits;
-                const TileCoord tc = decode_tile(p, item / splits);
+            for (int item = item0; item < total_tiles; item += item_step) {
+                const int split = CL > 1 ? 0 : item % splits;
+                const TileCoord tc = decode_tile_cl<CL>(p, tile_of(item), m_groups);
                 const int bb2 = p.b_mode ? tc.h0 : tc.g;
                 const int bb3 = p.b_mode ? tc.n0 : 0;
                 const int it0 = (int)(((long long)k_iters * split) / splits), it1 = (int)(((long long)k_iters * (split + 1)) / splits);
@@ -148,7 +193,13 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint8_t* b_dst = a_dst + S::A_BYTES;
                     mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
                     tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
-                    tma_load_4d(b_dst, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N, bb2, bb3);
+                    if constexpr (CL > 1) {
+                        constexpr int PIECE = BLOCK_N / CL;         // rows of the B tile this CTA fetches for the whole cluster
+                        tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N + crank * PIECE,
+                                       bb2, bb3, kMask);
+                    } else {
+                        tma_load_4d(b_dst, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N, bb2, bb3);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -159,8 +210,8 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, 0);
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
-            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-                const int split = item % splits;
+            for (int item = item0; item < total_tiles; item += item_step) {
+                const int split = CL > 1 ? 0 : item % splits;
                 const int it0 = (int)(((long long)k_iters * split) / splits), it1 = (int)(((long long)k_iters * (split + 1)) / splits);
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
                 tc_fence_after();
@@ -176,7 +227,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
                         umma_ss<kTF32>(d_tmem, ad, bd, idesc, (it > it0 || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);
+                    if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[acc]);
@@ -195,9 +246,9 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int G = p.gn_stats ? (p.Cout / p.cpg) : 0;
         const bool f32out = kTF32 || p.out_fp32;
         int acc = 0; uint32_t acc_ph = 0;
-        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-            const int tile = item / splits;
-            const TileCoord tc = decode_tile(p, tile);
+        for (int item = item0; item < total_tiles; item += item_step) {
+            const int tile = tile_of(item);
+            const TileCoord tc = decode_tile_cl<CL>(p, tile, m_groups);
             const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
             const bool valid = (n_in < p.nb) && (w < p.W) && (h < p.H) && (n < p.N);
             const long long o_off = n * p.oN + h * p.oH + w * p.oW + p.goff[tc.g];
@@ -469,6 +520,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / signal its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -476,37 +528,82 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <typename T, int BLOCK_N, int STAGES>
+template <typename T, int BLOCK_N, int STAGES, int CL>
 static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& p, int num_sms, cudaStream_t st) {
     using S = IgemmSmem<BLOCK_N, STAGES>;
-    auto kern = igemm_nt_kernel<T, BLOCK_N, STAGES>;
+    auto kern = igemm_nt_kernel<T, BLOCK_N, STAGES, CL>;
     static bool attr_set = false;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    if (CL > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = CL; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return set_error("igemm_nt: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        if (CL > 1) {
+            // clusters must sit inside one GPC: ask how many fit on this device with one 200 KB CTA per SM
+            cfg.gridDim = dim3((num_sms / CL) * CL);
+            int n = 0;
+            e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+            if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = num_sms / CL; }
+            max_clusters = n;
+        }
         attr_set = true;
     }
-    const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.splits;
-    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    B2_LAUNCH((kern), grid, kThreads, S::TOTAL, st, a, b, p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_error("igemm_nt launch: %s", cudaGetErrorString(e));
+    int grid;
+    if (CL > 1) {
+        const int m_total = p.tiles_n * p.tiles_h * p.tiles_w;
+        const long long groups = (long long)p.groups * ((m_total + CL - 1) / CL) * p.n_tiles;
+        const long long clusters = groups < max_clusters ? groups : max_clusters;
+        grid = (int)clusters * CL;
+    } else {
+        const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.splits;
+        grid = total_tiles < num_sms ? total_tiles : num_sms;
+    }
+    cfg.gridDim = dim3(grid);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return set_error("igemm_nt launch: %s", cudaGetErrorString(e)); }
     return 0;
 }
 
 int launch_igemm_nt(int dtype /*0 bf16, 1 fp32(tf32)*/, const CUtensorMap& a, const CUtensorMap& b,
                     const IgemmParams& p, int block_n, cudaStream_t st) {
     const int sms = device_sm_count();
+    const int cl = p.cluster > 1 ? p.cluster : 1;
+    if (cl > 1 && (p.splits != 1 || p.b_mode || p.act == 4)) return set_error("igemm_nt: cluster multicast needs an unsplit, unbatched GEMM");
     if (dtype == 0) {
-        if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4>(a, b, p, sms, st);
-        if (block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6>(a, b, p, sms, st);
-        if (block_n == 64)  return launch_cfg<__nv_bfloat16, 64, 8>(a, b, p, sms, st);
-    } else {
-        if (block_n == 256) return launch_cfg<float, 256, 4>(a, b, p, sms, st);
-        if (block_n == 128) return launch_cfg<float, 128, 6>(a, b, p, sms, st);
-        if (block_n == 64)  return launch_cfg<float, 64, 8>(a, b, p, sms, st);
+        if (cl == 1) {
+            if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 1>(a, b, p, sms, st);
+            if (block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 1>(a, b, p, sms, st);
+            if (block_n == 64)  return launch_cfg<__nv_bfloat16, 64, 8, 1>(a, b, p, sms, st);
+        } else if (cl == 2) {
+            if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 2>(a, b, p, sms, st);
+            if (block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 2>(a, b, p, sms, st);
+        } else if (cl == 4) {
+            if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 4>(a, b, p, sms, st);
+            if (block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 4>(a, b, p, sms, st);
+        }
+    } else if (cl == 1) {
+        if (block_n == 256) return launch_cfg<float, 256, 4, 1>(a, b, p, sms, st);
+        if (block_n == 128) return launch_cfg<float, 128, 6, 1>(a, b, p, sms, st);
+        if (block_n == 64)  return launch_cfg<float, 64, 8, 1>(a, b, p, sms, st);
     }
-    return set_error("igemm_nt: unsupported block_n %d", block_n);
+    return set_error("igemm_nt: unsupported block_n %d / cluster %d for dtype %d", block_n, cl, dtype);
 }
 
 }  // namespace b2
