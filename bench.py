@@ -199,6 +199,7 @@ def run_train_leg(args, dev, world, rank, barrier, max_over_ranks):
     net = U_Net(cond_dim=TRAIN_COND).to(dev).train().set_precision(args.precision)
     dp = DataParallel(net, device=dev)
     opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=True)
+    dp.attach_optimizer(opt)                 # bucket-wise Adam on a second stream, underneath the backward pass
     deg = NoiseDegradation(5e-3, 9e-3, T_MAX, device=dev)
     step = GraphedTrainStep(net, deg, opt, kind="eps")
     n, s = args.train_batch, TRAIN_IMG

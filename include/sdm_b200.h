@@ -184,10 +184,14 @@ int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, doub
                  float step_size, float inv_bc2_sqrt, float grad_scale, void* shadow_bf16, void* stream);
 
 /* CUDA-graph friendly form: `state` is a DEVICE float[8] = {steps taken, lr, grad_scale, (out) step_size, (out)
- * inv_bc2_sqrt, ...}; every call advances the step counter on the device, so a captured graph replays correctly.
+ * inv_bc2_sqrt, ...}; with advance != 0 the call first advances the step counter on the device, so a captured graph
+ * replays correctly.
  * The host changes the learning rate (train_diffusion.py:368-371) by writing state[1]. */
 int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
-                       float* state, void* shadow_bf16, void* stream);
+                       float* state, void* shadow_bf16, int advance, void* stream);
+/* Advances the device-side step state alone; b2_adam_flat_graph(..., advance = 0) then updates any number of sub-ranges of
+ * the flat buffers with the same bias corrections (bucket-wise updates overlapped with the backward pass). */
+int b2_adam_advance(float* state, double beta1, double beta2, void* stream);
 
 #ifdef __cplusplus
 }

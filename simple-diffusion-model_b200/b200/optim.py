@@ -56,9 +56,81 @@ class FusedAdam(torch.optim.Optimizer):
         call("b2_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), n, b1, b2, group["eps"], step_size, inv_bc2_sqrt, grad_scale,
              ptr(shadow), stream())
 
+    # ---- bucket-wise stepping (b200/parallel.py): begin_step -> step_range* -> step() finishes whatever is left ----------
+    def _flat_group(self, lay):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if getattr(p, "_b2_layout", None) is lay:
+                    return group
+        return None
+
+    @torch.no_grad()
+    def begin_step(self, lay):
+        """Fixes this step's bias corrections (device-side advance in capturable mode) so that ranges of the flat buffers
+        can be updated one by one, in any order, possibly on another stream."""
+        group = self._flat_group(lay)
+        if group is None or lay.params_flat is None:
+            return False
+        if id(lay) not in self._flat:
+            self._flat[id(lay)] = (torch.zeros_like(lay.flat), torch.zeros_like(lay.flat))
+        any_state = next((self.state[p] for p in group["params"] if self.state.get(p)), None)
+        steps_so_far = float(any_state["step"]) if any_state else 0.0
+        b1, b2 = group["betas"]
+        if self.capturable:
+            dev = self.device_state(lay, group, steps_so_far)
+            call("b2_adam_advance", ptr(dev), float(b1), float(b2), stream())
+        self._partial = {"lay": lay, "group": group, "done": [], "step": int(steps_so_far) + 1,
+                         "shadow": lay.ensure_shadow() if self.bf16_shadow else None}
+        return True
+
+    @torch.no_grad()
+    def step_range(self, lay, lo, hi):
+        part = getattr(self, "_partial", None)
+        if part is None or part["lay"] is not lay or hi <= lo:
+            return
+        group, shadow = part["group"], part["shadow"]
+        m_flat, v_flat = self._flat[id(lay)]
+        b1, b2 = group["betas"]
+        sh = shadow[lo:hi] if shadow is not None else None
+        if self.capturable:
+            call("b2_adam_flat_graph", ptr(lay.params_flat[lo:hi]), ptr(lay.flat[lo:hi]), ptr(m_flat[lo:hi]), ptr(v_flat[lo:hi]),
+                 hi - lo, float(b1), float(b2), group["eps"], ptr(self._dev_state[id(lay)]), ptr(sh), 0, stream())
+        else:
+            self._launch(lay.params_flat[lo:hi], lay.flat[lo:hi], m_flat[lo:hi], v_flat[lo:hi], hi - lo, group, part["step"],
+                         self.grad_scale, sh)
+        part["done"].append((lo, hi))
+
+    def _finish_partial(self):
+        """Updates the ranges no bucket covered, then does the per-step bookkeeping of step()."""
+        part = self._partial
+        lay, group = part["lay"], part["group"]
+        pos = 0
+        for lo, hi in sorted(part["done"]):
+            if lo > pos:
+                self.step_range(lay, pos, lo)
+            pos = max(pos, hi)
+        if pos < lay.total:
+            self.step_range(lay, pos, lay.total)
+        m_flat, v_flat = self._flat[id(lay)]
+        for p in group["params"]:
+            if getattr(p, "_b2_layout", None) is not lay or id(p) not in lay.offsets:
+                continue
+            st = self.state[p]
+            if not st:
+                off = lay.offsets[id(p)]
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = lay._shaped(m_flat, p)
+                st["exp_avg_sq"] = lay._shaped(v_flat, p)
+            st["step"] += 1
+        lay.stepped(part["shadow"] is not None)
+        self._partial = None
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        if getattr(self, "_partial", None) is not None:
+            self._finish_partial()
+            return loss
         for group in self.param_groups:
             done_layouts = set()
             for p in group["params"]:
@@ -75,8 +147,8 @@ class FusedAdam(torch.optim.Optimizer):
                     if not st:
                         off = lay.offsets[id(p)]
                         st["step"] = torch.tensor(0.0)
-                        st["exp_avg"] = m_flat[off:off + p.numel()].view(p.shape)
-                        st["exp_avg_sq"] = v_flat[off:off + p.numel()].view(p.shape)
+                        st["exp_avg"] = lay._shaped(m_flat, p)          # same (possibly channels-last) view as the parameter
+                        st["exp_avg_sq"] = lay._shaped(v_flat, p)
                     if self.capturable:
                         self.device_state(lay, group, float(st["step"]))      # created once, from the pre-step count
                     st["step"] += 1
@@ -87,7 +159,7 @@ class FusedAdam(torch.optim.Optimizer):
                             b1, b2 = group["betas"]
                             dev = self.device_state(lay, group)
                             call("b2_adam_flat_graph", ptr(lay.params_flat), ptr(lay.flat), ptr(m_flat), ptr(v_flat), lay.total,
-                                 float(b1), float(b2), group["eps"], ptr(dev), ptr(shadow), stream())
+                                 float(b1), float(b2), group["eps"], ptr(dev), ptr(shadow), 1, stream())
                         else:
                             self._launch(lay.params_flat, lay.flat, m_flat, v_flat, lay.total, group, int(st["step"]),
                                          self.grad_scale, shadow)

@@ -39,6 +39,16 @@ class DataParallel:
                     dist.broadcast(p.data, src=0, group=self.group)
         eng.on_grads_ready = self.ready
         eng.post_backward = self.finish
+        self.opt = None              # FusedAdam attached with attach_optimizer(): bucket-wise updates under the backward pass
+        self.opt_stream = None
+        self._stepping = False
+
+    def attach_optimizer(self, optimizer):
+        """Each bucket is updated (Adam, memory-bound) on a second stream as soon as its all-reduce has landed, underneath the
+        tensor-core kernels of the remaining backward pass, instead of one 17 GB pass after it.  `optimizer.step()` still has
+        to be called after backward: it finishes the ranges no bucket covered and does the bookkeeping."""
+        self.opt = optimizer
+        return self
 
     @property
     def grad_scale(self):
@@ -47,8 +57,28 @@ class DataParallel:
 
     def _launch(self, lay, lo, hi):
         self.launched.append((lo, hi))
+        work = None
         if self.world > 1:
-            self.pending.append(dist.all_reduce(lay.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            work = dist.all_reduce(lay.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        if self.opt is None or not hasattr(self.opt, "step_range"):
+            if work is not None:
+                self.pending.append(work)
+            return
+        dev = lay.flat.device
+        main = torch.cuda.current_stream(dev)
+        if self.opt_stream is None:
+            self.opt_stream = torch.cuda.Stream(device=dev)
+        if not self._stepping:
+            self._stepping = self.opt.begin_step(lay)      # on the main stream: ordered before every range update
+            if not self._stepping:
+                if work is not None:
+                    self.pending.append(work)
+                return
+        self.opt_stream.wait_stream(main)                  # the bucket's gradients are final on the main stream
+        with torch.cuda.stream(self.opt_stream):
+            if work is not None:
+                work.wait()                                # ... and summed over the ranks
+            self.opt.step_range(lay, lo, hi)
 
     def ready(self, lay, lo, hi):
         if self.open is not None and self.open[1] == lo:
@@ -68,3 +98,6 @@ class DataParallel:
         for w in self.pending:
             w.wait()
         self.pending = []
+        if self._stepping:
+            torch.cuda.current_stream(lay.flat.device).wait_stream(self.opt_stream)
+            self._stepping = False

@@ -169,6 +169,7 @@ def run_training(flavour, raw_args=None):
     dp = DataParallel(net, device=device)            # flattens the parameters; a no-op collective-wise when world == 1
     use_graph = os.environ.get("SDM_B200_CUDA_GRAPH", "1") != "0"
     optim = FusedAdam(net.parameters(), lr=cfg["diffusion_lr"], betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=use_graph)
+    dp.attach_optimizer(optim)
     if ckpt is not None and cfg.get("load_diffusion_optim"):
         optim.load_state_dict(ckpt["optimizer"])
     if cfg.get("config_checkpoint") is not None:

@@ -90,7 +90,7 @@ static int pick_cluster(int dtype, int bn, int splits, long long tiles, long lon
     const int sms = device_sm_count();
     int cl = forced > 0 ? forced : 2;
     if (cl != 1 && cl != 2 && cl != 4) cl = 2;
-    if (cl > 1 && (tiles < 2LL * sms || m_tiles < 8 * cl)) return 1;
+    if (cl > 1 && (tiles < (long long)sms || m_tiles < 8 * cl)) return 1;
     return cl;
 }
 

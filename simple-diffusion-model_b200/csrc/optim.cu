@@ -56,11 +56,13 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
 extern "C" int b2_adam_flat(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, float eps,
                             float step_size, float inv_bc2_sqrt, float grad_scale, void* shadow_bf16, void* stream) {
     if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)shadow_bf16) & 15) return set_error("b2_adam_flat: buffers must be 16-byte aligned");
-    long long blocks = (n / 4 + 255) / 256;
-    const long long cap = 16LL * device_sm_count();
+    // 128-thread blocks (6 K registers): small enough to share an SM with a resident tensor-core CTA, so a bucket's update can
+    // run on a second stream underneath the rest of the backward pass (b200/parallel.py)
+    long long blocks = (n / 4 + 127) / 128;
+    const long long cap = 32LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    B2_LAUNCH((adam_flat_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale, nullptr, (__nv_bfloat16*)shadow_bf16);
+    B2_LAUNCH((adam_flat_kernel), (int)blocks, 128, 0, (cudaStream_t)stream, p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, inv_bc2_sqrt, grad_scale, nullptr, (__nv_bfloat16*)shadow_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat: %s", cudaGetErrorString(e));
     return 0;
@@ -77,16 +79,24 @@ __global__ void adam_advance_kernel(float* state, double beta1, double beta2) {
     state[4] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
 }
 
+extern "C" int b2_adam_advance(float* state, double beta1, double beta2, void* stream) {
+    if (!state) return set_error("b2_adam_advance: state must be a device float[8]");
+    B2_LAUNCH((adam_advance_kernel), 1, 1, 0, (cudaStream_t)stream, state, beta1, beta2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("b2_adam_advance: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2,
-                                  float eps, float* state, void* shadow_bf16, void* stream) {
-    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return set_error("b2_adam_flat_graph: buffers must be 16-byte aligned");
+                                  float eps, float* state, void* shadow_bf16, int advance, void* stream) {
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)shadow_bf16) & 15) return set_error("b2_adam_flat_graph: buffers must be 16-byte aligned");
     if (!state) return set_error("b2_adam_flat_graph: state must be a device float[8]");
-    long long blocks = (n / 4 + 255) / 256;
-    const long long cap = 16LL * device_sm_count();
+    long long blocks = (n / 4 + 127) / 128;
+    const long long cap = 32LL * device_sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    B2_LAUNCH((adam_advance_kernel), 1, 1, 0, (cudaStream_t)stream, state, beta1, beta2);
-    B2_LAUNCH((adam_flat_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, 0.f, 0.f, 0.f, state, (__nv_bfloat16*)shadow_bf16);
+    if (advance) B2_LAUNCH((adam_advance_kernel), 1, 1, 0, (cudaStream_t)stream, state, beta1, beta2);
+    B2_LAUNCH((adam_flat_kernel), (int)blocks, 128, 0, (cudaStream_t)stream, p, g, m, v, n, (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, 0.f, 0.f, 0.f, state, (__nv_bfloat16*)shadow_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("b2_adam_flat_graph: %s", cudaGetErrorString(e));
     return 0;

@@ -171,3 +171,50 @@ def test_bf16_shadow_weights_equal_packed_weights():
         y_packed = nets[0](x, tt)
     # bf16 activations + order-dependent fp32 atomics in the GroupNorm sums: equal up to a few bf16 roundings
     assert rel_l2(y_shadow, y_packed) < 5e-3
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_bucketwise_overlapped_adam_equals_single_pass(graph):
+    """DataParallel.attach_optimizer: Adam runs bucket by bucket on a second stream during backward (after each bucket's
+    all-reduce; world size 1 here) -- same training trajectory as one Adam pass after backward."""
+    from b200.graph import GraphedTrainStep
+    from b200.optim import FusedAdam
+    from b200.parallel import DataParallel
+    from b200.steps import eps_prediction_step
+    from degraders import NoiseDegradation
+    from models.U_Net import U_Net
+    fx = load_golden("unet_gpu_small.pt")
+    sd0 = synth_state_dict(fx["shapes"], fx["seed"])
+    nets, opts, dps = [], [], []
+    for overlapped in (False, True):
+        net = U_Net(**fx["kwargs"])
+        net.load_state_dict(sd0)
+        net = net.cuda().train().set_precision("tf32")
+        dp = DataParallel(net, bucket_bytes=1 << 20, device=torch.device("cuda"))
+        opt = FusedAdam(net.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=graph)
+        if overlapped:
+            dp.attach_optimizer(opt)
+        nets.append(net); opts.append(opt); dps.append(dp)
+    deg = NoiseDegradation(5e-3, 9e-3, 1000, device="cuda")
+    steppers = [GraphedTrainStep(n_, deg, o_, kind="eps") if graph else None for n_, o_ in zip(nets, opts)]
+    g = torch.Generator().manual_seed(21)
+    for step in range(3):
+        x0 = (torch.rand((2, 3, 32, 32), generator=g) * 2 - 1).cuda()
+        eps = torch.randn((2, 3, 32, 32), generator=g).cuda()
+        t = torch.randint(1, 1000, (2,), generator=g).cuda()
+        losses = []
+        for i in range(2):
+            if graph:
+                losses.append(float(steppers[i](x0, t, eps)))
+            else:
+                losses.append(float(eps_prediction_step(nets[i], deg, opts[i], x0, t, eps)))
+        assert abs(losses[0] - losses[1]) < 1e-4 * abs(losses[0]), (step, losses)
+    assert len(dps[1].launched) > 3                      # several buckets were updated separately
+    p0 = {k: v.cuda() for k, v in sd0.items()}
+    num = den = 0.0
+    for (k, pa), (_, pb) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+        da, db = pa.detach() - p0[k], pb.detach() - p0[k]
+        num += float((da - db).double().pow(2).sum())
+        den += float(da.double().pow(2).sum())
+    assert (num / den) ** 0.5 < 2e-2
+    assert float(opts[1].state_dict()["state"][0]["step"]) == 3.0

@@ -36,6 +36,8 @@ def run(args):
     net = U_Net(cond_dim=args.cond_dim if args.cond_dim > 0 else None).to(dev).train().set_precision(args.precision)
     dp = DataParallel(net, device=dev)
     opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=args.graph)
+    if os.environ.get("SDM_B200_OVERLAP_ADAM", "1") != "0":
+        dp.attach_optimizer(opt)
     deg = NoiseDegradation(5e-3, 9e-3, 1000, device=dev)
     n, s = args.batch, args.size
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
