@@ -48,6 +48,16 @@ int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int Cin, long l
                    const float* bias, int Cout, void* y, long long ldy, int act, const void* residual,
                    long long ldr, float* gn_stats, int gn_groups, int out_mode, int dtype, void* stream);
 
+/* Network-edge 3x3 convolutions on CUDA cores (too narrow for a 128 x 64 tensor-core tile: models/U_Net.py:55-66, :113-130).
+ * first: x fp32 NCHW [N][Cin][H][W], Cin 3 or 6 (fuses the NCHW->NHWC edge); w_kc = weight as [Cin*9][Cout] fp32;
+ *        y NHWC `dtype`, act 0 none / 1 Swish.
+ * last : x NHWC `dtype`; w_tc4 = weight as [9][Cin][4] fp32 (Cout <= 4, unused slots zero); y fp32 NCHW [N][Cout][H][W],
+ *        act 0 none / 2 tanh (image_recon, U_Net.py:126). */
+int b2_conv3x3_first(const float* x, const float* w_kc, const float* bias, void* y, long long ldy, int N, int Cin, int H, int W,
+                     int Cout, int act, int dtype, void* stream);
+int b2_conv3x3_last(const void* x, long long ldx, const float* w_tc4, const float* bias, float* y, int N, int H, int W, int Cin,
+                    int Cout, int act, int dtype, void* stream);
+
 /* C = alpha * A . B^T (+bias) (act) (+residual); A [M][K], B [Ncols][K] (nn.Linear weight layout,
  * custom_layers.py:116,119; q.k^T custom_layers.py:144).  batch1/batch2 > 1: batched with element strides
  * *_s1 / *_s2 for A, B and C. */

@@ -18,6 +18,8 @@ _P, _I, _L, _F, _U, _D = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctyp
 SIGNATURES = {
     "b2_set_workspace": [_P, _L],
     "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
+    "b2_conv3x3_first": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b2_conv3x3_last": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_gemm_nt": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P, _F, _I, _P, _L, _I, _I, _P],
     "b2_attn_scores_softmax": [_P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P],
     "b2_attn_scores_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _L, _I, _I, _I, _I, _F, _I, _P],

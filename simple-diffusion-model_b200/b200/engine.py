@@ -50,6 +50,25 @@ class WeightCache:
             self._packed[key] = hit
         return hit[1]
 
+    def get_edge(self, param, which):
+        """fp32 weight layouts of the CUDA-core edge convs: "first" -> [Cin*9][Cout], "last" -> [9][Cin][4] (tiny tensors,
+        re-derived with torch ops when the parameter changes)."""
+        key = (id(param), which)
+        lay = getattr(param, "_b2_layout", None)
+        ver = (param.data_ptr(), param._version, lay.epoch if lay is not None else 0)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            w = param.detach().float()
+            cout, cin = w.shape[0], w.shape[1]
+            if which == "first":
+                t = w.permute(1, 2, 3, 0).reshape(cin * 9, cout).contiguous()
+            else:
+                t = torch.zeros((9, cin, 4), dtype=torch.float32, device=w.device)
+                t[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(9, cin, cout)
+            hit = (ver, t)
+            self._packed[key] = hit
+        return hit[1]
+
     def clear(self):
         self._packed.clear()
 
@@ -231,9 +250,15 @@ class UNetEngine:
             max_groups = max(m.group_norm.num_groups for m in self._adagn_modules())
             ctx.update(emb=emb, s_all=s_all, adagn_off=off, s_bstride=(total if be == n else 0),
                        stats=torch.zeros((n_adagn, n, max_groups, 2), dtype=torch.float32, device=x.device))
-        cpad = ((cin + ops.K_ALIGN[code] - 1) // ops.K_ALIGN[code]) * ops.K_ALIGN[code]
-        h = ops.nchw_to_nhwc_pad(x, cpad, code)
-        h = self.conv_block(net.in_layer[0], h, ctx)
+        first = net.in_layer[0]
+        if ops.edge_first_ok(first.conv_layer[0]) and first.adagn is None and first.use_activation and wid % 2 == 0:
+            conv0 = first.conv_layer[0]           # 3/6 input channels: CUDA-core kernel straight from the fp32 NCHW image
+            h = ops.conv_first(x.contiguous().float(), self.cache.get_edge(conv0.weight, "first"), conv0.bias,
+                               conv0.weight.shape[0], 1, code)
+        else:
+            cpad = ((cin + ops.K_ALIGN[code] - 1) // ops.K_ALIGN[code]) * ops.K_ALIGN[code]
+            h = ops.nchw_to_nhwc_pad(x, cpad, code)
+            h = self.conv_block(first, h, ctx)
         h = self.conv_block(net.in_layer[1], h, ctx)
         cats = []
         hh, ww = hgt, wid
@@ -259,5 +284,9 @@ class UNetEngine:
         last = net.out_layers[1]
         c_out = last.conv_layer[0].weight.shape[0]
         y = torch.empty((n, c_out, hgt, wid), dtype=torch.float32, device=x.device)
-        self.conv_block(last, h, ctx, out_nchw=y, act_override=(2 if net.image_recon else 0))
+        if ops.edge_last_ok(last.conv_layer[0]) and last.adagn is None and wid % 4 == 0:
+            conv_l = last.conv_layer[0]
+            ops.conv_last(h, self.cache.get_edge(conv_l.weight, "last"), conv_l.bias, c_out, 2 if net.image_recon else 0, y)
+        else:
+            self.conv_block(last, h, ctx, out_nchw=y, act_override=(2 if net.image_recon else 0))
         return y

@@ -136,3 +136,31 @@ def add(a, b, out):
     n, h, w, c, lda = _nhwc(a)
     call("b2_add", ptr(a), lda, ptr(b), _nhwc(b)[4], ptr(out), _nhwc(out)[4], n * h * w, c, code_of(a), stream())
     return out
+
+
+def conv_first(x_nchw, w_kc, bias, cout, act, code):
+    """First conv of the network on CUDA cores: fp32 NCHW image (3 or 6 channels) -> NHWC activation, bias (+ Swish)."""
+    n, cin, h, w = x_nchw.shape
+    y = new_act(n, h, w, cout, code, x_nchw.device)
+    call("b2_conv3x3_first", ptr(x_nchw), ptr(w_kc), ptr(bias), ptr(y), cout, n, cin, h, w, cout, act, code, stream())
+    return y
+
+
+def conv_last(x, w_tc4, bias, cout, act, out_nchw):
+    """Last conv of the network (<= 4 output channels) on CUDA cores: NHWC activation -> fp32 NCHW, bias (+ tanh)."""
+    n, h, w, cin, ldx = _nhwc(x)
+    call("b2_conv3x3_last", ptr(x), ldx, ptr(w_tc4), ptr(bias), ptr(out_nchw), n, h, w, cin, cout, act, code_of(x), stream())
+    return out_nchw
+
+
+def edge_first_ok(conv):
+    return conv.weight.shape[1] in (3, 6) and conv.weight.shape[0] % 16 == 0 and conv.weight.shape[0] <= 512
+
+
+def edge_last_ok(conv):
+    """The CUDA-core last conv measured 0.73 ms vs 0.50 ms for the (column-padded) tensor-core path at batch 256 x 64 x 64,
+    so the engines keep the tensor-core kernel unless SDM_B200_EDGE_LAST=1."""
+    import os
+    if os.environ.get("SDM_B200_EDGE_LAST", "0") != "1":
+        return False
+    return conv.weight.shape[0] <= 4 and conv.weight.shape[1] % 8 == 0 and conv.weight.shape[1] <= 1024

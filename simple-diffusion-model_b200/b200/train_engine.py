@@ -236,7 +236,17 @@ class UNetTrainEngine(UNetEngine):
         cpad = ((cin + kal - 1) // kal) * kal
         h = ops.nchw_to_nhwc_pad(x, cpad, code)
         tape.append(("mark", net.in_layer))
-        h = self._plain_conv_train(net.in_layer[0], h, ctx, need_dx=False)
+        first = net.in_layer[0]
+        if ops.edge_first_ok(first.conv_layer[0]) and wid % 2 == 0:
+            conv0 = first.conv_layer[0]           # forward on the CUDA-core edge kernel; the padded NHWC copy only feeds the wgrad
+            c0 = conv0.weight.shape[0]
+            z0 = ops.conv_first(x.contiguous().float(), self.cache.get_edge(conv0.weight, "first"), conv0.bias, c0, 0, code)
+            a0 = ops.new_act(n, hgt, wid, c0, code, dev)
+            ops.act(0, None, z0, a0, None, n * hgt * wid, c0, 0, z0.stride(2), a0.stride(2), code)
+            tape.append(("plain", first, h, z0, False))
+            h = a0
+        else:
+            h = self._plain_conv_train(first, h, ctx, need_dx=False)
         h = self._plain_conv_train(net.in_layer[1], h, ctx)
         cats = []
         hh, ww = hgt, wid
@@ -267,8 +277,11 @@ class UNetTrainEngine(UNetEngine):
         conv = last.conv_layer[0]
         c_out = conv.weight.shape[0]
         y = torch.empty((n, c_out, hgt, wid), dtype=torch.float32, device=dev)
-        w = self.cache.get(conv.weight, 0, code, c_out, conv.weight.shape[1], h.shape[3])
-        ops.conv2d(0, h, w, conv.bias, c_out, act=(2 if net.image_recon else 0), out_nchw_fp32=y)
+        if ops.edge_last_ok(conv) and wid % 4 == 0:
+            ops.conv_last(h, self.cache.get_edge(conv.weight, "last"), conv.bias, c_out, 2 if net.image_recon else 0, y)
+        else:
+            w = self.cache.get(conv.weight, 0, code, c_out, conv.weight.shape[1], h.shape[3])
+            ops.conv2d(0, h, w, conv.bias, c_out, act=(2 if net.image_recon else 0), out_nchw_fp32=y)
         tape.append(("last", last, h, y if net.image_recon else None))
         del ctx["tape"]          # break the ctx <-> tape reference cycle: activations must die by refcount, not by GC
         return y, tape

@@ -175,3 +175,44 @@ def test_attention_huge_logits_stay_finite():
     pt = saved["pt"][..., :256].float()
     assert torch.isfinite(pt).all()
     assert torch.allclose(pt.sum(dim=-1), torch.ones_like(pt[..., 0]), atol=2e-2)      # each key column of P sums to one over queries
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("cin", [3, 6])
+def test_edge_first_conv_matches_torch(prec, cin):
+    """CUDA-core first conv (fp32 NCHW image in, NHWC activation out, fused Swish) vs F.conv2d."""
+    from b200 import ops
+    code, dt, tol = DT[prec]
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, h, w, cout = 3, 20, 24, 128
+    x = torch.rand((n, cin, h, w), device="cuda", generator=g) * 2 - 1
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * 0.2
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    wk = wt.permute(1, 2, 3, 0).reshape(cin * 9, cout).contiguous()
+    for act in (0, 1):
+        y = ops.conv_first(x, wk, bias, cout, act, code)
+        ref = F.conv2d(x, wt, bias, padding=1)
+        ref = ref * torch.sigmoid(ref) if act else ref
+        assert rel_l2(_nchw(y), ref) < tol
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("cout", [1, 3, 4])
+def test_edge_last_conv_matches_torch(prec, cout):
+    """CUDA-core last conv (NHWC activation in, fp32 NCHW out, optional tanh) vs F.conv2d."""
+    from b200 import ops
+    code, dt, tol = DT[prec]
+    g = torch.Generator(device="cuda").manual_seed(6)
+    n, h, w, cin = 2, 18, 16, 128
+    x = torch.randn((n, cin, h, w), device="cuda", generator=g)
+    xq = _nhwc(x, dt)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * 0.05
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    w4 = torch.zeros((9, cin, 4), device="cuda")
+    w4[:, :, :cout] = wt.permute(2, 3, 1, 0).reshape(9, cin, cout)
+    for act in (0, 2):
+        y = torch.empty((n, cout, h, w), device="cuda")
+        ops.conv_last(xq, w4, bias, cout, act, y)
+        ref = F.conv2d(_nchw(xq), wt, bias, padding=1)
+        ref = torch.tanh(ref) if act else ref
+        assert rel_l2(y, ref) < tol
