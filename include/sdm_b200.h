@@ -114,6 +114,9 @@ int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int k
 /* bf16 [Cout][9][Cin] (a 3x3 weight stored channels-last, the layout of kind 0) -> [Cin][9 flipped][Cout] (kind 1):
  * data-gradient weights derived from the optimiser's bf16 copy; Cout, Cin multiples of 64. */
 int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int Cin, void* stream);
+/* GroupNorm statistics as a separate pass: stats[n][g] += (sum, sum of squares) of y (pre_swish: of Swish(y)); used for
+ * group widths the conv epilogue does not fuse and by the standalone AdaGN module (custom_layers.py:35-45). */
+int b2_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, int C, int groups, int pre_swish, int dtype, void* stream);
 /* out = s*(gamma*(y-mean)*rstd+beta) + s (+residual): GroupNorm x AdaGN (custom_layers.py:35-45) fused with the
  * ResidualBlock add (custom_layers.py:282-287).  stats from b2_conv2d_nhwc; s = y_scale(emb) [B][C] with row
  * stride s_bstride (0 broadcasts one embedding over the batch, as the samplers do).  pre_swish: y holds the conv

@@ -30,6 +30,7 @@ SIGNATURES = {
     "b2_nhwc_to_nchw": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
     "b2_space_to_depth2": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
     "b2_pack_weight": [_I, _P, _P, _I, _I, _I, _I, _P],
+    "b2_gn_stats": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _P],
     "b2_adagn_apply": [_P, _L, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _I, _P],
     "b2_adagn_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _P],
     "b2_act": [_I, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],

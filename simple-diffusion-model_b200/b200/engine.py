@@ -212,9 +212,15 @@ class UNetEngine:
             x = self.residual_block(res, x, ctx)
             if isinstance(attn, AttentionBlock):
                 x = self.attention(attn, x)
+        return self.resample(blk.out_layer, x, out)
+
+    def resample(self, layer, x, out=None):
+        """UpsampleBlock (ConvTranspose 4x4/s2 + Swish, custom_layers.py:169-185) / DownsampleBlock (Conv 3x3/s2 + Swish,
+        :191-207); `out` may be a channel slice of a concat buffer."""
+        from models.custom_layers import UpsampleBlock
         code = ops.code_of(x)
-        conv = blk.out_layer.conv_layer[0]
-        if isinstance(blk.out_layer, UpsampleBlock):
+        conv = layer.conv_layer[0]
+        if isinstance(layer, UpsampleBlock):
             cin, cout = conv.weight.shape[0], conv.weight.shape[1]
             w = self.cache.get(conv.weight, 2, code, cout, cin, cin)
             return ops.conv2d(2, x, w, conv.bias, cout, act=1, out=out)

@@ -399,6 +399,10 @@ int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, i
     return 0;
 }
 }  // namespace b2
+extern "C" int b2_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, int C, int groups, int pre_swish, int dtype,
+                           void* stream) {
+    return b2::launch_gn_stats(y, ldy, stats, N, HW, C, groups, pre_swish, dtype, (cudaStream_t)stream);
+}
 
 // ------------------------------------------------------------------------------------------------ attention helpers
 // Fix-up of the fused score kernel when a key row spans several 256-query tiles: tile t of row r holds

@@ -122,3 +122,23 @@ def test_dataset_table_reader(tmp_path):
     img, lab = ds[2]
     assert len(ds) == 5 and img.shape == (3, 16, 16) and lab.shape == (4,) and float(img.abs().max()) <= 1.0
     assert torch.equal(ds[2][0], img)
+
+
+def test_every_custom_layer_class_is_exposed_and_refuses_cpu():
+    """models/custom_layers.py exports (reference :18-341): every class constructs with the reference signature, and its
+    standalone forward fails loudly on CPU tensors instead of falling back."""
+    import models.custom_layers as cl
+    from b200._lib import B200Error
+    from b200.blocks import run_standalone  # noqa: F401  (the runner every standalone forward goes through)
+    for name in ("Swish", "AdaGN", "ConditionalEmbedding", "AttentionBlock", "UpsampleBlock", "DownsampleBlock", "UNet_ConvBlock",
+                 "ResidualBlock", "UNetBlock", "UNetBlockType"):
+        assert hasattr(cl, name), name
+    x = torch.randn((1, 64, 4, 4))
+    for mod, args in ((cl.UNet_ConvBlock(64, 64, emb_dim=16), (torch.randn(1, 16),)), (cl.ResidualBlock(64, 64, emb_dim=16), (torch.randn(1, 16),)),
+                      (cl.AttentionBlock(64), ()), (cl.UpsampleBlock(64, 64), ()), (cl.DownsampleBlock(64, 64), ()),
+                      (cl.AdaGN(16, 64), (torch.randn(1, 16),)),
+                      (cl.UNetBlock(64, 64, emb_dim=16, block_type=cl.UNetBlockType.DOWN), (torch.randn(1, 16),))):
+        with pytest.raises(B200Error):
+            mod(x, *args)
+    with pytest.raises(B200Error):
+        cl.Swish()(x)
