@@ -143,7 +143,7 @@ def run_training(flavour, raw_args=None):
     sampler = torch.utils.data.distributed.DistributedSampler(dataset, world, rank, shuffle=True) if world > 1 else None
     loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, num_workers=cfg.get("num_workers", 4),
                                          shuffle=sampler is None, sampler=sampler, pin_memory=True, drop_last=world > 1)
-    plot_batch = next(iter(torch.utils.data.DataLoader(dataset, batch_size=plot_img_count, num_workers=0, shuffle=False)))
+    plot_batch = next(iter(torch.utils.data.DataLoader(dataset, batch_size=max(plot_img_count, 1), num_workers=0, shuffle=False)))
     plot_labels, plot_cond = None, None
     if flavour == "doodle":
         plot_imgs, plot_cond = plot_batch
