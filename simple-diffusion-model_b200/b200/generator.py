@@ -19,6 +19,17 @@ from .functional import area_resize
 SUPPORTED_IMG_FORMATS = ["jpeg", "jpg", "png"]
 
 
+def _shard(t):
+    """Under torchrun every rank draws the same full batch (same seed) and keeps its contiguous shard of the images: the
+    sampling loop needs no collective and the union of the shards equals the single-process result."""
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world <= 1 or t is None:
+        return t
+    from .parallel import shard_range
+    lo, hi = shard_range(t.shape[0], rank, world)
+    return t[lo:hi].contiguous()
+
+
 def _image_kind(path):
     with open(path, "rb") as f:
         head = f.read(16)
@@ -65,6 +76,13 @@ def _setup(args):
     return out_dir, details["models"], os.path.split(args["config"])[0]
 
 
+def _device():
+    """One process per GPU: LOCAL_RANK selects the device under torchrun."""
+    if "LOCAL_RANK" in os.environ:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _degrader(model_dict, args, device):
     from degraders import CosineNoiseDegradation, NoiseDegradation
     name = model_dict["noise_scheduler"].upper()
@@ -106,6 +124,8 @@ def _finish(x, img_h, img_w, out_dir, save_locally, log):
         return x
     from utils.utils import plot_sampled_images
     name = datetime.now().strftime("%d-%m-%Y %H:%M:%S") + "_" + f"({img_h},{img_w})" + "_" + uuid.uuid4().hex
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        name += f"_rank{os.environ.get('RANK', '0')}"
     plot_sampled_images(sampled_imgs=x, file_name=name, dest_path=out_dir, log=log)
     return None
 
@@ -123,7 +143,7 @@ def generate_images_diffusion(raw_args=None, log=print, cond_img=None, save_loca
     if args["diff_alg"] == "ddim" and (args["ddim_step_size"] < 0 or args["ddim_step_size"] > args["max_T"]):
         raise ValueError("Invalid step size for DDIM!")
     out_dir, models, folder = _setup(args)
-    device = torch.device("cuda", torch.cuda.current_device())
+    device = _device()
     if args["cond_img_path"] is not None:
         if not os.path.isfile(args["cond_img_path"]):
             raise FileNotFoundError("Invalid path for conditional image, kindly correct and try again!")
@@ -139,7 +159,8 @@ def generate_images_diffusion(raw_args=None, log=print, cond_img=None, save_loca
     for model_dict in models:
         if x_t is None:                                  # X_T ~ N(0, I) once; later ensemble members continue from x_t
             img_h, img_w = model_dict["img_H"], model_dict["img_W"]
-            x_t = 1 * torch.randn((args["num_images"], model_dict["img_C"], img_h, img_w), device=device)
+            x_t = _shard(1 * torch.randn((args["num_images"], model_dict["img_C"], img_h, img_w), device=device))
+            cond_img = _shard(cond_img)
         labels = _labels(model_dict, args, device)
         degrader = _degrader(model_dict, args, device)
         net = _load_net(model_dict, folder, device)
@@ -166,13 +187,13 @@ def generate_images_cold_diffusion(raw_args=None, log=print, save_locally=True):
     if args["cold_step_size"] < 0 or args["cold_step_size"] > args["max_T"]:
         raise ValueError("Invalid step size for Cold Diffusion!")
     out_dir, models, folder = _setup(args)
-    device = torch.device("cuda", torch.cuda.current_device())
+    device = _device()
     noise, x0_approx, img_h, img_w = None, None, None, None
     for model_dict in models:
         degrader = _degrader(model_dict, args, device)
         if noise is None:
             img_h, img_w = model_dict["img_H"], model_dict["img_W"]
-            noise = torch.randn((args["num_images"], model_dict["img_C"], img_h, img_w), device=device)
+            noise = _shard(torch.randn((args["num_images"], model_dict["img_C"], img_h, img_w), device=device))
             x_t = 1 * noise
         else:                                            # ensemble hand-off: re-noise the estimate with the SAME noise
             x_t = degrader(img=x0_approx, steps=torch.tensor([model_dict["max_noise"]], device=device), eps=noise)
@@ -193,7 +214,7 @@ def generate_sr_images_diffusion(raw_args=None, lr_img=None, log=print, save_loc
     if args["cold_step_size"] < 0 or args["cold_step_size"] > args["max_T"]:
         raise ValueError("Invalid step size for Cold Diffusion!")
     out_dir, models, folder = _setup(args)
-    device = torch.device("cuda", torch.cuda.current_device())
+    device = _device()
     if lr_img is not None:
         if not isinstance(lr_img, np.ndarray):
             raise ValueError("Invalid low resolution image passed!")
