@@ -111,6 +111,11 @@ int b2_space_to_depth2(const void* x, long long ldx, void* planes, int N, int H,
  * 4 Linear -> transposed [Cin][k_pad>=Cout] (dgrad); 5 Conv2d -> [4][Cin][4 zero-padded taps][Cout] (dgrad, s2);
  * 6 ConvTranspose2d -> [Cin][16][Cout] (dgrad).  dtype 1 rounds to TF32 (nearest) so the MMA's truncation is exact. */
 int b2_pack_weight(int kind, const float* w, void* out, int Cout, int Cin, int k_pad, int dtype, void* stream);
+/* Batched forms: every stale kernel-layout weight of a training step in ONE launch each.  jobs_dev: device int64 records,
+ * pack: {w, out, kind, Cout, Cin, k_pad, first element, element count} (first elements ascending, total = sum of counts);
+ * transpose: {in, out, Cout, Cin, first tile, tile count} with tiles = (Cin/64)*(Cout/64)*9 per weight. */
+int b2_pack_weight_multi(const long long* jobs_dev, int njobs, long long total, int dtype, void* stream);
+int b2_transpose_weight_cl_multi(const long long* jobs_dev, int njobs, long long total_tiles, void* stream);
 /* bf16 [Cout][9][Cin] (a 3x3 weight stored channels-last, the layout of kind 0) -> [Cin][9 flipped][Cout] (kind 1):
  * data-gradient weights derived from the optimiser's bf16 copy; Cout, Cin multiples of 64. */
 int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int Cin, void* stream);

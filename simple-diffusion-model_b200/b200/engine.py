@@ -24,6 +24,9 @@ def _version_key(params):
 class WeightCache:
     def __init__(self):
         self._packed = {}
+        self._log = {}            # key -> request: every derived layout a step asked for (refresh_all re-derives them in bulk)
+        self._tables = {}         # job-table device tensors keyed by the pointers they describe
+        self.bulk_transposes = False
 
     def get(self, param, kind, code, cout, cin, cin_pad):
         key = (id(param), kind, code, cin_pad)
@@ -37,6 +40,7 @@ class WeightCache:
             if kind == 1 and lay.is_cl(param) and cin_pad == cout and cout % 64 == 0:
                 ver = (param.data_ptr(), param._version, lay.epoch)
                 hit = self._packed.get(key)
+                self._log.setdefault(key, (param, kind, code, cout, cin, cin_pad, "tr"))
                 if hit is None or hit[0] != ver:
                     out = hit[1] if hit is not None else torch.empty((cin, 9 * cout), dtype=torch.bfloat16, device=param.device)
                     call("b2_transpose_weight_cl", ptr(lay.shadow_slice(param)), ptr(out), cout, cin, stream())
@@ -45,10 +49,86 @@ class WeightCache:
                 return hit[1]
         ver = (param.data_ptr(), param._version, lay.epoch if lay is not None else 0)
         hit = self._packed.get(key)
+        if lay is not None:
+            self._log.setdefault(key, (param, kind, code, cout, cin, cin_pad, "pack"))
         if hit is None or hit[0] != ver:
             hit = (ver, ops.pack_weight(kind, param, cout, cin, cin_pad, code))
             self._packed[key] = hit
         return hit[1]
+
+    def _table(self, name, rows, device):
+        """Device int64 job table, cached by content (pointers are stable across steps, so steady state uploads nothing --
+        and nothing is uploaded inside a CUDA-graph capture, whose eager warm-up steps build the tables first)."""
+        key = (name, tuple(rows))
+        t = self._tables.get(key)
+        if t is None:
+            if torch.cuda.is_current_stream_capturing():
+                return None
+            if len(self._tables) > 16:
+                self._tables.clear()
+            t = torch.tensor(rows, dtype=torch.int64, device=device).reshape(-1)
+            self._tables[key] = t
+        return t
+
+    def refresh_all(self):
+        """Re-derives every stale kernel-layout weight a previous step asked for with ONE launch per family (bf16 transposes
+        of the channels-last shadow; fp32 -> kernel-layout packs) instead of ~180 few-microsecond launches per train step."""
+        tr, packs = [], {}
+        pending = []
+        for key, (param, kind, code, cout, cin, cin_pad, family) in self._log.items():
+            lay = getattr(param, "_b2_layout", None)
+            if lay is None:
+                continue
+            ver = (param.data_ptr(), param._version, lay.epoch)
+            hit = self._packed.get(key)
+            if hit is not None and hit[0] == ver:
+                continue
+            if family == "tr":
+                # measured: producing the 1.2 GB of data-gradient transposes up front costs more than it saves -- made just
+                # in time in the backward pass each one is still in L2 when its conv reads it -- so they stay lazy
+                if lay.shadow is None or not self.bulk_transposes:
+                    continue
+                out = hit[1] if hit is not None else torch.empty((cin, 9 * cout), dtype=torch.bfloat16, device=param.device)
+                src = lay.shadow_slice(param)
+                tiles = (cin // 64) * (cout // 64) * 9
+                tr.append((src.data_ptr(), out.data_ptr(), cout, cin, tiles))
+                pending.append((key, ver, out))
+            else:
+                if not param.is_contiguous():
+                    continue                      # channels-last stored parameter read through a permuted view: stays lazy
+                shape = {0: (cout, 9 * cin_pad), 1: (cin, 9 * cin_pad), 2: (4 * cout, 4 * cin), 3: (cout, cin_pad), 4: (cin, cin_pad),
+                         5: (4 * cin, 4 * cout), 6: (cin, 16 * cout)}[kind]
+                out = hit[1] if hit is not None and tuple(hit[1].shape) == shape else \
+                    torch.empty(shape, dtype=ops.TORCH_DTYPE[code], device=param.device)
+                packs.setdefault(code, []).append((param.data_ptr(), out.data_ptr(), kind, cout, cin, cin_pad, out.numel()))
+                pending.append((key, ver, out))
+        if not pending:
+            return
+        dev = pending[0][2].device
+        ok = True
+        if tr:
+            rows, start = [], 0
+            for src, out, cout, cin, tiles in tr:
+                rows.append((src, out, cout, cin, start, tiles))
+                start += tiles
+            table = self._table("tr", rows, dev)
+            if table is None:
+                ok = False
+            else:
+                call("b2_transpose_weight_cl_multi", ptr(table), len(rows), start, stream())
+        for code, jobs in packs.items():
+            rows, start = [], 0
+            for w, out, kind, cout, cin, k_pad, numel in jobs:
+                rows.append((w, out, kind, cout, cin, k_pad, start, numel))
+                start += numel
+            table = self._table(("pack", code), rows, dev)
+            if table is None:
+                ok = False
+            else:
+                call("b2_pack_weight_multi", ptr(table), len(rows), start, code, stream())
+        if ok:
+            for key, ver, out in pending:
+                self._packed[key] = (ver, out)
 
     def get_edge(self, param, which):
         """fp32 weight layouts of the CUDA-core edge convs: "first" -> [Cin*9][Cout], "last" -> [9][Cin][4] (tiny tensors,

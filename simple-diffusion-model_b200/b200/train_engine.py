@@ -212,6 +212,7 @@ class UNetTrainEngine(UNetEngine):
         if hgt % (1 << levels) or wid % (1 << levels):
             raise B200Error(f"H and W must be divisible by 2**num_layers = {1 << levels}")
         dev = x.device
+        self.cache.refresh_all()         # every kernel-layout weight the optimiser invalidated, in two launches
         tape = []
         ctx = {"emb": None, "stats_i": 0, "tape": tape, "n": n}
         if net.cond_emb is None:

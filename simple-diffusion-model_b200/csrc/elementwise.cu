@@ -149,45 +149,78 @@ template <> __device__ __forceinline__ float pack_val<float>(float v) { return r
 // kind 5: Conv2d [Cout][Cin][3][3]          -> [4 parities][Cin][4 taps, zero padded][Cout]   data gradient, stride 2
 // kind 6: ConvTranspose2d [Cin][Cout][4][4] -> [Cin][16][Cout]                          data gradient
 template <typename T>
+__device__ __forceinline__ T pack_weight_elem(int kind, const float* __restrict__ w, int Cout, int Cin, int k_pad, long long i) {
+    float v = 0.f;
+    if (kind == 0) {
+        const int ci = (int)(i % k_pad); const int tap = (int)((i / k_pad) % 9); const int co = (int)(i / (9LL * k_pad));
+        if (ci < Cin) v = __ldg(w + ((long long)co * Cin + ci) * 9 + tap);
+    } else if (kind == 1) {
+        const int co = (int)(i % k_pad); const int tap = (int)((i / k_pad) % 9); const int ci = (int)(i / (9LL * k_pad));
+        if (co < Cout) v = __ldg(w + ((long long)co * Cin + ci) * 9 + (8 - tap));
+    } else if (kind == 2) {
+        const int ci = (int)(i % Cin); long long r = i / Cin;
+        const int t = (int)(r % 4); r /= 4;
+        const int co = (int)(r % Cout); const int g = (int)(r / Cout);
+        const int a = g >> 1, b = g & 1, ti = t >> 1, tj = t & 1;
+        const int kh = a == 0 ? (ti == 0 ? 1 : 3) : (ti == 0 ? 2 : 0);
+        const int kw = b == 0 ? (tj == 0 ? 1 : 3) : (tj == 0 ? 2 : 0);
+        v = __ldg(w + (((long long)ci * Cout + co) * 4 + kh) * 4 + kw);
+    } else if (kind == 3) {
+        const int c = (int)(i % k_pad); const int r = (int)(i / k_pad);
+        if (c < Cin) v = __ldg(w + (long long)r * Cin + c);
+    } else if (kind == 4) {
+        const int r = (int)(i % k_pad); const int c = (int)(i / k_pad);
+        if (r < Cout) v = __ldg(w + (long long)r * Cin + c);
+    } else if (kind == 5) {
+        const int co = (int)(i % Cout); long long r = i / Cout;
+        const int t = (int)(r % 4); r /= 4;
+        const int ci = (int)(r % Cin); const int g = (int)(r / Cin);
+        const int a = g >> 1, b = g & 1, ti = t >> 1, tj = t & 1;
+        const int kh = a == 0 ? (ti == 0 ? 1 : -1) : (ti == 0 ? 2 : 0);
+        const int kw = b == 0 ? (tj == 0 ? 1 : -1) : (tj == 0 ? 2 : 0);
+        if (kh >= 0 && kw >= 0) v = __ldg(w + ((long long)co * Cin + ci) * 9 + kh * 3 + kw);
+    } else {
+        const int co = (int)(i % Cout); const int t = (int)((i / Cout) % 16); const int ci = (int)(i / (16LL * Cout));
+        v = __ldg(w + ((long long)ci * Cout + co) * 16 + t);
+    }
+    return pack_val<T>(v);
+}
+template <typename T>
 __global__ void pack_weight_kernel(int kind, const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int k_pad,
                                    long long total) {
     pdl_launch_dependents();
     pdl_wait();
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float v = 0.f;
-        if (kind == 0) {
-            const int ci = (int)(i % k_pad); const int tap = (int)((i / k_pad) % 9); const int co = (int)(i / (9LL * k_pad));
-            if (ci < Cin) v = __ldg(w + ((long long)co * Cin + ci) * 9 + tap);
-        } else if (kind == 1) {
-            const int co = (int)(i % k_pad); const int tap = (int)((i / k_pad) % 9); const int ci = (int)(i / (9LL * k_pad));
-            if (co < Cout) v = __ldg(w + ((long long)co * Cin + ci) * 9 + (8 - tap));
-        } else if (kind == 2) {
-            const int ci = (int)(i % Cin); long long r = i / Cin;
-            const int t = (int)(r % 4); r /= 4;
-            const int co = (int)(r % Cout); const int g = (int)(r / Cout);
-            const int a = g >> 1, b = g & 1, ti = t >> 1, tj = t & 1;
-            const int kh = a == 0 ? (ti == 0 ? 1 : 3) : (ti == 0 ? 2 : 0);
-            const int kw = b == 0 ? (tj == 0 ? 1 : 3) : (tj == 0 ? 2 : 0);
-            v = __ldg(w + (((long long)ci * Cout + co) * 4 + kh) * 4 + kw);
-        } else if (kind == 3) {
-            const int c = (int)(i % k_pad); const int r = (int)(i / k_pad);
-            if (c < Cin) v = __ldg(w + (long long)r * Cin + c);
-        } else if (kind == 4) {
-            const int r = (int)(i % k_pad); const int c = (int)(i / k_pad);
-            if (r < Cout) v = __ldg(w + (long long)r * Cin + c);
-        } else if (kind == 5) {
-            const int co = (int)(i % Cout); long long r = i / Cout;
-            const int t = (int)(r % 4); r /= 4;
-            const int ci = (int)(r % Cin); const int g = (int)(r / Cin);
-            const int a = g >> 1, b = g & 1, ti = t >> 1, tj = t & 1;
-            const int kh = a == 0 ? (ti == 0 ? 1 : -1) : (ti == 0 ? 2 : 0);
-            const int kw = b == 0 ? (tj == 0 ? 1 : -1) : (tj == 0 ? 2 : 0);
-            if (kh >= 0 && kw >= 0) v = __ldg(w + ((long long)co * Cin + ci) * 9 + kh * 3 + kw);
-        } else {
-            const int co = (int)(i % Cout); const int t = (int)((i / Cout) % 16); const int ci = (int)(i / (16LL * Cout));
-            v = __ldg(w + ((long long)ci * Cout + co) * 16 + t);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = pack_weight_elem<T>(kind, w, Cout, Cin, k_pad, i);
+}
+// Several pack jobs in ONE launch (the ~80 kernel-layout weights a training step re-derives after the optimiser moved the
+// masters are each a few microseconds of work: launching them one by one costs more latency than bandwidth).
+// Job record (8 x int64): w, out, kind, Cout, Cin, k_pad, first global element, element count.
+template <typename T>
+__global__ void pack_weight_multi_kernel(const long long* __restrict__ jobs, int njobs, long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int CHUNK = 4096;                          // consecutive elements per block: one job lookup per block
+    __shared__ int job0;
+    for (long long base = (long long)blockIdx.x * CHUNK; base < total; base += (long long)gridDim.x * CHUNK) {
+        if (threadIdx.x == 0) {
+            int lo = 0, hi = njobs - 1;                  // last job whose first element is <= base
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (jobs[mid * 8 + 6] <= base) lo = mid; else hi = mid - 1;
+            }
+            job0 = lo;
         }
-        out[i] = pack_val<T>(v);
+        __syncthreads();
+        int jb = job0;
+        const long long end = base + CHUNK < total ? base + CHUNK : total;
+        for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+            while (jb + 1 < njobs && jobs[(jb + 1) * 8 + 6] <= i) ++jb;
+            const long long* j = jobs + jb * 8;
+            reinterpret_cast<T*>(j[1])[i - j[6]] =
+                pack_weight_elem<T>((int)j[2], reinterpret_cast<const float*>(j[0]), (int)j[3], (int)j[4], (int)j[5], i - j[6]);
+        }
+        __syncthreads();
     }
 }
 static long long pack_total(int kind, int Cout, int Cin, int k_pad) {
@@ -208,6 +241,14 @@ extern "C" int b2_pack_weight(int kind, const float* w, void* out, int Cout, int
     if (dtype == 0) B2_LAUNCH((pack_weight_kernel<bf16>), g, 256, 0, (cudaStream_t)stream, kind, w, (bf16*)out, Cout, Cin, k_pad, total);
     else B2_LAUNCH((pack_weight_kernel<float>), g, 256, 0, (cudaStream_t)stream, kind, w, (float*)out, Cout, Cin, k_pad, total);
     LAUNCH_CHECK("b2_pack_weight");
+}
+
+extern "C" int b2_pack_weight_multi(const long long* jobs_dev, int njobs, long long total, int dtype, void* stream) {
+    if (njobs < 1 || total < 1) return 0;
+    const int g = grid_for((total + 15) / 16, 256);     // 4096-element chunks per 256-thread block
+    if (dtype == 0) B2_LAUNCH((pack_weight_multi_kernel<bf16>), g, 256, 0, (cudaStream_t)stream, jobs_dev, njobs, total);
+    else B2_LAUNCH((pack_weight_multi_kernel<float>), g, 256, 0, (cudaStream_t)stream, jobs_dev, njobs, total);
+    LAUNCH_CHECK("b2_pack_weight_multi");
 }
 
 // Data-gradient weights of a 3x3/s1 conv straight from the bf16 "channels-last" copy the optimiser maintains:
@@ -341,6 +382,52 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
         B2_LAUNCH((adagn_apply_kernel<float>), N * slabs, cv * k, 0, (cudaStream_t)stream, (const float*)y, ldy, stats, gamma, beta, s, s_bstride,
                                                                                    (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs, k, pre_swish);
     LAUNCH_CHECK("b2_adagn_apply");
+}
+
+// All channels-last data-gradient transposes of a step in one launch.  Job record (6 x int64): in, out, Cout, Cin, first
+// tile, tile count (tiles = Cin/64 x Cout/64 x 9 per weight).
+__global__ void transpose_weight_cl_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ bf16 tile[64][64 + 8];
+    int lo = 0, hi = njobs - 1;
+    const long long b = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid * 6 + 4] <= b) lo = mid; else hi = mid - 1;
+    }
+    const long long* j = jobs + lo * 6;
+    const bf16* in = reinterpret_cast<const bf16*>(j[0]);
+    bf16* out = reinterpret_cast<bf16*>(j[1]);
+    const int Cout = (int)j[2], Cin = (int)j[3];
+    int t = (int)(b - j[4]);
+    const int ci0 = (t % (Cin / 64)) * 64;  t /= (Cin / 64);
+    const int co0 = (t % (Cout / 64)) * 64; const int tap = t / (Cout / 64);
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = tid + i * 256;
+        const int r = idx >> 3, v = idx & 7;
+        *reinterpret_cast<uint4*>(&tile[r][v * 8]) =
+            __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * 9 + tap) * Cin + ci0 + v * 8));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = tid + i * 256;
+        const int r = idx >> 3, v = idx & 7;
+        uint4 x;
+        bf16* e = reinterpret_cast<bf16*>(&x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = tile[v * 8 + k][r];
+        *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * 9 + (8 - tap)) * Cout + co0 + v * 8) = x;
+    }
+}
+extern "C" int b2_transpose_weight_cl_multi(const long long* jobs_dev, int njobs, long long total_tiles, void* stream) {
+    if (njobs < 1 || total_tiles < 1) return 0;
+    if (total_tiles > 0x7fffffffLL) return set_error("b2_transpose_weight_cl_multi: too many tiles");
+    B2_LAUNCH((transpose_weight_cl_multi_kernel), (int)total_tiles, 256, 0, (cudaStream_t)stream, jobs_dev, njobs);
+    LAUNCH_CHECK("b2_transpose_weight_cl_multi");
 }
 
 // GroupNorm statistics as a separate pass, for widths the conv epilogue does not fuse (fewer than 4 channels per
