@@ -64,3 +64,20 @@ def test_reference_unit_test_shape():
     with torch.no_grad():
         y = net(torch.randn((1, 3, 128, 128), device="cuda"), torch.tensor([1000], device="cuda"))
     assert tuple(y.shape) == (1, 3, 128, 128) and torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 64), (1, 96, 32)])
+def test_non_square_and_odd_batch_forward(shape):
+    """Rectangular images and batch sizes that do not fill an M tile: engine vs the oracle on the same weights (tf32 mode)."""
+    from oracle import diffusion_oracle as orc
+    fx = load_golden("unet_gpu_small.pt")
+    net = _build(fx, "tf32")
+    n, h, w = shape
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand((n, fx["x"].shape[1], h, w), generator=g) * 2 - 1
+    t = torch.randint(1, 1000, (n,), generator=g)
+    sd = synth_state_dict(fx["shapes"], fx["seed"])
+    with torch.no_grad():
+        want = orc.unet_forward(sd, x, t, None)
+        got = net(x.cuda(), t.cuda()).cpu()
+    assert rel_l2(got, want) < TOL["tf32"]
