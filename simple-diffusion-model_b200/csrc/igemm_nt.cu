@@ -58,7 +58,7 @@ __device__ __forceinline__ TileCoord decode_tile_cl(const IgemmParams& p, int ti
 }
 
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, interleaved over 32-column chunks
-constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiWarps * 32 + 32;      // + a second TMA producer warp (the last one)
 
 // Per-(image, group) sum / sum-of-squares of one 32-column chunk.  Each lane owns one pixel; the NV = 2*32/GS partial
 // values are reduced over the 32 lanes with a reduce-scatter butterfly (NV-1+log2(32/NV) shuffles instead of 5*NV),
@@ -174,8 +174,12 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int BK_ELEMS = 128 / sizeof(T);
     const uint32_t a_bytes = static_cast<uint32_t>(p.wb * p.hb * p.nb) * 128u;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
+    if (warp == 0 || warp == kThreads / 32 - 1) {
+        // ------------------------------------------------------------ TMA producers
+        // Two of them: warp 0 fetches the A (activation) box and posts the stage's byte count, the last warp fetches B.
+        // One thread issuing both boxes of every stage could not keep the ring full on the short-K layers (ncu source
+        // sampling: the producer sat on UTMALDG while the MMA warp waited for data; same finding as in gemm_tn.cu).
+        const bool load_a = warp == 0;
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int item = item0; item < total_tiles; item += item_step) {
@@ -191,9 +195,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + S::A_BYTES;
-                    mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
-                    tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
-                    if constexpr (CL > 1) {
+                    if (load_a) {
+                        mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
+                        tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
+                    } else if constexpr (CL > 1) {
                         constexpr int PIECE = BLOCK_N / CL;         // rows of the B tile this CTA fetches for the whole cluster
                         tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N + crank * PIECE,
                                        bb2, bb3, kMask);
