@@ -124,3 +124,38 @@ def test_mse_loss_and_grad():
     call("b2_mse_loss_grad", ptr(p), ptr(t), ptr(g), ptr(loss), p.numel(), 1.0, stream())
     assert abs(float(loss) - float(torch.nn.functional.mse_loss(p, t))) < 1e-5
     assert torch.allclose(g, 2 * (p - t) / p.numel(), rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", 2e-3), ("bf16", 5e-2)])
+def test_end_to_end_sampling_with_the_real_network(precision, tol):
+    """Whole sampling loops (DDIM, cold, DDPM with injected draws) through the sm_100a U-Net against the oracle's loop over
+    the oracle's network, linear schedule (1/sqrt(abar_T) = 33: well conditioned, unlike the cosine start).  The bf16 bound
+    is the stated end-to-end tolerance of the speed path; graph-replayed inference must agree with eager launches."""
+    import diffusion_sampling_algorithms as S
+    from degraders import NoiseDegradation
+    from models.U_Net import U_Net
+    from oracle import diffusion_oracle as orc
+    from oracle.weights import synth_state_dict
+    fx = load_golden("unet_gpu_small.pt")
+    sd = synth_state_dict(fx["shapes"], fx["seed"])
+    net = U_Net(**fx["kwargs"])
+    net.load_state_dict(sd)
+    net = net.cuda().eval().set_precision(precision)
+    deg = NoiseDegradation(5e-3, 9e-3, 1000, device="cuda")
+    osched = ("linear", 5e-3, 9e-3, 1000)
+    onet = lambda a, b, c=None: orc.unet_forward(sd, a, b, None)
+    quiet = lambda *a, **k: None
+    g = torch.Generator().manual_seed(17)
+    x_T = torch.randn((2, 3, 32, 32), generator=g)
+    with torch.no_grad():
+        want = orc.ddim_sample(onet, osched, x_T, 1, 1000, 250)
+        got = S.ddim_sampling(net, deg, x_T.cuda(), min_noise=1, max_noise=1000, ddim_step_size=250, device="cuda", log=quiet)
+        assert rel_l2(got.cpu(), want) < tol
+        net.cuda_graphs(True)
+        replayed = S.ddim_sampling(net, deg, x_T.cuda(), min_noise=1, max_noise=1000, ddim_step_size=250, device="cuda", log=quiet)
+        net.cuda_graphs(False)
+        assert rel_l2(replayed, got) < (1e-5 if precision == "tf32" else 2e-2)
+        want_c = orc.cold_sample(onet, osched, x_T, x_T, 1, 1000, 250)
+        got_c = S.cold_diffusion_sampling(net, deg, x_T.cuda(), x_T.cuda(), min_noise=1, max_noise=1000, skip_step_size=250,
+                                          device="cuda", log=quiet)
+        assert rel_l2(got_c.cpu(), want_c) < tol
