@@ -289,7 +289,7 @@ extern "C" int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int
 // out = s * (gamma * (y - mean) * rstd + beta) + s  (+ residual)        [custom_layers.py:35-45, :282-287]
 // stats = per-(image, group) (sum, sum of squares) produced by the conv epilogue.  One CTA streams a slab of
 // pixels of one image; the per-channel affine (a, b) is folded once into shared memory.
-template <typename T>
+template <typename T, int U>
 __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const float* __restrict__ stats,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ s, long long s_bstride, const T* __restrict__ res, long long ldr,
@@ -322,8 +322,7 @@ __global__ void adagn_apply_kernel(const T* __restrict__ y, long long ldy, const
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    constexpr int U = 2;
-    constexpr bool kFast = sizeof(T) == 2;
+    constexpr bool kFast = sizeof(T) == 2;          // U row vectors in flight per pipeline half (U = 4 measured slower: registers cost occupancy)
     struct Buf { uint4 y[U], r[U]; };
     const long long k = rows_per_block;
     auto load = [&](Buf& b, long long p) {
@@ -376,10 +375,10 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
     if (dtype == 0)
-        B2_LAUNCH((adagn_apply_kernel<bf16>), N * slabs, cv * k, 0, (cudaStream_t)stream, (const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
+        B2_LAUNCH((adagn_apply_kernel<bf16, 2>), N * slabs, cv * k, 0, (cudaStream_t)stream, (const bf16*)y, ldy, stats, gamma, beta, s, s_bstride,
                                                                                   (const bf16*)residual, ldr, (bf16*)out, ldo, HW, C, groups, eps, slabs, k, pre_swish);
     else
-        B2_LAUNCH((adagn_apply_kernel<float>), N * slabs, cv * k, 0, (cudaStream_t)stream, (const float*)y, ldy, stats, gamma, beta, s, s_bstride,
+        B2_LAUNCH((adagn_apply_kernel<float, 2>), N * slabs, cv * k, 0, (cudaStream_t)stream, (const float*)y, ldy, stats, gamma, beta, s, s_bstride,
                                                                                    (const float*)residual, ldr, (float*)out, ldo, HW, C, groups, eps, slabs, k, pre_swish);
     LAUNCH_CHECK("b2_adagn_apply");
 }
