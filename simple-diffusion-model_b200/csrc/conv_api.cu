@@ -464,6 +464,13 @@ extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int
         p.taps = 4; p.ldc = 4LL * Cin;
     }
     tn_pick_splits(&p, 1);
+    {   // CTA pairs sharing the activation slabs: measured neutral on B200 (weight-gradient layers at batch 32: 5.4 ms either way),
+        // so off unless SDM_B200_TN_CLUSTER=2; needs an even number of M tiles and enough items
+        static int tn_cl = -1;
+        if (tn_cl < 0) { const char* e = getenv("SDM_B200_TN_CLUSTER"); tn_cl = e ? atoi(e) : 1; }
+        const long long items = (long long)p.splits * p.m_tiles * p.n_tiles * p.taps;
+        p.cluster = (tn_cl == 2 && dtype == 0 && p.m_tiles % 2 == 0 && bn >= 128 && items >= device_sm_count()) ? 2 : 1;
+    }
     CUtensorMap ta, tb;
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)b_images};

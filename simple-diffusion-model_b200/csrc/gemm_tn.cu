@@ -39,7 +39,9 @@ __device__ __forceinline__ TnWork tn_decode(const GemmTnParams& p, int item) {
 }
 
 // T = bf16: 64 elements per 128-byte slab row; T = float (tf32): 32 elements per slab row.
-template <typename T, int BLOCK_N, int STAGES>
+// CL == 2: the two CTAs of a cluster take M tiles 2q and 2q+1 of the same (split, N tile, tap); the B slabs of a stage are
+// identical for them, so each fetches half of the slabs and TMA-multicasts them to both (same scheme as igemm_nt.cu).
+template <typename T, int BLOCK_N, int STAGES, int CL>
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmTnParams p) {
@@ -68,19 +70,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kTnEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_holder);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     pdl_wait();                            // everything above overlapped the previous kernel's tail; global memory from here on
 
     const int batches = p.batch_mode ? p.H * p.N : 1;
-    const int total_items = p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    // CL == 2 (never batched): an item is a PAIR of M tiles; cluster c takes pairs c, c + #clusters, ...
+    const int total_items = CL > 1 ? p.splits * (p.m_tiles / CL) * p.n_tiles * p.taps
+                                   : p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
+    const int item0 = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    const int item_step = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
+    auto decode = [&](int item) -> TnWork {
+        if constexpr (CL > 1) {
+            TnWork w;
+            w.split = item % p.splits;  item /= p.splits;
+            const int mp = item % (p.m_tiles / CL);  item /= (p.m_tiles / CL);
+            w.mt = mp * CL + crank;
+            w.nt_in_tap = item % p.n_tiles;  item /= p.n_tiles;
+            w.tap = item;
+            w.bh = 0; w.bn = 0;
+            return w;
+        } else {
+            return tn_decode(p, item);
+        }
+    };
     const int k_boxes = p.kt_w * p.kt_h * p.kt_n;
     const uint32_t box_rows = static_cast<uint32_t>(p.wb * p.hb * p.nb);
 
@@ -91,8 +114,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int prod = warp == 0 ? 0 : 1;
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                const TnWork wk = tn_decode(p, item);
+            for (int item = item0; item < total_items; item += item_step) {
+                const TnWork wk = decode(item);
                 const int kb0 = (int)(((long long)k_boxes * wk.split) / p.splits);
                 const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -108,14 +131,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int bw = w0 + p.tap_dw[wk.tap];
                     const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
                     const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
+                    if constexpr (CL > 1) {
+                        // producer 0: this CTA's own A slabs; producer 1: its share of the B slabs, multicast to the pair
+                        if (prod == 0) {
 #pragma unroll
-                    for (int sl = 0; sl < A_SLABS + B_SLABS; ++sl) {
-                        if ((sl & 1) != prod) continue;
-                        if (sl < A_SLABS)
-                            tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
-                        else
-                            tma_load_4d(b_dst + (sl - A_SLABS) * SLAB_BYTES, &tmB, &full[s],
-                                        wk.nt_in_tap * BLOCK_N + (sl - A_SLABS) * SLAB, bw, bh, bn);
+                            for (int sl = 0; sl < A_SLABS; ++sl)
+                                tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
+                        } else {
+#pragma unroll
+                            for (int sl = 0; sl < B_SLABS; ++sl) {
+                                if ((sl % CL) != crank) continue;
+                                tma_load_4d_mc(b_dst + sl * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + sl * SLAB, bw, bh, bn, kMask);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int sl = 0; sl < A_SLABS + B_SLABS; ++sl) {
+                            if ((sl & 1) != prod) continue;
+                            if (sl < A_SLABS)
+                                tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
+                            else
+                                tma_load_4d(b_dst + (sl - A_SLABS) * SLAB_BYTES, &tmB, &full[s],
+                                            wk.nt_in_tap * BLOCK_N + (sl - A_SLABS) * SLAB, bw, bh, bn);
+                        }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -127,8 +165,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             const int k_steps = (int)(box_rows + UMMA_K - 1) / UMMA_K;      // rows beyond the box are never touched
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                const TnWork wk = tn_decode(p, item);
+            for (int item = item0; item < total_items; item += item_step) {
+                const TnWork wk = decode(item);
                 const int kb0 = (int)(((long long)k_boxes * wk.split) / p.splits);
                 const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -145,7 +183,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t bd = umma_desc_sw128(b_addr + k * UMMA_K * 128, SLAB_BYTES, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
                         umma_ss<kTF32>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);
+                    if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[acc]);
@@ -156,8 +194,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_ph = 0;
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-            const TnWork wk = tn_decode(p, item);
+        for (int item = item0; item < total_items; item += item_step) {
+            const TnWork wk = decode(item);
             const int m = wk.mt * 128 + q * 32 + lane;
             const bool valid = m < p.M;
             const long long off = (long long)m * p.ldc + (long long)wk.tap * p.tap_stride + wk.bh * p.c_s1 + wk.bn * p.c_s2;
@@ -234,44 +272,82 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
-template <typename T, int BLOCK_N, int STAGES>
+template <typename T, int BLOCK_N, int STAGES, int CL>
 static int launch_tn_cfg(const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int num_sms, cudaStream_t st) {
     constexpr int SLAB = 128 / sizeof(T);
     constexpr int stage_bytes = (128 / SLAB + BLOCK_N / SLAB) * kTnBK * 128;
     constexpr int total = STAGES * stage_bytes + (2 * STAGES + 4) * 8 + 16 + 1024;
     static_assert(total <= 227 * 1024, "shared memory budget");
-    auto kern = gemm_tn_kernel<T, BLOCK_N, STAGES>;
+    auto kern = gemm_tn_kernel<T, BLOCK_N, STAGES, CL>;
     static bool attr_set = false;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kTnThreads);
+    cfg.dynamicSmemBytes = total;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    if (CL > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = CL; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
         if (e != cudaSuccess) return set_error("gemm_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        if (CL > 1) {
+            cfg.gridDim = dim3((num_sms / CL) * CL);
+            int n = 0;
+            e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+            if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = num_sms / CL; }
+            max_clusters = n;
+        }
         attr_set = true;
     }
     const int batches = p.batch_mode ? p.H * p.N : 1;
-    const long long items = (long long)p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
-    const int grid = (int)(items < num_sms ? items : num_sms);
-    B2_LAUNCH((kern), grid, kTnThreads, total, st, a, b, p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_error("gemm_tn launch: %s", cudaGetErrorString(e));
+    int grid;
+    if (CL > 1) {
+        const long long pairs = (long long)p.splits * (p.m_tiles / CL) * p.n_tiles * p.taps;
+        grid = (int)(pairs < max_clusters ? pairs : max_clusters) * CL;
+    } else {
+        const long long items = (long long)p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
+        grid = (int)(items < num_sms ? items : num_sms);
+    }
+    cfg.gridDim = dim3(grid);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return set_error("gemm_tn launch: %s", cudaGetErrorString(e)); }
     return 0;
 }
 
 int launch_gemm_tn(int dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int block_n, cudaStream_t st) {
     const int sms = device_sm_count();
+    const bool pair = p.cluster == 2 && !p.batch_mode && p.m_tiles % 2 == 0 && dtype == 0 && block_n >= 128;
     if (dtype == 0) {
-        if (block_n == 256) return launch_tn_cfg<__nv_bfloat16, 256, 4>(a, b, p, sms, st);
-        if (block_n == 128) return launch_tn_cfg<__nv_bfloat16, 128, 6>(a, b, p, sms, st);
-        if (block_n == 64)  return launch_tn_cfg<__nv_bfloat16, 64, 8>(a, b, p, sms, st);
+        if (pair) {
+            if (block_n == 256) return launch_tn_cfg<__nv_bfloat16, 256, 4, 2>(a, b, p, sms, st);
+            return launch_tn_cfg<__nv_bfloat16, 128, 6, 2>(a, b, p, sms, st);
+        }
+        if (block_n == 256) return launch_tn_cfg<__nv_bfloat16, 256, 4, 1>(a, b, p, sms, st);
+        if (block_n == 128) return launch_tn_cfg<__nv_bfloat16, 128, 6, 1>(a, b, p, sms, st);
+        if (block_n == 64)  return launch_tn_cfg<__nv_bfloat16, 64, 8, 1>(a, b, p, sms, st);
     } else {
-        if (block_n == 128) return launch_tn_cfg<float, 128, 3>(a, b, p, sms, st);
-        if (block_n == 64)  return launch_tn_cfg<float, 64, 4>(a, b, p, sms, st);
-        if (block_n == 32)  return launch_tn_cfg<float, 32, 5>(a, b, p, sms, st);
+        if (block_n == 128) return launch_tn_cfg<float, 128, 3, 1>(a, b, p, sms, st);
+        if (block_n == 64)  return launch_tn_cfg<float, 64, 4, 1>(a, b, p, sms, st);
+        if (block_n == 32)  return launch_tn_cfg<float, 32, 5, 1>(a, b, p, sms, st);
     }
     return set_error("gemm_tn: unsupported block_n %d for dtype %d", block_n, dtype);
 }

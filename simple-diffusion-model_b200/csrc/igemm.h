@@ -60,6 +60,7 @@ struct GemmTnParams {
     int taps;                    // taps (n-tile index = tap * n_tiles_per_tap + j)
     int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dn[kMaxTaps];
     int splits;                  // split-K factor (work item = tile x split)
+    int cluster;                 // 1, or 2: CTA pairs on consecutive M tiles share the B (activation) slabs through TMA multicast
     int M, Ncols;                // valid rows / valid columns per tap
     void* out;                   // C; row stride ldc, tap stride tap_stride (elements), batch strides c_s1 (h) / c_s2 (n)
     long long ldc, tap_stride, c_s1, c_s2;
