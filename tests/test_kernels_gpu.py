@@ -216,3 +216,52 @@ def test_edge_last_conv_matches_torch(prec, cout):
         ref = F.conv2d(_nchw(xq), wt, bias, padding=1)
         ref = torch.tanh(ref) if act else ref
         assert rel_l2(y, ref) < tol
+
+
+def _guarded(shape, dt, pad=4096):
+    """A tensor carved out of a larger sentinel-filled buffer; returns (view, check) where check() asserts the guards are intact."""
+    numel = 1
+    for s_ in shape:
+        numel *= s_
+    buf = torch.full((numel + 2 * pad,), 7.0, device="cuda").to(dt)
+    view = buf[pad:pad + numel].view(shape)
+    sentinel = buf[:1].clone()
+
+    def check():
+        assert torch.equal(buf[:pad], sentinel.expand(pad)) and torch.equal(buf[pad + numel:], sentinel.expand(pad)), "out-of-bounds write"
+    return view, check
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+def test_partial_tiles_do_not_write_out_of_bounds(prec):
+    """Shapes that leave partial M / N tiles (odd batch, 3 and 192 output columns, split-K and cluster paths): outputs live
+    between sentinel guards that must survive (compute-sanitizer is not available on the GPU pool)."""
+    from b200 import ops
+    code, dt, tol = DT[prec]
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for (n, h, w, cin, cout) in ((3, 6, 6, 128, 192), (5, 2, 2, 256, 512), (1, 20, 12, 64, 64), (37, 8, 8, 128, 128)):
+        x = (torch.randn((n, h, w, cin), device="cuda", generator=g) * 0.5).to(dt)
+        wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * 0.05
+        wp = ops.pack_weight(0, wt, cout, cin, cin, code)
+        y, chk = _guarded((n, h, w, cout), dt)
+        stats = torch.zeros((n, 32, 2), device="cuda")
+        ops.conv2d(0, x, wp, None, cout, act=1, out=y, gn_stats=stats if cout % 128 == 0 else None, groups=32)
+        torch.cuda.synchronize()
+        chk()
+        ref = F.conv2d(_nchw(x), wt, None, padding=1)
+        assert rel_l2(_nchw(y), ref * torch.sigmoid(ref)) < 2 * tol
+        # weight gradient into a guarded buffer
+        gw, chk2 = _guarded((cout, 9 * cin), torch.float32)
+        gw.zero_()
+        dz = (torch.randn((n, h, w, cout), device="cuda", generator=g) * 0.5).to(dt)
+        ops.conv2d_wgrad(0, x, dz, cout, gw)
+        torch.cuda.synchronize()
+        chk2()
+    # plain / batched GEMMs with ragged sizes
+    a = (torch.randn((300, 192), device="cuda", generator=g)).to(dt)
+    b = (torch.randn((72, 192), device="cuda", generator=g)).to(dt)
+    c, chk3 = _guarded((300, 72), dt)
+    ops.gemm_nt(a, b, 300, 72, 192, 192, 192, c, 72)
+    torch.cuda.synchronize()
+    chk3()
+    assert rel_l2(c.float(), a.float() @ b.float().t()) < 2 * tol
