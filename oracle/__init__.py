@@ -1,0 +1,1 @@
+"""CPU oracle: test infrastructure only (tests/, smoke(), bench.py cpu_baseline / --impl reference)."""

@@ -10,6 +10,19 @@ from .custom_layers import ConditionalEmbedding, UNet_ConvBlock, UNetBlock, UNet
 
 
 class U_Net(nn.Module):
+    """Parameter tree of the reference U-Net; none of the sub-modules' `forward`s run when the net is called.
+
+    `forward` hands (x, t, cond) to one engine object (built lazily, owns the activation arena, weight cache and flat
+    parameter / gradient buffers):
+      * grad disabled  -> `Engine.forward`: NCHW fp32 in -> NHWC bf16 (or fp32/TF32) activations -> ~1.2 k launches of the
+        C-ABI kernels, or one CUDA-graph replay after `cuda_graphs(True)`;
+      * grad enabled   -> `UNetTrainEngine.forward_train`: same kernels with the activations the hand-written backward
+        needs kept on a tape; the returned tensor's autograd node runs that backward and fills `param.grad` (views into one
+        flat fp32 buffer, 3x3 weights stored channels-last behind a permuted view).
+    The skip connections concatenate along channels, which in NHWC is two column ranges of one buffer: the down path's
+    epilogues write straight into the right half of the up path's input, no cat kernel.
+    """
+
     def __init__(self, num_resnet_blocks=5, in_channel=3, out_channel=3, time_dim=64, cond_dim=None, num_layers=5,
                  attn_layers=[2, 3, 4], num_heads=1, dim_per_head=None, groups=32, min_channel=128, max_channel=512,
                  image_recon=False):
@@ -58,6 +71,7 @@ class U_Net(nn.Module):
         self._graphed = None
 
     def set_precision(self, precision):
+        """'bf16': bf16 activations/weights, fp32 accumulation (default).  'tf32': fp32 storage, TF32 MMA (parity mode)."""
         if precision not in ("bf16", "tf32"):
             raise ValueError("precision must be 'bf16' or 'tf32'")
         self.precision = precision
@@ -74,6 +88,7 @@ class U_Net(nn.Module):
         return self
 
     def engine(self):
+        """The per-net engine (weights packed lazily on first use; rebuilt caches follow `.to()` / `load_state_dict`)."""
         if self._engine is None:
             from b200.train_engine import UNetTrainEngine
             self._engine = UNetTrainEngine(self)

@@ -34,6 +34,9 @@ class Swish(nn.Module):
 
 
 class AdaGN(nn.Module):
+    """Adaptive GroupNorm (custom_layers.py:26-45).  In the engine this is ONE streaming pass (`b2_adagn_apply`): the
+    GroupNorm sums were already produced by the epilogue of the convolution that wrote `x`, and the `y_scale` Linears of
+    every AdaGN in the net are evaluated together as a single small GEMM per forward (engine.Engine._scales)."""
     def __init__(self, emb_dim, out_dim, groups=32):
         super().__init__()
         self.y_scale = nn.Linear(emb_dim, out_dim)
@@ -45,6 +48,8 @@ class AdaGN(nn.Module):
 
 
 class ConditionalEmbedding(nn.Module):
+    """Sinusoidal timestep features -> 4-layer MLP, plus an optional second MLP over the condition vector whose output is
+    added (custom_layers.py:51-98).  Engine: `b2_sinusoid` + `b2_small_gemm` with the Swish fused; a few microseconds."""
     def __init__(self, time_dim, cond_dim=None):
         super().__init__()
         self.time_dim = time_dim
@@ -62,6 +67,9 @@ class ConditionalEmbedding(nn.Module):
 
 
 class AttentionBlock(nn.Module):
+    """Self-attention over pixels with a residual (custom_layers.py:104-160).  Engine: QKV projection as a tcgen05 GEMM,
+    scores + query-axis softmax fused in one kernel epilogue (`b2_attn_scores_softmax`), P.V as a TN GEMM on the
+    un-transposed V, output projection with the residual added in its epilogue."""
     def __init__(self, channels, heads=1, d_k=None, groups=32):
         super().__init__()
         if d_k is None:
@@ -79,6 +87,8 @@ class AttentionBlock(nn.Module):
 
 
 class UpsampleBlock(nn.Module):
+    """ConvTranspose2d(4, stride 2, pad 1) + Swish (custom_layers.py:169-186).  Engine: four parity sub-convolutions, each
+    a 2x2-tap implicit GEMM writing its interleaved quarter of the output through a strided TMA-free epilogue."""
     def __init__(self, in_channels, out_channels):
         super().__init__()
         self.conv_layer = nn.Sequential(
@@ -90,6 +100,8 @@ class UpsampleBlock(nn.Module):
 
 
 class DownsampleBlock(nn.Module):
+    """Conv2d(3, stride 2, pad 1) + Swish (custom_layers.py:191-208).  Engine: space-to-depth of the input, then a 2x2-tap
+    stride-1 implicit GEMM over 4x the channels (weights re-packed once per optimiser step)."""
     def __init__(self, in_channels, out_channels):
         super().__init__()
         self.conv_layer = nn.Sequential(
@@ -101,6 +113,8 @@ class DownsampleBlock(nn.Module):
 
 
 class UNet_ConvBlock(nn.Module):
+    """Conv 3x3 -> Swish -> AdaGN (custom_layers.py:213-245): the hot layer.  Engine: one persistent tcgen05 implicit-GEMM
+    launch (bias + Swish + GroupNorm partial sums in the epilogue) followed by one `b2_adagn_apply` pass."""
     def __init__(self, in_channels, out_channels, use_activation=True, emb_dim=None, groups=32):
         super().__init__()
         layers = [nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1)]
@@ -118,6 +132,7 @@ class UNet_ConvBlock(nn.Module):
 
 
 class ResidualBlock(nn.Module):
+    """x + block2(block1(x)) (custom_layers.py:251-287); the skip add rides in the second block's AdaGN apply pass."""
     def __init__(self, in_channels, out_channels, use_activation=True, emb_dim=None, groups=32):
         super().__init__()
         self.conv_block_1 = UNet_ConvBlock(in_channels=in_channels, out_channels=out_channels,
@@ -135,6 +150,8 @@ class ResidualBlock(nn.Module):
 
 
 class UNetBlock(nn.Module):
+    """`num_resnet_blocks` x (ResidualBlock, AttentionBlock | Identity) then a down- or up-sampling layer
+    (custom_layers.py:293-350)."""
     def __init__(self, in_channels, out_channels, emb_dim, num_resnet_blocks=1, use_attn=True, num_heads=1,
                  dim_per_head=None, groups=32, block_type=UNetBlockType.DOWN):
         super().__init__()

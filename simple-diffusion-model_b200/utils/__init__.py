@@ -1,0 +1,1 @@
+"""Host-side helpers behind the reference names (progress bar, plots, checkpoints)."""

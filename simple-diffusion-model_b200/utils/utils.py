@@ -6,6 +6,8 @@ import torch
 
 
 def printProgressBar(iteration, total, prefix='', suffix='', decimals=1, length=100, fill='█', printEnd="\r", log=print):
+    """One-line console bar redrawn in place; `log` is the callable the trainers pass so that rank != 0 stays silent
+    (reference utils/utils.py:8-36, same keyword names because the train scripts call it by keyword)."""
     frac = iteration / float(total)
     done = int(length * iteration // total)
     log(f"\r{prefix} |{fill * done}{'-' * (length - done)}| {100 * frac:.{decimals}f}% {suffix}", end=printEnd)
@@ -29,6 +31,9 @@ def plot_sampled_images(sampled_imgs, file_name, dest_path=None, log=print):
 
 
 def save_model(model_net, file_name, dest_path, checkpoint=False, steps=0, log=print):
+    """torch.save of `model_net` (a state dict or a {"model", "optimizer", ...} bundle) to
+    <dest>/checkpoint/<name>_<steps>.pt or <dest>/models/<name>_<steps>.pt; True on success, never raises
+    (reference utils/utils.py:67-82).  The trainers call it on rank 0 only."""
     try:
         folder = os.path.join(dest_path, "checkpoint" if checkpoint else "models")
         os.makedirs(folder, exist_ok=True)
