@@ -509,6 +509,18 @@ __global__ void softmax_tiles_fixup_kernel(T* __restrict__ pt, long long ldp, co
     for (int t = 0; t < n_tiles; ++t) z += st[2 * t + 1] * exp2f(st[2 * t] - m);
     const float inv = 1.0f / z;
     T* o = pt + row * ldp;
+    constexpr int V = 16 / (int)sizeof(T);      // one 16-byte vector per lane; a vector never straddles a tile (tile_cols % V == 0)
+    if (P % V == 0 && ldp % V == 0 && tile_cols % V == 0 && (reinterpret_cast<uintptr_t>(pt) & 15) == 0) {
+        for (int c = lane * V; c < P; c += 32 * V) {
+            const float f = exp2f(st[2 * (c / tile_cols)] - m) * inv;
+            uint4 raw = *reinterpret_cast<const uint4*>(o + c);
+            T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+            for (int i = 0; i < V; ++i) e[i] = from_f<T>(to_f<T>(e[i]) * f);
+            *reinterpret_cast<uint4*>(o + c) = raw;
+        }
+        return;
+    }
     for (int c = lane; c < P; c += 32) {
         const float f = exp2f(st[2 * (c / tile_cols)] - m) * inv;
         o[c] = from_f<T>(to_f<T>(o[c]) * f);

@@ -115,9 +115,10 @@ def test_conv_forward_dgrad_wgrad(prec, cfg):
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
-# last config: 576 positions -> a key row of the fused score kernel spans three 256-query tiles (fix-up pass)
+# 576 positions -> a key row of the fused score kernel spans three 256-query tiles (fix-up pass); 4096 positions = the
+# 64x64 attention level of the default net at 256x256 (16 tiles); 324 positions: not a multiple of 8 (scalar fix-up path)
 @pytest.mark.parametrize("cfg", [(2, 128, 1, None, 8, 8), (3, 128, 2, 64, 4, 4), (2, 256, 1, None, 2, 2), (1, 128, 4, 32, 16, 16),
-                                 (2, 128, 2, 64, 24, 24)])
+                                 (2, 128, 2, 64, 24, 24), (1, 128, 1, None, 64, 64), (1, 128, 1, None, 18, 18)])
 def test_attention_block_forward_backward(prec, cfg):
     from models.custom_layers import AttentionBlock
     from b200.blocks import run_block_train
