@@ -119,6 +119,12 @@ int b2_transpose_weight_cl_multi(const long long* jobs_dev, int njobs, long long
 /* bf16 [Cout][9][Cin] (a 3x3 weight stored channels-last, the layout of kind 0) -> [Cin][9 flipped][Cout] (kind 1):
  * data-gradient weights derived from the optimiser's bf16 copy; Cout, Cin multiples of 64. */
 int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int Cin, void* stream);
+/* bf16 Linear weight [rows][cols] -> [cols][rows] (kind 4, the data-gradient layout of custom_layers.py:116,119) from the
+ * optimiser's bf16 copy; rows, cols multiples of 64. */
+int b2_transpose_linear_weight(const void* w, void* out, int rows, int cols, void* stream);
+/* bf16 ConvTranspose2d weight [Cin][Cout][4][4] (custom_layers.py:174) -> fwd (kind 2 layout) and/or dgrad (kind 6 layout),
+ * either may be NULL; Cin, Cout multiples of 32. */
+int b2_pack_convt_bf16(const void* w, void* fwd, void* dgrad, int Cin, int Cout, void* stream);
 /* GroupNorm statistics as a separate pass: stats[n][g] += (sum, sum of squares) of y (pre_swish: of Swish(y)); used for
  * group widths the conv epilogue does not fuse and by the standalone AdaGN module (custom_layers.py:35-45). */
 int b2_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, int C, int groups, int pre_swish, int dtype, void* stream);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "b2_pack_weight_multi": [_P, _I, _L, _I, _P],
     "b2_transpose_weight_cl_multi": [_P, _I, _L, _P],
     "b2_transpose_weight_cl": [_P, _P, _I, _I, _P],
+    "b2_transpose_linear_weight": [_P, _P, _I, _I, _P],
+    "b2_pack_convt_bf16": [_P, _P, _P, _I, _I, _P],
     "b2_area_resample": [_P, _P, _L, _I, _I, _I, _I, _P],
     "b2_mse_loss_grad": [_P, _P, _P, _P, _L, _F, _P],
 }

@@ -47,6 +47,27 @@ class WeightCache:
                     hit = (ver, out)
                     self._packed[key] = hit
                 return hit[1]
+            # Linear data-gradient weights (a transpose) and both ConvTranspose layouts come from the bf16 copy as well,
+            # through shared-memory tiles: the generic fp32 gather reads one 32-byte sector per element for these layouts
+            # (1.3 ms per train step when it handled them)
+            derived = None
+            if self._from_shadow(param, lay, kind, code, cout, cin, cin_pad):
+                if kind == 4:
+                    derived = ((cin, cout), lambda src, out: call("b2_transpose_linear_weight", ptr(src), ptr(out), cout, cin, stream()))
+                elif kind == 2:
+                    derived = ((4 * cout, 4 * cin), lambda src, out: call("b2_pack_convt_bf16", ptr(src), ptr(out), None, cin, cout, stream()))
+                else:
+                    derived = ((cin, 16 * cout), lambda src, out: call("b2_pack_convt_bf16", ptr(src), None, ptr(out), cin, cout, stream()))
+            if derived is not None:
+                ver = (param.data_ptr(), param._version, lay.epoch)
+                hit = self._packed.get(key)
+                if hit is None or hit[0] != ver or tuple(hit[1].shape) != derived[0]:
+                    out = hit[1] if hit is not None and tuple(hit[1].shape) == derived[0] else \
+                        torch.empty(derived[0], dtype=torch.bfloat16, device=param.device)
+                    derived[1](lay.shadow_slice(param), out)
+                    hit = (ver, out)
+                    self._packed[key] = hit
+                return hit[1]
         ver = (param.data_ptr(), param._version, lay.epoch if lay is not None else 0)
         hit = self._packed.get(key)
         if lay is not None:
@@ -55,6 +76,15 @@ class WeightCache:
             hit = (ver, ops.pack_weight(kind, param, cout, cin, cin_pad, code))
             self._packed[key] = hit
         return hit[1]
+
+    @staticmethod
+    def _from_shadow(param, lay, kind, code, cout, cin, cin_pad):
+        """True when get() derives this layout from the optimiser's bf16 copy with a tiled kernel (so refresh_all leaves it)."""
+        if lay is None or code != ops.BF16 or lay.shadow is None or id(param) not in lay.offsets or lay.is_cl(param):
+            return False
+        if kind == 4:
+            return cin_pad == cout and cout % 64 == 0 and cin % 64 == 0
+        return kind in (2, 6) and cin % 32 == 0 and cout % 32 == 0
 
     def _table(self, name, rows, device):
         """Device int64 job table, cached by content (pointers are stable across steps, so steady state uploads nothing --
@@ -96,6 +126,8 @@ class WeightCache:
             else:
                 if not param.is_contiguous():
                     continue                      # channels-last stored parameter read through a permuted view: stays lazy
+                if self._from_shadow(param, lay, kind, code, cout, cin, cin_pad):
+                    continue                      # made just in time from the bf16 copy (get)
                 shape = {0: (cout, 9 * cin_pad), 1: (cin, 9 * cin_pad), 2: (4 * cout, 4 * cin), 3: (cout, cin_pad), 4: (cin, cin_pad),
                          5: (4 * cin, 4 * cout), 6: (cin, 16 * cout)}[kind]
                 out = hit[1] if hit is not None and tuple(hit[1].shape) == shape else \

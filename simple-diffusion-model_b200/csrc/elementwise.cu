@@ -252,18 +252,19 @@ extern "C" int b2_pack_weight_multi(const long long* jobs_dev, int njobs, long l
 }
 
 // Data-gradient weights of a 3x3/s1 conv straight from the bf16 "channels-last" copy the optimiser maintains:
-// in [Cout][9][Cin] -> out [Cin][9 flipped][Cout].  64x64 tiles through shared memory, 128-byte rows on both sides.
+// in [Cout][taps][Cin] -> out [Cin][taps flipped][Cout], taps = gridDim.z (9: a 3x3 weight; 1: a Linear weight).  64x64 tiles
+// through shared memory, 128-byte rows on both sides.
 __global__ void transpose_weight_cl_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int Cout, int Cin) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ bf16 tile[64][64 + 8];
-    const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
+    const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z, taps = gridDim.z;
     const int t = threadIdx.x;                       // 256 threads
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int idx = t + i * 256;                 // 512 16-byte vectors: 64 rows (co) x 8
         const int r = idx >> 3, v = idx & 7;
-        const uint4 x = __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * 9 + tap) * Cin + ci0 + v * 8));
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * taps + tap) * Cin + ci0 + v * 8));
         *reinterpret_cast<uint4*>(&tile[r][v * 8]) = x;
     }
     __syncthreads();
@@ -275,7 +276,7 @@ __global__ void transpose_weight_cl_kernel(const bf16* __restrict__ in, bf16* __
         bf16* e = reinterpret_cast<bf16*>(&x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) e[j] = tile[v * 8 + j][r];
-        *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * 9 + (8 - tap)) * Cout + co0 + v * 8) = x;
+        *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * taps + (taps - 1 - tap)) * Cout + co0 + v * 8) = x;
     }
 }
 extern "C" int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int Cin, void* stream) {
@@ -283,6 +284,69 @@ extern "C" int b2_transpose_weight_cl(const void* w_cl, void* out, int Cout, int
     dim3 grid(Cin / 64, Cout / 64, 9);
     B2_LAUNCH((transpose_weight_cl_kernel), grid, 256, 0, (cudaStream_t)stream, (const bf16*)w_cl, (bf16*)out, Cout, Cin);
     LAUNCH_CHECK("b2_transpose_weight_cl");
+}
+extern "C" int b2_transpose_linear_weight(const void* w, void* out, int rows, int cols, void* stream) {
+    if (rows % 64 || cols % 64) return set_error("b2_transpose_linear_weight: rows and cols must be multiples of 64");
+    dim3 grid(cols / 64, rows / 64, 1);
+    B2_LAUNCH((transpose_weight_cl_kernel), grid, 256, 0, (cudaStream_t)stream, (const bf16*)w, (bf16*)out, rows, cols);
+    LAUNCH_CHECK("b2_transpose_linear_weight");
+}
+
+// Both kernel layouts of a ConvTranspose2d(4, stride 2, pad 1) weight from its bf16 copy w[Cin][Cout][4][4] (the 16 taps of
+// one (ci, co) pair are one 32-byte sector): a CTA stages a 32 ci x 32 co tile in shared memory and writes
+//   fwd   [4 parities][Cout][4 taps][Cin]   (kind 2; 64-byte runs along ci)     and / or
+//   dgrad [Cin][16][Cout]                   (kind 6; 64-byte runs along co).
+__global__ void pack_convT_bf16_kernel(const bf16* __restrict__ w, bf16* __restrict__ fwd, bf16* __restrict__ dgrad, int Cin, int Cout) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ uint32_t tile[32][32][9];             // [ci][co][8 tap pairs + 1 pad word]
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const int t = threadIdx.x;                       // 256 threads
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = t + i * 256;                 // 2048 16-byte vectors: (ci, co, half)
+        const int half = idx & 1, co = (idx >> 1) & 31, ci = idx >> 6;
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(w + ((long long)(ci0 + ci) * Cout + co0 + co) * 16 + half * 8));
+        uint32_t* d = &tile[ci][co][half * 4];
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    }
+    __syncthreads();
+    auto elem = [&](int ci, int co, int tap) -> uint32_t {          // the bf16 bits of w[ci][co][tap]
+        const uint32_t pair = tile[ci][co][tap >> 1];
+        return (tap & 1) ? (pair >> 16) : (pair & 0xffffu);
+    };
+    if (dgrad) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = t + i * 256;             // (ci, tap, 8-co vector)
+            const int v = idx & 3, tap = (idx >> 2) & 15, ci = idx >> 6;
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = elem(ci, v * 8 + 2 * j, tap) | (elem(ci, v * 8 + 2 * j + 1, tap) << 16);
+            *reinterpret_cast<uint4*>(dgrad + ((long long)(ci0 + ci) * 16 + tap) * Cout + co0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (fwd) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = t + i * 256;             // (parity g, co, tap t4, 8-ci vector)
+            const int v = idx & 3, t4 = (idx >> 2) & 3, co = (idx >> 4) & 31, g = idx >> 9;
+            const int a = g >> 1, b = g & 1, ti = t4 >> 1, tj = t4 & 1;
+            const int kh = a == 0 ? (ti == 0 ? 1 : 3) : (ti == 0 ? 2 : 0);
+            const int kw = b == 0 ? (tj == 0 ? 1 : 3) : (tj == 0 ? 2 : 0);
+            const int tap = kh * 4 + kw;
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = elem(v * 8 + 2 * j, co, tap) | (elem(v * 8 + 2 * j + 1, co, tap) << 16);
+            *reinterpret_cast<uint4*>(fwd + (((long long)g * Cout + co0 + co) * 4 + t4) * Cin + ci0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+extern "C" int b2_pack_convt_bf16(const void* w, void* fwd, void* dgrad, int Cin, int Cout, void* stream) {
+    if (Cin % 32 || Cout % 32) return set_error("b2_pack_convt_bf16: Cin and Cout must be multiples of 32");
+    dim3 grid(Cin / 32, Cout / 32, 1);
+    B2_LAUNCH((pack_convT_bf16_kernel), grid, 256, 0, (cudaStream_t)stream, (const bf16*)w, (bf16*)fwd, (bf16*)dgrad, Cin, Cout);
+    LAUNCH_CHECK("b2_pack_convt_bf16");
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm x AdaGN apply
@@ -403,12 +467,13 @@ __global__ void transpose_weight_cl_multi_kernel(const long long* __restrict__ j
     const int ci0 = (t % (Cin / 64)) * 64;  t /= (Cin / 64);
     const int co0 = (t % (Cout / 64)) * 64; const int tap = t / (Cout / 64);
     const int tid = threadIdx.x;
+    constexpr int taps = 9;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int idx = tid + i * 256;
         const int r = idx >> 3, v = idx & 7;
         *reinterpret_cast<uint4*>(&tile[r][v * 8]) =
-            __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * 9 + tap) * Cin + ci0 + v * 8));
+            __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * taps + tap) * Cin + ci0 + v * 8));
     }
     __syncthreads();
 #pragma unroll
@@ -419,7 +484,7 @@ __global__ void transpose_weight_cl_multi_kernel(const long long* __restrict__ j
         bf16* e = reinterpret_cast<bf16*>(&x);
 #pragma unroll
         for (int k = 0; k < 8; ++k) e[k] = tile[v * 8 + k][r];
-        *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * 9 + (8 - tap)) * Cout + co0 + v * 8) = x;
+        *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * taps + (taps - 1 - tap)) * Cout + co0 + v * 8) = x;
     }
 }
 extern "C" int b2_transpose_weight_cl_multi(const long long* jobs_dev, int njobs, long long total_tiles, void* stream) {

@@ -266,3 +266,29 @@ def test_partial_tiles_do_not_write_out_of_bounds(prec):
     torch.cuda.synchronize()
     chk3()
     assert rel_l2(c.float(), a.float() @ b.float().t()) < 2 * tol
+
+
+def test_shadow_derived_weight_layouts_match_generic_pack():
+    """The tiled bf16 -> kernel-layout kernels the training path uses (ConvTranspose forward / data-gradient layouts,
+    Linear data-gradient transpose) are bit-identical to the generic fp32 pack of the same weights."""
+    from b200 import ops
+    from b200._lib import call, ptr, stream
+    torch.manual_seed(5)
+    for cin, cout in ((64, 32), (128, 96)):
+        w = torch.randn((cin, cout, 4, 4), device="cuda")
+        wb = w.bfloat16().contiguous()
+        want_f = ops.pack_weight(2, w, cout, cin, cin, ops.BF16)
+        want_d = ops.pack_weight(6, w, cout, cin, cout, ops.BF16)
+        fwd, dg = torch.zeros_like(want_f), torch.zeros_like(want_d)
+        call("b2_pack_convt_bf16", ptr(wb), ptr(fwd), ptr(dg), cin, cout, stream())
+        assert torch.equal(fwd, want_f) and torch.equal(dg, want_d)
+        fwd2, dg2 = torch.zeros_like(want_f), torch.zeros_like(want_d)
+        call("b2_pack_convt_bf16", ptr(wb), ptr(fwd2), None, cin, cout, stream())
+        call("b2_pack_convt_bf16", ptr(wb), None, ptr(dg2), cin, cout, stream())
+        assert torch.equal(fwd2, want_f) and torch.equal(dg2, want_d)
+    for rows, cols in ((192, 64), (128, 256)):
+        w = torch.randn((rows, cols), device="cuda")
+        out = torch.zeros((cols, rows), dtype=torch.bfloat16, device="cuda")
+        call("b2_transpose_linear_weight", ptr(w.bfloat16().contiguous()), ptr(out), rows, cols, stream())
+        assert torch.equal(out, ops.pack_weight(4, w, rows, cols, rows, ops.BF16))
+        assert torch.equal(out, w.bfloat16().t())
