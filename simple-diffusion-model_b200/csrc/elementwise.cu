@@ -265,7 +265,7 @@ __global__ void transpose_weight_cl_kernel(const bf16* __restrict__ in, bf16* __
         const int idx = t + i * 256;                 // 512 16-byte vectors: 64 rows (co) x 8
         const int r = idx >> 3, v = idx & 7;
         const uint4 x = __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * taps + tap) * Cin + ci0 + v * 8));
-        *reinterpret_cast<uint4*>(&tile[r][v * 8]) = x;
+        *reinterpret_cast<uint4*>(&tile[r][(v ^ ((r >> 3) & 7)) * 8]) = x;      // 16-byte chunks XOR-swizzled by row / 8
     }
     __syncthreads();
 #pragma unroll
@@ -275,7 +275,7 @@ __global__ void transpose_weight_cl_kernel(const bf16* __restrict__ in, bf16* __
         uint4 x;
         bf16* e = reinterpret_cast<bf16*>(&x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = tile[v * 8 + j][r];
+        for (int j = 0; j < 8; ++j) e[j] = tile[v * 8 + j][(((r >> 3) ^ v) << 3) + (r & 7)];    // conflict-free across v
         *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * taps + (taps - 1 - tap)) * Cout + co0 + v * 8) = x;
     }
 }
@@ -472,7 +472,7 @@ __global__ void transpose_weight_cl_multi_kernel(const long long* __restrict__ j
     for (int i = 0; i < 2; ++i) {
         const int idx = tid + i * 256;
         const int r = idx >> 3, v = idx & 7;
-        *reinterpret_cast<uint4*>(&tile[r][v * 8]) =
+        *reinterpret_cast<uint4*>(&tile[r][(v ^ ((r >> 3) & 7)) * 8]) =
             __ldg(reinterpret_cast<const uint4*>(in + ((long long)(co0 + r) * taps + tap) * Cin + ci0 + v * 8));
     }
     __syncthreads();
@@ -483,7 +483,7 @@ __global__ void transpose_weight_cl_multi_kernel(const long long* __restrict__ j
         uint4 x;
         bf16* e = reinterpret_cast<bf16*>(&x);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) e[k] = tile[v * 8 + k][r];
+        for (int k = 0; k < 8; ++k) e[k] = tile[v * 8 + k][(((r >> 3) ^ v) << 3) + (r & 7)];
         *reinterpret_cast<uint4*>(out + ((long long)(ci0 + r) * taps + (taps - 1 - tap)) * Cout + co0 + v * 8) = x;
     }
 }

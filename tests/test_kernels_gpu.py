@@ -292,3 +292,9 @@ def test_shadow_derived_weight_layouts_match_generic_pack():
         call("b2_transpose_linear_weight", ptr(w.bfloat16().contiguous()), ptr(out), rows, cols, stream())
         assert torch.equal(out, ops.pack_weight(4, w, rows, cols, rows, ops.BF16))
         assert torch.equal(out, w.bfloat16().t())
+    for cout, cin in ((64, 128), (192, 64)):                 # 3x3 weight stored channels-last -> stride-1 data-gradient layout
+        w = torch.randn((cout, cin, 3, 3), device="cuda")
+        wcl = w.permute(0, 2, 3, 1).contiguous().bfloat16()
+        out = torch.zeros((cin, 9 * cout), dtype=torch.bfloat16, device="cuda")
+        call("b2_transpose_weight_cl", ptr(wcl), ptr(out), cout, cin, stream())
+        assert torch.equal(out, ops.pack_weight(1, w, cout, cin, cout, ops.BF16))
