@@ -85,6 +85,9 @@ def run(args):
                           "gpu_launches_per_step": (b2lib.LAUNCHES - l0) // args.steps, "scaling": "weak",
                           "graph": bool(args.graph), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "host_ms_per_step": wall}), flush=True)
     if world > 1:
+        # the captured graph holds NCCL kernels: release it before the communicator (destroying the group first hangs)
+        del graphed, opt, dp, net
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
