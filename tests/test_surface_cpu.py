@@ -72,6 +72,36 @@ def test_c_abi_exports_every_declared_symbol():
     assert handle.b2_version() >= 100
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/sdm_b200.h, parameter by parameter, against the ctypes table the host side calls through
+    (a drifted argument list would corrupt the call silently: ctypes cannot check it)."""
+    from b200._lib import SIGNATURES
+    header = open(os.path.join(ROOT, "include", "sdm_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", " ", header)
+    protos = dict(re.findall(r"\bint\s+(b2_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header))
+
+    def code(param):
+        param = " ".join(param.split())
+        if "*" in param:
+            return ctypes.c_void_p
+        if param.startswith("unsigned long long"):
+            return ctypes.c_ulonglong
+        if param.startswith("long long"):
+            return ctypes.c_longlong
+        if param.startswith("double"):
+            return ctypes.c_double
+        if param.startswith("float"):
+            return ctypes.c_float
+        assert param.startswith("int"), param
+        return ctypes.c_int
+
+    for name, argtypes in SIGNATURES.items():
+        assert name in protos, name
+        params = [q for q in protos[name].split(",") if q.strip() and q.strip() != "void"]
+        assert [code(q) for q in params] == list(argtypes), f"{name}: header {protos[name]!r} vs ctypes table"
+
+
 def test_entry_points_keep_reference_names_and_fail_loudly_without_cuda(tmp_path):
     """train_*/generate_* (reference L4 scripts): same module / function names, config validation errors of the
     reference (train_diffusion.py:69-116), and no silent CPU path."""
