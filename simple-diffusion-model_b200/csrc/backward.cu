@@ -201,6 +201,20 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
     if (dbias) block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
 }
 
+// Optional L2 blocking of the two passes (SDM_B200_BWD_L2_CHUNK_MB=<MiB>, default off): both passes read dout and z, so
+// running them over groups of images whose (dout, z) fit in the 126 MB L2 lets pass 2 hit L2 instead of HBM
+// (10 -> 6 algorithmic DRAM bytes per element).  Images are independent in both kernels, so the result is unchanged.
+static int adagn_bwd_chunk_images(int N, long long bytes_per_image) {
+    static const long long budget = [] {
+        const char* e = getenv("SDM_B200_BWD_L2_CHUNK_MB");
+        return e ? atoll(e) * (1LL << 20) : 0LL;
+    }();
+    if (budget <= 0 || bytes_per_image <= 0) return N;
+    long long nc = budget / bytes_per_image;
+    if (nc < 1) nc = 1;
+    return nc < N ? (int)nc : N;
+}
+
 extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
                             const float* gamma, const float* beta, const float* s, long long s_bstride, float* work,
                             float* ds, long long ds_bstride, float* dgamma, float* dbeta, void* dz, long long lddz,
@@ -211,20 +225,31 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
     const int cv = C / V;
     if (cv > 1024) return set_error("b2_adagn_bwd: C too large");
     cudaStream_t st = (cudaStream_t)stream;
-    // work: [2][N][C] fp32 (a1, a2), zeroed by the caller
-    float* a1 = work;
-    float* a2 = work + (long long)N * C;
-    const SlabLaunch sl = slab_launch(N, HW, cv);
-    size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
-    if (red_bytes < (size_t)groups * 2 * sizeof(float)) red_bytes = (size_t)groups * 2 * sizeof(float);
-    if (dtype == 0)
-        B2_LAUNCH((adagn_bwd_reduce_kernel<bf16>), N * sl.slabs, sl.threads, red_bytes, st, (const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
-    else
-        B2_LAUNCH((adagn_bwd_reduce_kernel<float>), N * sl.slabs, sl.threads, red_bytes, st, (const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
-    if (dtype == 0)
-        B2_LAUNCH((adagn_bwd_apply_kernel<bf16>), N * sl.slabs, sl.threads, red_bytes, st, (const bf16*)dout, ldd, (const bf16*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (bf16*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
-    else
-        B2_LAUNCH((adagn_bwd_apply_kernel<float>), N * sl.slabs, sl.threads, red_bytes, st, (const float*)dout, ldd, (const float*)z, ldz, stats, a1, a2, s, s_bstride, gamma, beta, ds, ds_bstride, dgamma, dbeta, (float*)dz, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+    const long long eb = dtype == 0 ? 2 : 4;
+    const int chunk = adagn_bwd_chunk_images(N, 2LL * HW * C * eb);
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int nc = N - n0 < chunk ? N - n0 : chunk;
+        // work: [2][N][C] fp32 (a1, a2), zeroed by the caller
+        float* a1 = work + (long long)n0 * C;
+        float* a2 = work + (long long)N * C + (long long)n0 * C;
+        const char* d_c = (const char*)dout + (long long)n0 * HW * ldd * eb;
+        const char* z_c = (const char*)z + (long long)n0 * HW * ldz * eb;
+        char* dz_c = (char*)dz + (long long)n0 * HW * lddz * eb;
+        const float* stats_c = stats + (long long)n0 * groups * 2;
+        const float* s_c = s + (long long)n0 * s_bstride;
+        float* ds_c = ds ? ds + (long long)n0 * ds_bstride : nullptr;
+        const SlabLaunch sl = slab_launch(nc, HW, cv);
+        size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
+        if (red_bytes < (size_t)groups * 2 * sizeof(float)) red_bytes = (size_t)groups * 2 * sizeof(float);
+        if (dtype == 0)
+            B2_LAUNCH((adagn_bwd_reduce_kernel<bf16>), nc * sl.slabs, sl.threads, red_bytes, st, (const bf16*)d_c, ldd, (const bf16*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        else
+            B2_LAUNCH((adagn_bwd_reduce_kernel<float>), nc * sl.slabs, sl.threads, red_bytes, st, (const float*)d_c, ldd, (const float*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        if (dtype == 0)
+            B2_LAUNCH((adagn_bwd_apply_kernel<bf16>), nc * sl.slabs, sl.threads, red_bytes, st, (const bf16*)d_c, ldd, (const bf16*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (bf16*)dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+        else
+            B2_LAUNCH((adagn_bwd_apply_kernel<float>), nc * sl.slabs, sl.threads, red_bytes, st, (const float*)d_c, ldd, (const float*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (float*)dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+    }
     LAUNCH_CHECK("b2_adagn_bwd");
 }
 
