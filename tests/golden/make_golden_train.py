@@ -1,6 +1,8 @@
 """Generates tests/golden/train_runs.pt by running the UNMODIFIED reference trainers from /root/reference on CPU:
 `train_diffusion.main()`, `train_noise_cold_diffusion.main()` and `train_SR_diffusion.main()`, four optimisation steps each
-of a tiny U_Net on four synthetic PNG images.  (train_doodle_diffusion imports tinydb, which this image lacks.)
+of a tiny U_Net on four synthetic PNG images -- and `train_doodle_diffusion.main()`, whose dataset class imports `tinydb`:
+that package is absent from this image, so a minimal read-only stand-in (same `TinyDB(path).table(name).all()` surface over
+the same JSON file format) is registered in sys.modules for the run.
 
 Nothing of the reference is modified: the script only wraps, at run time, the functions the trainers call so that it can
 RECORD what flowed through them -- the (image, timestep, eps) triples given to the noise degrader, the target and value of
@@ -28,6 +30,27 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
+import types  # noqa: E402
+
+try:
+    import tinydb  # noqa: F401,E402
+except ImportError:                                  # stand-in for the one call chain custom_dataset/doodle_dataset.py:19-28 uses
+    class _Table(list):
+        def all(self):
+            return list(self)
+
+    class _TinyDB:
+        def __init__(self, path):
+            with open(path) as f:
+                self._tables = json.load(f)
+
+        def table(self, name):
+            return _Table(self._tables.get(name, {}).values())
+
+    _mod = types.ModuleType("tinydb")
+    _mod.TinyDB = _TinyDB
+    sys.modules["tinydb"] = _mod
+
 import degraders as ref_degraders  # noqa: E402  (reference)
 from models.U_Net import U_Net  # noqa: E402  (reference)
 from oracle.weights import synth_state_dict  # noqa: E402
@@ -43,6 +66,8 @@ RUNS = {
     "cold": ("train_noise_cold_diffusion", dict(NET, image_recon=True), 16, dict(noise_scheduler="COSINE")),
     "sr": ("train_SR_diffusion", dict(NET, in_channel=6, image_recon=True), 32,
            dict(noise_scheduler="COSINE", lr_dim=8, sr_dim=32, cond_t=5)),
+    "doodle": ("train_doodle_diffusion", dict(NET, in_channel=6), 16,
+               dict(noise_scheduler="LINEAR", beta1=5e-3, betaT=9e-3, diffusion_alg="DDPM")),
 }
 
 
@@ -62,8 +87,17 @@ def run(name, module, net_kw, size, overrides, work):
     os.makedirs(img_dir)
     for i in range(4):
         cv2.imwrite(os.path.join(img_dir, f"{i}.png"), rng.randint(0, 256, (size, size, 3)).astype(np.uint8))
+    dataset_path = os.path.join(img_dir, "*.png")
+    if name == "doodle":                             # TinyDB file: Data rows {filename, <label>: condition image path}
+        for i in range(4):
+            cv2.imwrite(os.path.join(img_dir, f"c{i}.png"), rng.randint(0, 256, (size, size, 3)).astype(np.uint8))
+        dataset_path = os.path.join(work, "doodle_db.json")
+        with open(dataset_path, "w") as f:
+            json.dump({"Labels": {"1": {"labels": ["doodle"]}},
+                       "Data": {str(i + 1): {"filename": os.path.join(img_dir, f"{i}.png"),
+                                             "doodle": os.path.join(img_dir, f"c{i}.png")} for i in range(4)}}, f)
     out_dir = os.path.join(work, f"{name}_out")
-    cfg = dict(dataset_path=os.path.join(img_dir, "*.png"), out_dir=out_dir, checkpoint_steps=1, lr_steps=2, max_epoch=2,
+    cfg = dict(dataset_path=dataset_path, out_dir=out_dir, checkpoint_steps=1, lr_steps=2, max_epoch=2,
                plot_img_count=1, use_conditional=False, flip_imgs=False, model_checkpoint=init, config_checkpoint=None,
                load_diffusion_optim=False, diffusion_lr=2e-4, batch_size=2, min_noise_step=1, max_noise_step=20,
                max_actual_noise_step=20, skip_step=5, in_channel=net_kw.get("in_channel", 3), out_channel=3,
@@ -76,9 +110,14 @@ def run(name, module, net_kw, size, overrides, work):
         json.dump(cfg, f)
 
     # ---- recorders around the functions the trainer calls (the trainer itself is untouched)
-    pending, steps = [], []
+    pending, net_inputs, steps = [], [], []
     orig_fwd = {cls: cls.forward for cls in (ref_degraders.NoiseDegradation, ref_degraders.CosineNoiseDegradation)}
-    orig_mse, orig_zero = F.mse_loss, torch.optim.Adam.zero_grad
+    orig_mse, orig_zero, orig_net = F.mse_loss, torch.optim.Adam.zero_grad, U_Net.forward
+
+    def net_forward(self, x, t=None, cond=None):
+        if torch.is_grad_enabled() and self.training:
+            net_inputs.append(dict(x=x.detach().clone(), t=t.detach().clone(), cond=cond))
+        return orig_net(self, x, t, cond)
 
     def make_fwd(orig):
         def fwd(self, img, steps, eps=None):
@@ -92,8 +131,8 @@ def run(name, module, net_kw, size, overrides, work):
     def mse(pred, target, *a, **k):
         loss = orig_mse(pred, target, *a, **k)
         if torch.is_grad_enabled() and pred.requires_grad:
-            steps.append(dict(degrader_calls=list(pending), target=target.detach().clone(), pred=pred.detach().clone(),
-                              loss=float(loss)))
+            steps.append(dict(degrader_calls=list(pending), net_input=net_inputs[-1], target=target.detach().clone(),
+                              pred=pred.detach().clone(), loss=float(loss.detach())))
         return loss
 
     def zero_grad(self, *a, **k):
@@ -104,6 +143,7 @@ def run(name, module, net_kw, size, overrides, work):
         cls.forward = make_fwd(orig)
     F.mse_loss = mse
     torch.optim.Adam.zero_grad = zero_grad
+    U_Net.forward = net_forward
     argv = sys.argv
     try:
         sys.argv = [module, "-c", cfg_path, "--device", "cpu"]
@@ -115,6 +155,7 @@ def run(name, module, net_kw, size, overrides, work):
             cls.forward = orig
         F.mse_loss = orig_mse
         torch.optim.Adam.zero_grad = orig_zero
+        U_Net.forward = orig_net
 
     assert len(steps) == 4, len(steps)
     ckpts = []

@@ -1,6 +1,6 @@
 """The oracle's train-step restatement against runs of the UNMODIFIED reference trainers (tests/golden/train_runs.pt, written
 by tests/golden/make_golden_train.py): `train_diffusion.main()`, `train_noise_cold_diffusion.main()` and
-`train_SR_diffusion.main()`, four optimisation steps each.  The fixture holds what flowed through the reference's degrader
+`train_SR_diffusion.main()` and `train_doodle_diffusion.main()`, four optimisation steps each.  The fixture holds what flowed through the reference's degrader
 and F.mse_loss at every step and samples of the checkpoints it wrote; replaying the recorded (x0, t, eps) through the oracle
 must reproduce every loss, every checkpointed weight and the learning-rate schedule."""
 import pytest
@@ -17,7 +17,7 @@ def _sample(t, n):
     return flat[(torch.arange(n, dtype=torch.int64) * flat.numel()) // n]
 
 
-@pytest.mark.parametrize("name", ["base", "cold", "sr"])
+@pytest.mark.parametrize("name", ["base", "cold", "sr", "doodle"])
 def test_oracle_reproduces_reference_trainer_run(name):
     fx = load_golden("train_runs.pt")[name]
     cfg, kw = fx["config"], fx["kwargs"]
@@ -44,11 +44,21 @@ def test_oracle_reproduces_reference_trainer_run(name):
             assert calls[1]["steps"].tolist() == [cfg["cond_t"]]
             inp = torch.cat((x_t, orc.q_sample(sched, low, calls[1]["steps"], eps)), dim=1)
             target = x0 - low
+        elif name == "doodle":
+            # train_doodle_diffusion.py:296-315: the condition image is concatenated un-noised; target eps; no labels
+            assert len(calls) == 1
+            cond_img = rec["net_input"]["x"][:, 3:]
+            assert float(cond_img.abs().max()) <= 1.0 and cond_img.shape == x0.shape
+            inp = torch.cat((x_t, cond_img), dim=1)
+            target = eps
         else:
             assert len(calls) == 1
             inp = x_t
             target = eps if name == "base" else x0
         assert torch.equal(rec["target"], target)
+        # what the reference's U_Net actually received: (x_t [, condition]), the per-image timesteps, no labels
+        assert rel_l2(inp, rec["net_input"]["x"]) < 1e-6 and torch.equal(rec["net_input"]["t"], t)
+        assert rec["net_input"]["cond"] is None
         pred = orc.unet_forward(params, inp, t, None, heads=1, image_recon=recon)
         assert rel_l2(pred.detach(), rec["pred"]) < 1e-5
         loss = F.mse_loss(pred, target)
