@@ -18,11 +18,23 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "simple-diffusion-model_b200"))
-sys.path.insert(1, ROOT)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")            # verbatim copy of the unmodified reference (__graft_entry__.install_reference)
+_REF_ARM = any(a in ("reference", "torch-eager") or a.endswith("=reference") or a.endswith("=torch-eager") for a in sys.argv[1:]) \
+    and os.path.isfile(os.path.join(REF_DIR, "models", "U_Net.py"))
+if _REF_ARM:
+    # the reference arms import the reference's OWN modules (models.U_Net, degraders, diffusion_sampling_algorithms): this repo's
+    # same-named package must not be importable in that process -- none of our models, kernels or engine on that path
+    sys.path.insert(0, REF_DIR)
+    sys.path.insert(1, ROOT)
+else:
+    sys.path.insert(0, os.path.join(ROOT, "simple-diffusion-model_b200"))
+    sys.path.insert(1, ROOT)
 
 import torch  # noqa: E402
 
+WORKLOAD = ("DDIM-50 (51 evals, ddim_step_size=20, T=1000) cosine schedule, class-default U_Net (610.7M params, random init) "
+            "64x64 RGB, batch {batch}/GPU, sharded by image")
+L2_NOTE = "inputs larger than L2: working set per evaluation (1.2 GB weights + >250 MB activations per layer) exceeds the 126 MB L2"
 METRIC = "ddim50_sampled_images_per_s"
 UNIT = "img/s"
 IMG, BATCH, STEP_SIZE, T_MAX = 64, 256, 20, 1000
@@ -36,6 +48,23 @@ def load_peaks():
             p = json.load(f)
         return p, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def load_traffic(batch):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch of the family's heaviest shape, READ from the
+    committed summary of an `ncu --set full` capture (profiles/roofline_traffic.json, written by tools/ncu_summary.py --traffic);
+    null when no capture of this batch size is on file -- never a constant in this script."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if int(t.get("batch", -1)) == int(batch):
+            return {"traffic": float(t["dram_bytes_per_launch"]), "traffic_unit": "bytes/launch (heaviest shape)",
+                    "traffic_kernel": t.get("kernel"), "traffic_algorithmic_bytes": t.get("algorithmic_bytes"),
+                    "traffic_source": t.get("source")}
+    except (OSError, ValueError, KeyError):
+        pass
+    return {"traffic": None}
 
 
 class ClockSampler:
@@ -135,28 +164,185 @@ def cpu_reference_sample(threads, evals=3, batch=4):
     return batch / (dt * 51.0 / evals), dt, f"{evals} of 51 DDIM evaluations at batch {batch} (class-default U_Net 64x64, fp32), scaled x51/{evals}"
 
 
+REF_BATCH, REF_EVALS = 8, 3        # bounded sample of the reference arm: 3 of the 51 DDIM evaluations at batch 8
+
+
+def ref_reference_sample(threads, evals=REF_EVALS, batch=REF_BATCH):
+    """The UNMODIFIED reference (baseline/_ref: its U_Net, its CosineNoiseDegradation, its ddim_sampling) on the host CPU, all
+    threads, on a bounded sample of the bench workload: the last `evals` steps of the DDIM-50 schedule (t = ..., 41, 21, 1) at
+    batch `batch` through the reference's own public sampler.  Per-evaluation cost does not depend on t, so
+    img/s = batch / (seconds * 51 / evals)."""
+    from degraders import CosineNoiseDegradation          # reference modules (sys.path[0] == baseline/_ref)
+    from diffusion_sampling_algorithms import ddim_sampling
+    from models.U_Net import U_Net
+    torch.set_num_threads(threads)
+    net = getattr(ref_reference_sample, "_net", None)
+    if net is None:
+        torch.manual_seed(0)
+        net = U_Net().eval()                              # class-default 610.7 M net, reference initialisation
+        ref_reference_sample._net = net
+    x_t = torch.randn((batch, 3, IMG, IMG), generator=torch.Generator().manual_seed(1))
+    top = 1 + STEP_SIZE * (evals - 1)
+    t0 = time.perf_counter()
+    out = ddim_sampling(net, CosineNoiseDegradation(T_MAX), x_t, min_noise=1, max_noise=top, ddim_step_size=STEP_SIZE,
+                        device="cpu", log=lambda *a, **k: None)
+    dt = time.perf_counter() - t0
+    assert tuple(out.shape) == (batch, 3, IMG, IMG)
+    return batch / (dt * 51.0 / evals), dt, (f"unmodified reference (baseline/_ref) ddim_sampling: {evals} of 51 DDIM evaluations at batch {batch} "
+                                             f"(class-default U_Net {IMG}x{IMG}, fp32, torch CPU), scaled x51/{evals}")
+
+
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores.  kind "reference" when
+    baseline/_ref is present (the normal case), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_reference_sample(threads, evals=1, batch=2)
-    vals, secs = [], 0.0
-    sample = ""
+    real = _REF_ARM
+    sampler = ref_reference_sample if real else cpu_reference_sample
+    for _ in range(max(args.warmup, 1)):
+        sampler(threads, evals=1, batch=2)
+    vals, secs, sample = [], [], ""
     for _ in range(args.steps):
-        v, dt, sample = cpu_reference_sample(threads)
+        v, dt, sample = sampler(threads)
         vals.append(v)
-        secs += dt
+        secs.append(dt)
     value = len(vals) / sum(1.0 / v for v in vals)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH / value, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"DDIM-50 (51 evals) cosine schedule, class-default U_Net {IMG}x{IMG}, batch {BATCH}/GPU"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "warmup": args.warmup,
+            # one timed step = one bounded sample (see cpu_baseline.sample); the full 51-evaluation batch-256 sampling would take
+            # ms_per_full_step on these cores
+            "ms_per_step": 1000.0 * sum(secs) / len(secs), "ms_per_full_step": 1000.0 * BATCH / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            # the same workload, metric and unit as the b200 arm; what one timed step actually ran is in cpu_baseline.sample
+            "config": {"workload": WORKLOAD.format(batch=BATCH), "global_batch": BATCH * max(args.gpus, 1), "l2": L2_NOTE},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference" if real else "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
+
+# ---------------------------------------------------------------------------------------------------- torch eager on the B200
+def run_torch_eager_arm(args):
+    """`--impl torch-eager`: the UNMODIFIED reference modules (baseline/_ref) executed by PyTorch eager on the B200 -- cuDNN /
+    cuBLAS / ATen, the only pre-existing Blackwell kernels for this path -- on the bench's two workloads:
+    the reference's own `ddim_sampling` (51 evaluations, batch 256, 64x64, cosine) and the reference's train-step body
+    (train_diffusion.py:310-366: randn_like, randint, q-sample, U_Net, mse_loss, GradScaler backward/step, Adam(0.5, 0.999)) on
+    the label-conditioned net at 128x128.  Two precisions each: the reference's own mode on CUDA, autocast (its default
+    dtype is fp16; bf16 is measured too because that is what this repo computes in), and fp32 with TF32 enabled.  CUDA
+    events, 1 warm-up sampling / 3 warm-up steps.  Prints one JSON line."""
+    import torch.nn.functional as F
+    from degraders import CosineNoiseDegradation, NoiseDegradation      # reference modules
+    from diffusion_sampling_algorithms import ddim_sampling
+    from models.U_Net import U_Net
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    quiet = lambda *a, **k: None
+    out = {"impl": "torch-eager", "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(),
+           "note": "unmodified reference modules from baseline/_ref, PyTorch eager on the same B200; TF32 enabled for fp32"}
+
+    def timed(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- DDIM-50, batch 256, 64x64, cosine (BASELINE configs[1])
+    torch.manual_seed(0)
+    net = U_Net().to(dev).eval()
+    deg = CosineNoiseDegradation(T_MAX)
+    batch = args.batch
+    x_T = torch.randn((batch, 3, IMG, IMG), device=dev)
+    ddim = {}
+    for mode in ("bf16_autocast", "fp16_autocast", "fp32_tf32"):
+        def sample():
+            if mode == "fp32_tf32":
+                return ddim_sampling(net, deg, x_T, min_noise=1, max_noise=T_MAX, ddim_step_size=STEP_SIZE, device=dev, log=quiet)
+            with torch.autocast("cuda", dtype=torch.bfloat16 if mode == "bf16_autocast" else torch.float16):
+                return ddim_sampling(net, deg, x_T, min_noise=1, max_noise=T_MAX, ddim_step_size=STEP_SIZE, device=dev, log=quiet)
+        try:
+            # warm-up: a short schedule (3 evaluations) is enough to settle cuDNN's heuristics and the allocator
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                ddim_sampling(net, deg, x_T, min_noise=1, max_noise=41, ddim_step_size=STEP_SIZE, device=dev, log=quiet)
+            ms = timed(sample, 0, max(1, min(args.steps, 2)))
+            ddim[mode] = {"img_per_s": batch / (ms / 1000.0), "ms_per_step": ms}
+        except Exception as e:      # noqa: BLE001  (an OOM here must not lose the other numbers)
+            ddim[mode] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
+    out["ddim50"] = {"workload": WORKLOAD.format(batch=batch), "unit": "img/s", **ddim}
+    del net
+    torch.cuda.empty_cache()
+
+    # ---- train step, 128x128, cond_dim 10 (BASELINE configs[2])
+    train = {}
+    for mode in ("bf16_autocast", "fp16_autocast", "fp32_tf32"):
+        n = args.train_batch
+        while n >= 4:
+            try:
+                torch.manual_seed(0)
+                net = U_Net(cond_dim=TRAIN_COND).to(dev).train()
+                opt = torch.optim.Adam(net.parameters(), lr=2e-5, betas=(0.5, 0.999))
+                scaler = torch.amp.GradScaler("cuda", enabled=(mode == "fp16_autocast"))
+                degl = NoiseDegradation(5e-3, 9e-3, T_MAX, dev)
+                x0 = torch.rand((n, 3, TRAIN_IMG, TRAIN_IMG), device=dev) * 2 - 1
+                labels = (torch.rand((n, TRAIN_COND), device=dev) > 0.7).float()
+
+                def step():
+                    noise = torch.randn_like(x0)
+                    opt.zero_grad()
+                    t = torch.randint(low=1, high=T_MAX, size=(n,), device=dev)
+                    with torch.autocast("cuda", dtype=torch.float16 if mode == "fp16_autocast" else torch.bfloat16,
+                                        enabled=(mode != "fp32_tf32")):
+                        x_t = degl(img=x0, steps=t, eps=noise)
+                        loss = F.mse_loss(net(x_t, t, labels), noise)
+                    scaler.scale(loss).backward()
+                    scaler.step(opt)
+                    scaler.update()
+                    return loss.item()                       # the reference reads the loss every step (train_diffusion.py:366)
+
+                ms = timed(step, 3, 5)
+                train[mode] = {"img_per_s": n / (ms / 1000.0), "ms_per_step": ms, "batch": n,
+                               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+                break
+            except torch.OutOfMemoryError:
+                n //= 2
+                train[mode] = {"error": "out of memory", "batch_tried": n * 2}
+            finally:
+                net = opt = None
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats()
+    out["train"] = {"workload": f"eps-prediction train step, class-default U_Net(cond_dim={TRAIN_COND}) {TRAIN_IMG}x{TRAIN_IMG}, "
+                                f"Adam(0.5, 0.999), torch eager", "unit": "img/s", **train}
+    print(json.dumps(out), flush=True)
+
+
+def torch_eager_subprocess(args, timeout=900):
+    """Runs `bench.py --impl torch-eager` in a fresh process (the reference's module names clash with this repo's) once this
+    process has released the GPU; returns its JSON object, or {"unavailable": why}."""
+    if not os.path.isfile(os.path.join(REF_DIR, "models", "U_Net.py")):
+        return {"unavailable": "baseline/_ref missing (run __graft_entry__.build() where /root/reference exists)"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "torch-eager", "--steps", str(args.steps), "--batch", str(args.batch),
+           "--train-batch", str(args.train_batch)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"torch-eager arm exceeded {timeout} s"}
+    for ln in reversed(res.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            try:
+                return json.loads(ln)
+            except json.JSONDecodeError:
+                break
+    return {"unavailable": "torch-eager arm printed no JSON", "stderr_tail": res.stderr[-300:]}
 
 
 # ---------------------------------------------------------------------------------------------------- train-step leg
@@ -201,8 +387,10 @@ def run_train_leg(args, dev, world, rank, barrier, max_over_ranks):
     opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=True)
     dp.attach_optimizer(opt)                 # bucket-wise Adam on a second stream, underneath the backward pass
     deg = NoiseDegradation(5e-3, 9e-3, T_MAX, device=dev)
-    step = GraphedTrainStep(net, deg, opt, kind="eps")
     n, s = args.train_batch, TRAIN_IMG
+    # eps is drawn inside the q-sample kernel and re-drawn inside the loss kernel (Philox keyed on the step count held in device
+    # memory and the global element index): no RNG launch, no eps tensor (north_star; reference train_diffusion.py:310)
+    step = GraphedTrainStep(net, deg, opt, kind="eps", philox_seed=4321, philox_first_elem=rank * n * 3 * s * s)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     x0_host = (torch.rand((n, 3, s, s)) * 2 - 1).pin_memory()
     lab_host = (torch.rand((n, TRAIN_COND)) > 0.7).float().pin_memory()
@@ -213,9 +401,8 @@ def run_train_leg(args, dev, world, rank, barrier, max_over_ranks):
         if h2d:                                   # e2e: this step's batch arrives from pinned host memory
             x0.copy_(x0_host, non_blocking=True)
             labels.copy_(lab_host, non_blocking=True)
-        eps = torch.randn(x0.shape, device=dev, generator=gen)
         t = torch.randint(1, T_MAX, (n,), device=dev, generator=gen)
-        return step(x0, t, eps, labels)
+        return step(x0, t, None, labels)
 
     for _ in range(3):
         loss = one(False)
@@ -256,7 +443,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-eager"])
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-on-B200 comparison (a subprocess after the timed legs)")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -266,6 +454,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "torch-eager":
+        return run_torch_eager_arm(args)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -378,9 +568,7 @@ def main():
     achieved_tf = flops_step / (kern_ms / 1000.0) / 1e12 if kern_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "igemm_nt_kernel / gemm_tn_kernel (tcgen05 implicit GEMM: conv3x3/convT/linear/softmax(QK^T)/PV)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the family's heaviest shape (conv3x3 N256 16x16
-                # C1024, 1237 GFLOP, algorithmic bytes 287e6) from profiles/r01d_ncu_conv_b256.md (ncu --set full)
-                "traffic": 253.9e6 if batch == BATCH else None, "traffic_unit": "bytes/launch (heaviest shape)",
+                **load_traffic(batch),
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": n_kern, "avg_launch_ms": kern_ms / max(n_kern, 1),
                 "kernel_share_of_step": kern_ms / ms_eager if ms_eager else None,
@@ -390,15 +578,26 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "tf32", "data": "synthetic",
-            "config": {"workload": f"DDIM-50 (51 evals, ddim_step_size=20, T=1000) cosine schedule, class-default U_Net "
-                                   f"(610.7M params, random init) {IMG}x{IMG} RGB, batch {batch}/GPU, sharded by image",
-                       "global_batch": world * batch, "cuda_graph": use_graph, "l2": "working set per evaluation (1.2 GB weights + >250 MB activations per layer) exceeds the 126 MB L2"},
+            "config": {"workload": WORKLOAD.format(batch=batch), "global_batch": world * batch, "l2": L2_NOTE},
+            "execution": {"cuda_graph": use_graph},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "finite_output": finite},
             "gpu_launches": launches, "roofline": roofline}
     if train is not None:
         line["train"] = train
+    if world == 1 and not args.no_eager:
+        # the bar that matters on this hardware: the unmodified reference through PyTorch eager (cuDNN / cuBLAS) on the same B200
+        eager = torch_eager_subprocess(args)
+        line["torch_eager_b200"] = eager
+        try:
+            best = max(v["img_per_s"] for v in eager["ddim50"].values() if isinstance(v, dict) and "img_per_s" in v)
+            line["torch_eager_b200"]["speedup_ddim50_vs_best_eager"] = value / best
+            if train is not None:
+                best_t = max(v["img_per_s"] for v in eager["train"].values() if isinstance(v, dict) and "img_per_s" in v)
+                line["torch_eager_b200"]["speedup_train_vs_best_eager"] = train["value"] / best_t
+        except (KeyError, ValueError, TypeError):
+            pass
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, dt, sample_desc = cpu_reference_sample(threads)

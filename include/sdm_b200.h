@@ -23,10 +23,16 @@ extern "C" {
 const char* b2_last_error(void);
 int b2_version(void);
 
-/* Optional split-K workspace for the tensor-core kernels: a device buffer (256-byte aligned, >= 1 MiB, first 4 KiB
- * ZEROED: per-tile arrival counters; 32 MiB covers every layer of the reference's configurations) owned by the caller.
- * Layers whose output tiles cannot fill the 148 SMs then split their K loop; counters are handed back zeroed.  One buffer serves one
- * stream at a time.  Passing NULL disables split-K. */
+/* Deterministic mode (also SDM_B200_DETERMINISTIC=1): GroupNorm statistics from a fixed-order pass instead of the conv
+ * epilogue's fp32 atomics and no split-K on the forward kernel, so an image's result is bitwise independent of batch size,
+ * sharding and timing (sharded sampling == unsharded sampling).  Weight-gradient split-K is ordered
+ * (bitwise repeatable) in every mode.  Returns 0. */
+int b2_set_deterministic(int on);
+/* Optional split-K workspace for the tensor-core kernels: a device buffer (256-byte aligned, >= 2 MiB, ZEROED: each half
+ * starts with 4 KiB of per-tile arrival counters) owned by the caller and registered for the CURRENT device (one per device).
+ * The first half serves the NT kernel (forward / data gradients), the second the TN kernel (ordered weight-gradient split-K),
+ * so the two may run on different streams; kernels sharing a half must be stream-ordered.  Layers whose output tiles cannot
+ * fill the 148 SMs then split their K loop; counters are handed back zeroed.  Passing NULL disables split-K on that device. */
 int b2_set_workspace(void* ws, long long bytes);
 
 /* ---- dense contractions (tcgen05 implicit GEMM) ------------------------------------------------------- */
@@ -181,6 +187,13 @@ int b2_philox_normal(float* out, long long n, unsigned long long seed, unsigned 
  * degraders.py:70-82,96-104 cosine closed form otherwise); steps int64, 1 or N entries. */
 int b2_qsample(const float* img, const float* eps, float* out, const long long* steps, int steps_count,
                const float* abar_table, int max_step, int N, long long per_image, void* stream);
+/* Same, with eps ~ N(0, I) drawn IN the kernel (the reference's `torch.randn_like`, train_diffusion.py:310 /
+ * degraders.py:53-54) from Philox keyed on (seed, offset, first_elem + element index); offset_dev != NULL overrides
+ * `offset` with (u64)*offset_dev (device-resident step counter: CUDA-graph replays draw fresh noise); eps_out optional.
+ * A timestep outside [0, max_step] yields NaN for that image in both variants (the reference's gather raises). */
+int b2_qsample_philox(const float* img, float* out, float* eps_out, const long long* steps, int steps_count,
+                      const float* abar_table, int max_step, int N, long long per_image, unsigned long long seed,
+                      unsigned long long offset, const float* offset_dev, long long first_elem, void* stream);
 /* diffusion_sampling_algorithms.py:107-136: x0 = c_scale*(x - c_s*e); x' = c_an*x0 + c_dir*e + sigma*noise. */
 int b2_ddim_step(const float* x_t, const float* eps_hat, const float* noise, float* x_out, float* x0_out, long long n,
                  float c_scale, float c_s, float c_an, float c_dir, float sigma, int last, void* stream);
@@ -197,6 +210,30 @@ int b2_area_resample(const float* x, float* y, long long planes, int H, int W, i
 /* loss = mean((pred-target)^2) (train_diffusion.py:350), grad (optional) = 2 (pred-target)/n * grad_scale. */
 int b2_mse_loss_grad(const float* pred, const float* target, float* grad, float* loss, long long n, float grad_scale,
                      void* stream);
+
+/* Same with target = the eps b2_qsample_philox drew for (seed, offset | *offset_dev, first_elem): re-generated in the kernel,
+ * never stored (eps-prediction target, train_diffusion.py:336-350). */
+int b2_mse_loss_grad_philox(const float* pred, float* grad, float* loss, long long n, float grad_scale,
+                            unsigned long long seed, unsigned long long offset, const float* offset_dev, long long first_elem,
+                            void* stream);
+
+/* ---- image input / output edges (uint8 <-> fp32, on the device) ---------------------------------------------- */
+
+/* uint8 [N][H][W][C] (cv2 BGR bytes) -> fp32 [N][C][H][W] = (x - 127.5) / 127.5, computed in double and rounded once like
+ * custom_dataset/img_dataset.py:26-35 and generate_sr_images_diffusion.py:117-126; flip_flags (optional, N bytes): nonzero =
+ * horizontal flip of that image (torchvision RandomHorizontalFlip per image, train_diffusion.py:312-314). */
+int b2_u8_to_image(const void* src_u8_nhwc, float* dst_nchw, const void* flip_flags, int N, int H, int W, int C, void* stream);
+/* Per-image horizontal flip of an fp32 [N][C][H][W] batch (train_diffusion.py:312-314). */
+int b2_flip_images(const float* x_nchw, float* out_nchw, const void* flip_flags, int N, int C, int H, int W, void* stream);
+/* fp32 [N][C][H][W] -> uint8 [N][H][W][C]: clamp to [lo, hi], (v - lo) / (hi - lo), *255 + 0.5, truncate -- the uint8-range
+ * image generate_sr_images_diffusion.py:106-126 takes as `lr_img` (cascade hand-off), produced without leaving the device. */
+int b2_image_to_u8(const float* x_nchw, void* out_u8_nhwc, int N, int C, int H, int W, float lo, float hi, void* stream);
+/* utils/utils.py:39-65 (plot_sampled_images): channel swap (swap_rb: BGR -> RGB), torchvision make_grid(nrow, padding,
+ * normalize=True, value_range=(lo, hi), pad_value=0) and save_image's *255 + 0.5 quantisation, as ONE pass writing the uint8
+ * [GH][GW][C] picture.  N == 1: GH = H, GW = W (make_grid returns a single image unframed); otherwise xmaps = min(nrow, N),
+ * GH = ceil(N / xmaps) * (H + padding) + padding, GW = xmaps * (W + padding) + padding. */
+int b2_image_grid_u8(const float* x_nchw, void* grid_u8_hwc, int N, int C, int H, int W, int nrow, int padding, int swap_rb,
+                     float lo, float hi, void* stream);
 
 /* ---- optimiser ------------------------------------------------------------------------------------------- */
 

@@ -17,6 +17,7 @@ _P, _I, _L, _F, _U, _D = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctyp
 # name -> argument ctypes, in the order of include/sdm_b200.h
 SIGNATURES = {
     "b2_set_workspace": [_P, _L],
+    "b2_set_deterministic": [_I],
     "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
     "b2_conv3x3_first": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_conv3x3_last": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -44,6 +45,8 @@ SIGNATURES = {
     "b2_small_gemm": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _P, _I, _I, _P],
     "b2_philox_normal": [_P, _L, _U, _U, _L, _P],
     "b2_qsample": [_P, _P, _P, _P, _I, _P, _I, _I, _L, _P],
+    "b2_qsample_philox": [_P, _P, _P, _P, _I, _P, _I, _I, _L, _U, _U, _P, _L, _P],
+    "b2_mse_loss_grad_philox": [_P, _P, _P, _L, _F, _U, _U, _P, _L, _P],
     "b2_ddim_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "b2_ddpm_step": [_P, _P, _P, _P, _L, _F, _F, _F, _I, _U, _U, _L, _P],
     "b2_cold_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P],
@@ -56,6 +59,10 @@ SIGNATURES = {
     "b2_transpose_linear_weight": [_P, _P, _I, _I, _P],
     "b2_pack_convt_bf16": [_P, _P, _P, _I, _I, _P],
     "b2_area_resample": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "b2_u8_to_image": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "b2_flip_images": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "b2_image_to_u8": [_P, _P, _I, _I, _I, _I, _F, _F, _P],
+    "b2_image_grid_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
     "b2_mse_loss_grad": [_P, _P, _P, _P, _L, _F, _P],
 }
 
@@ -93,7 +100,8 @@ def set_launch_hook(hook):
 
 
 _WORKSPACE = {}       # device index -> zeroed split-K workspace registered with the library (b2_set_workspace)
-WORKSPACE_BYTES = 32 << 20
+WORKSPACE_BYTES = 128 << 20
+_WORKSPACE_USERS = ("b2_conv2d_nhwc", "b2_gemm_nt", "b2_conv2d_wgrad", "b2_gemm_tn")
 
 
 def _ensure_workspace():
@@ -112,7 +120,7 @@ def _ensure_workspace():
 def call(name, *args):
     global LAUNCHES
     handle = lib()
-    if name in ("b2_conv2d_nhwc", "b2_gemm_nt") and not _WORKSPACE:
+    if name in _WORKSPACE_USERS and torch.cuda.current_device() not in _WORKSPACE:
         _ensure_workspace()
     LAUNCHES += 1
     if _HOOK is not None:

@@ -21,9 +21,36 @@ class _MSE(torch.autograd.Function):
         return grad * g, None
 
 
+class _MSEPhilox(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, noise):
+        loss, grad = mse_loss_philox(pred, noise)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
 def mse_loss(pred, target):
-    """F.mse_loss(pred, target) (mean reduction) on CUDA tensors: one kernel yields the loss and d(loss)/d(pred)."""
+    """F.mse_loss(pred, target) (mean reduction) on CUDA tensors: one kernel yields the loss and d(loss)/d(pred).
+    `target` may be a degraders.PhiloxNoise: the eps that `forward_philox` drew, re-generated inside the kernel."""
+    if not torch.is_tensor(target):
+        return _MSEPhilox.apply(pred, target)
     return _MSE.apply(pred, target)
+
+
+def mse_loss_philox(pred, noise):
+    """F.mse_loss(pred, eps) where eps is the in-kernel Philox draw of `degrader.forward_philox(..., noise)`: the target is
+    re-generated inside the loss kernel, never stored.  Returns (loss, d loss / d pred); no autograd node."""
+    p = pred.contiguous().float()
+    grad = torch.empty_like(p)
+    loss = torch.empty((), dtype=torch.float32, device=p.device)
+    call("b2_mse_loss_grad_philox", ptr(p), ptr(grad), ptr(loss), p.numel(), 1.0, noise.seed, noise.offset, ptr(noise.offset_dev),
+         noise.first_elem, stream())
+    return loss, grad
 
 
 def area_resize(x, size):

@@ -21,12 +21,15 @@ SUPPORTED_IMG_FORMATS = ["jpeg", "jpg", "png"]
 
 def _shard(t):
     """Under torchrun every rank draws the same full batch (same seed) and keeps its contiguous shard of the images: the
-    sampling loop needs no collective and the union of the shards equals the single-process result."""
+    sampling loop needs no collective and the union of the shards equals the single-process result (the per-step DDPM noise
+    is drawn for the whole job and sliced likewise, diffusion_sampling_algorithms.set_shard)."""
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if world <= 1 or t is None:
         return t
+    import diffusion_sampling_algorithms as S
     from .parallel import shard_range
     lo, hi = shard_range(t.shape[0], rank, world)
+    S.set_shard(lo, hi, t.shape[0])          # the samplers' per-step draws (DDPM z) follow the same sharding
     return t[lo:hi].contiguous()
 
 
@@ -40,9 +43,22 @@ def _image_kind(path):
     return None
 
 
+def _is_image(img):
+    return isinstance(img, np.ndarray) or (torch.is_tensor(img) and img.dtype == torch.uint8)
+
+
 def _to_tensor(img, device):
-    """uint8-range HWC BGR numpy image -> [-1, 1] CHW tensor (the cascade hand-off format, generate_sr:117-126)."""
-    return torch.from_numpy((img.astype(float) - 127.5) / 127.5).float().permute(2, 0, 1).to(device)
+    """uint8-range HWC BGR image -> [-1, 1] CHW tensor (the cascade hand-off format, generate_sr:117-126).  A numpy array (cv2)
+    takes the reference's host arithmetic; a CUDA uint8 tensor -- produced by `b200.image_io.image_to_u8` from the previous
+    stage's samples -- is normalised by one kernel on the device (device-side cascade: no host round trip, same values).
+    A leading batch dimension ([N, H, W, C]) is kept."""
+    if torch.is_tensor(img):
+        from .image_io import u8_to_image
+        t = img.to(device)
+        out = u8_to_image(t if t.dim() == 4 else t.unsqueeze(0))
+        return out if t.dim() == 4 else out[0]
+    t = torch.from_numpy((img.astype(float) - 127.5) / 127.5).float()
+    return (t.permute(0, 3, 1, 2) if t.dim() == 4 else t.permute(2, 0, 1)).to(device)
 
 
 def _common_args(description, step_flag, step_help):
@@ -152,9 +168,10 @@ def generate_images_diffusion(raw_args=None, log=print, cond_img=None, save_loca
         import cv2
         cond_img = cv2.imread(str(args["cond_img_path"]))
     if cond_img is not None:
-        if not isinstance(cond_img, np.ndarray):
+        if not _is_image(cond_img):
             raise ValueError("Unsupported conditional image.")
-        cond_img = _to_tensor(cond_img, device).unsqueeze(0).repeat(args["num_images"], 1, 1, 1)
+        cond_img = _to_tensor(cond_img, device)
+        cond_img = cond_img if cond_img.dim() == 4 else cond_img.unsqueeze(0).repeat(args["num_images"], 1, 1, 1)
     x_t, img_h, img_w = None, None, None
     for model_dict in models:
         if x_t is None:                                  # X_T ~ N(0, I) once; later ensemble members continue from x_t
@@ -196,7 +213,7 @@ def generate_images_cold_diffusion(raw_args=None, log=print, save_locally=True):
             noise = _shard(torch.randn((args["num_images"], model_dict["img_C"], img_h, img_w), device=device))
             x_t = 1 * noise
         else:                                            # ensemble hand-off: re-noise the estimate with the SAME noise
-            x_t = degrader(img=x0_approx, steps=torch.tensor([model_dict["max_noise"]], device=device), eps=noise)
+            x_t = degrader(img=x0_approx, steps=torch.tensor([model_dict["max_noise"]]), eps=noise)
         labels = _labels(model_dict, args, device)
         net = _load_net(model_dict, folder, device)
         x0_approx = S.cold_diffusion_sampling(diffusion_net=net, noise_degradation=degrader, x_t=x_t, noise=noise,
@@ -216,7 +233,7 @@ def generate_sr_images_diffusion(raw_args=None, lr_img=None, log=print, save_loc
     out_dir, models, folder = _setup(args)
     device = _device()
     if lr_img is not None:
-        if not isinstance(lr_img, np.ndarray):
+        if not _is_image(lr_img):
             raise ValueError("Invalid low resolution image passed!")
     else:
         path = args["lr_img_path"]
@@ -224,7 +241,8 @@ def generate_sr_images_diffusion(raw_args=None, lr_img=None, log=print, save_loc
             raise ValueError("Invalid/No path for low resolution image or unsupported image.")
         import cv2
         lr_img = cv2.imread(str(path))
-    lr = _to_tensor(lr_img, device).unsqueeze(0)
+    lr = _to_tensor(lr_img, device)
+    lr = lr if lr.dim() == 4 else lr.unsqueeze(0)
     noise, delta, upsampled, cond_in, img_h, img_w = None, None, None, None, None, None
     for model_dict in models:
         degrader = _degrader(model_dict, args, device)
@@ -235,9 +253,9 @@ def generate_sr_images_diffusion(raw_args=None, lr_img=None, log=print, save_loc
             noise = torch.randn((lr.shape[0], model_dict["img_C"], img_h, img_w), device=device)
             x_t = 1 * noise
             upsampled = area_resize(lr, (img_h, img_w))
-            cond_in = degrader(img=upsampled, steps=torch.tensor([model_dict["cond_t"]], device=device), eps=noise)
+            cond_in = degrader(img=upsampled, steps=torch.tensor([model_dict["cond_t"]]), eps=noise)
         else:
-            x_t = degrader(img=delta, steps=torch.tensor([model_dict["max_noise"]], device=device), eps=noise)
+            x_t = degrader(img=delta, steps=torch.tensor([model_dict["max_noise"]]), eps=noise)
         labels = _labels(model_dict, args, device)
         net = _load_net(model_dict, folder, device)
         delta = S.cold_diffusion_sampling(diffusion_net=net, noise_degradation=degrader, x_t=x_t, noise=noise,

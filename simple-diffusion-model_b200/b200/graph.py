@@ -18,12 +18,18 @@ class GraphedTrainStep:
     target = eps), "x0" (train_noise_cold_diffusion.py:330-340; target = x0) or "target" (train_SR_diffusion.py:366-372;
     explicit target tensor).  The optimiser must be a FusedAdam(capturable=True) over `net.parameters()`."""
 
-    def __init__(self, net, degrader, optimizer, kind="eps", warmup=2):
+    def __init__(self, net, degrader, optimizer, kind="eps", warmup=2, philox_seed=None, philox_first_elem=0, cond_t=None):
+        """philox_seed: draw eps INSIDE the q-sample kernel (and re-draw it inside the MSE kernel for kind "eps") instead of
+        taking an `eps` tensor: call the step with eps=None.  The draw number is the fused optimiser's device-side step count,
+        so every replay of the graph sees fresh noise without an RNG launch.  philox_first_elem: global index of this rank's
+        first image element (rank * N * C * H * W).  cond_t: kind "target" in Philox mode -- `cond_img` is then the CLEAN
+        low-resolution image, noised here at cond_t with the SAME eps (train_SR_diffusion.py:358-366)."""
         if kind not in ("eps", "x0", "target"):
             raise ValueError("kind must be 'eps', 'x0' or 'target'")
         if not getattr(optimizer, "capturable", False):
             raise B200Error("GraphedTrainStep needs FusedAdam(..., capturable=True)")
         self.net, self.degrader, self.opt, self.kind, self.warmup = net, degrader, optimizer, kind, warmup
+        self.philox_seed, self.philox_first_elem, self.cond_t = philox_seed, int(philox_first_elem), cond_t
         self.graph = None
         self.key = None
         self.replays = 0
@@ -32,20 +38,38 @@ class GraphedTrainStep:
     # the step body, written against the engine directly (no autograd graph is built)
     def _body(self):
         s = self.static
-        x_t = self.degrader(s["x0"], s["t"], s["eps"])
-        inp = torch.cat((x_t, s["cond_img"]), dim=1) if s["cond_img"] is not None else x_t
+        noise = None
+        cond_img = s["cond_img"]
+        if self.philox_seed is not None:
+            from degraders import PhiloxNoise
+            eng0 = self.net.engine()
+            lay = eng0.grad_layout(s["x0"].device)
+            dev_state = self.opt.device_state(lay, self.opt._flat_group(lay) or self.opt.param_groups[0])
+            noise = PhiloxNoise(self.philox_seed, 0, dev_state[0:1], self.philox_first_elem)
+            x_t = self.degrader.forward_philox(s["x0"], s["t"], noise)
+            if self.cond_t is not None and cond_img is not None:
+                cond_img = self.degrader.forward_philox(cond_img, s["cond_t"], noise)
+        else:
+            x_t = self.degrader(s["x0"], s["t"], s["eps"])
+        inp = torch.cat((x_t, cond_img), dim=1) if cond_img is not None else x_t
         eng = self.net.engine()
         with torch.no_grad():
             pred, tape = eng._forward_tape(inp, s["t"], s["labels"])
-            target = {"eps": s["eps"], "x0": s["x0"], "target": s["target"]}[self.kind]
-            call("b2_mse_loss_grad", ptr(pred), ptr(target), ptr(s["dpred"]), ptr(s["loss"]), pred.numel(), 1.0, stream())
+            if noise is not None and self.kind == "eps":
+                call("b2_mse_loss_grad_philox", ptr(pred), ptr(s["dpred"]), ptr(s["loss"]), pred.numel(), 1.0, noise.seed,
+                     noise.offset, ptr(noise.offset_dev), noise.first_elem, stream())
+            else:
+                target = {"eps": s["eps"], "x0": s["x0"], "target": s["target"]}[self.kind]
+                call("b2_mse_loss_grad", ptr(pred), ptr(target), ptr(s["dpred"]), ptr(s["loss"]), pred.numel(), 1.0, stream())
             eng._backward_tape(tape, s["dpred"])
             self.opt.step()
 
     def _capture(self, x0, t, eps, labels, cond_img, target):
         dev = x0.device
         clone = lambda v: None if v is None else v.detach().clone().contiguous()
-        self.static = {"x0": clone(x0.float()), "t": clone(t.to(torch.int64)), "eps": clone(eps.float()), "labels": clone(labels),
+        self.static = {"x0": clone(x0.float()), "t": clone(t.to(torch.int64)), "eps": clone(eps.float()) if eps is not None else None,
+                       "cond_t": torch.tensor([int(self.cond_t)], dtype=torch.int64, device=dev) if self.cond_t is not None else None,
+                       "labels": clone(labels),
                        "cond_img": clone(cond_img), "target": clone(target), "loss": torch.zeros((), dtype=torch.float32, device=dev)}
         n, _, h, w = x0.shape
         out_ch = self.net.out_layers[1].conv_layer[0].weight.shape[0]
@@ -97,9 +121,11 @@ class GraphedTrainStep:
             lay.stepped(True)
         del saved
 
-    def __call__(self, x0, t, eps, labels=None, cond_img=None, target=None):
+    def __call__(self, x0, t, eps=None, labels=None, cond_img=None, target=None):
         if not x0.is_cuda:
             raise B200Error("training needs CUDA tensors: this build has no CPU path")
+        if (eps is None) != (self.philox_seed is not None):
+            raise B200Error("GraphedTrainStep: pass eps=None exactly when the step was built with philox_seed")
         key = (tuple(x0.shape), tuple(t.shape), None if labels is None else tuple(labels.shape),
                None if cond_img is None else tuple(cond_img.shape), None if target is None else tuple(target.shape),
                self.net.precision)
@@ -109,7 +135,8 @@ class GraphedTrainStep:
         elif key != self.key:
             # a differently shaped batch (the short last batch of an epoch): run the same kernel sequence eagerly
             captured, self.static = self.static, {
-                "x0": x0.contiguous().float(), "t": t.to(torch.int64), "eps": eps.contiguous().float(), "labels": labels,
+                "x0": x0.contiguous().float(), "t": t.to(torch.int64), "eps": eps.contiguous().float() if eps is not None else None,
+                "cond_t": captured.get("cond_t"), "labels": labels,
                 "cond_img": cond_img, "target": target, "loss": torch.zeros((), dtype=torch.float32, device=x0.device),
                 "dpred": torch.empty((x0.shape[0], captured["dpred"].shape[1]) + tuple(x0.shape[2:]), dtype=torch.float32,
                                      device=x0.device)}
@@ -122,7 +149,8 @@ class GraphedTrainStep:
         s = self.static
         s["x0"].copy_(x0, non_blocking=True)
         s["t"].copy_(t, non_blocking=True)
-        s["eps"].copy_(eps, non_blocking=True)
+        if eps is not None:
+            s["eps"].copy_(eps, non_blocking=True)
         for name, v in (("labels", labels), ("cond_img", cond_img), ("target", target)):
             if v is not None:
                 s[name].copy_(v, non_blocking=True)

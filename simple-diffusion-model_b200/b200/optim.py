@@ -11,7 +11,10 @@ from ._lib import call, ptr, stream
 
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, capturable=False):
-        defaults = dict(lr=lr, betas=betas, eps=eps)
+        # the extra keys are torch.optim.Adam's remaining per-group options at their defaults, so that a state_dict written
+        # here loads into the reference's torch.optim.Adam (train_diffusion.py:214-227) and vice versa
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
         super().__init__(params, defaults)
         self.grad_scale = grad_scale          # e.g. 1 / world_size when gradients were sum-all-reduced
         self._flat = {}                       # id(layout) -> (m_flat, v_flat)
@@ -21,6 +24,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.bf16_shadow = True               # emit the bf16 copy of the weights the tensor-core kernels read (flat layouts)
         self._dev_state = {}                  # id(layout) -> device float[8]
         self._dev_lr = {}
+        self._adopted = set()                 # id(param) whose state moments are views of the flat buffers
 
     def device_state(self, lay, group, steps=0.0):
         st = self._dev_state.get(id(lay))
@@ -48,6 +52,55 @@ class FusedAdam(torch.optim.Optimizer):
                 if st and "step" in st:
                     st["step"] += 1
 
+    def _moments(self, lay):
+        if id(lay) not in self._flat:
+            self._flat[id(lay)] = (torch.zeros_like(lay.flat), torch.zeros_like(lay.flat))
+        return self._flat[id(lay)]
+
+    def _adopt_state(self, lay, p, st):
+        """Makes state[p]'s moments views of the flat moment buffers the kernels update.  Fresh state starts at zero; moments
+        that arrived as standalone tensors (load_state_dict of a reference / earlier checkpoint) are copied in first."""
+        if id(p) in self._adopted and st:
+            return
+        self._adopted.add(id(p))
+        m_flat, v_flat = self._moments(lay)
+        m_view, v_view = lay._shaped(m_flat, p), lay._shaped(v_flat, p)
+        if not st:
+            st["step"] = torch.tensor(0.0)
+        for key, view in (("exp_avg", m_view), ("exp_avg_sq", v_view)):
+            have = st.get(key)
+            if have is not None and have.data_ptr() != view.data_ptr():
+                view.copy_(have.to(view.device, torch.float32))
+            st[key] = view
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """torch's loader installs standalone `exp_avg` / `exp_avg_sq` tensors; the kernels only see the flat buffers, so
+        the loaded moments are copied into them (and the device-side step count / learning rate re-seeded).  Resuming
+        with `load_diffusion_optim` (train_diffusion.py:219-227) therefore continues the reference's Adam trajectory."""
+        super().load_state_dict(state_dict)
+        self._adopted.clear()
+        for group in self.param_groups:
+            group["capturable"] = False          # a foreign checkpoint must not move `step` handling to torch's capturable path
+            seen = {}
+            for p in group["params"]:
+                lay = getattr(p, "_b2_layout", None)
+                st = self.state.get(p)
+                if lay is None or not st or lay.params_flat is None or id(p) not in lay.offsets:
+                    continue
+                if not torch.is_tensor(st.get("step")):
+                    st["step"] = torch.tensor(float(st.get("step", 0.0)))
+                st["step"] = st["step"].detach().to("cpu", torch.float32).reshape(())
+                self._adopt_state(lay, p, st)
+                seen[id(lay)] = (lay, float(st["step"]))
+            for lay, steps in seen.values():
+                if self.capturable:
+                    dev = self.device_state(lay, group, steps)
+                    dev[0:1].fill_(steps)
+                    dev[1:2].fill_(group["lr"])
+                    dev[2:3].fill_(self.grad_scale)
+                    self._dev_lr[id(lay)] = group["lr"]
+
     @staticmethod
     def _launch(p, g, m, v, n, group, step, grad_scale, shadow=None):
         b1, b2 = group["betas"]
@@ -71,8 +124,7 @@ class FusedAdam(torch.optim.Optimizer):
         group = self._flat_group(lay)
         if group is None or lay.params_flat is None:
             return False
-        if id(lay) not in self._flat:
-            self._flat[id(lay)] = (torch.zeros_like(lay.flat), torch.zeros_like(lay.flat))
+        self._moments(lay)
         any_state = next((self.state[p] for p in group["params"] if self.state.get(p)), None)
         steps_so_far = float(any_state["step"]) if any_state else 0.0
         b1, b2 = group["betas"]
@@ -116,11 +168,7 @@ class FusedAdam(torch.optim.Optimizer):
             if getattr(p, "_b2_layout", None) is not lay or id(p) not in lay.offsets:
                 continue
             st = self.state[p]
-            if not st:
-                off = lay.offsets[id(p)]
-                st["step"] = torch.tensor(0.0)
-                st["exp_avg"] = lay._shaped(m_flat, p)
-                st["exp_avg_sq"] = lay._shaped(v_flat, p)
+            self._adopt_state(lay, p, st)
             st["step"] += 1
         lay.stepped(part["shadow"] is not None)
         self._partial = None
@@ -141,14 +189,13 @@ class FusedAdam(torch.optim.Optimizer):
                     and p.data_ptr() == lay.param_view(p).data_ptr()
                 st = self.state[p]
                 if flat_ok:
-                    if id(lay) not in self._flat:
-                        self._flat[id(lay)] = (torch.zeros_like(lay.flat), torch.zeros_like(lay.flat))
-                    m_flat, v_flat = self._flat[id(lay)]
-                    if not st:
-                        off = lay.offsets[id(p)]
-                        st["step"] = torch.tensor(0.0)
-                        st["exp_avg"] = lay._shaped(m_flat, p)          # same (possibly channels-last) view as the parameter
-                        st["exp_avg_sq"] = lay._shaped(v_flat, p)
+                    m_flat, v_flat = self._moments(lay)
+                    if id(lay) not in done_layouts:
+                        # every parameter of the layout is adopted BEFORE the single flat launch below (same, possibly
+                        # channels-last, view as the parameter; standalone moments loaded from a checkpoint are copied in)
+                        for q in group["params"]:
+                            if getattr(q, "_b2_layout", None) is lay and id(q) in lay.offsets and q.grad is not None:
+                                self._adopt_state(lay, q, self.state[q])
                     if self.capturable:
                         self.device_state(lay, group, float(st["step"]))      # created once, from the pre-step count
                     st["step"] += 1

@@ -47,31 +47,38 @@ def _parse(raw_args, description):
     return vars(parser.parse_args(raw_args))
 
 
-def _dataset(flavour, cfg):
+def _dataset(flavour, cfg, shuffle_seed=None, raw_uint8=False):
+    """`shuffle_seed`: under torchrun every rank must map DistributedSampler's indices onto the SAME row order, so the one-off
+    table shuffle of the labelled datasets is seeded (the reference is single-process and shuffles unseeded)."""
     path = cfg["dataset_path"]
     if path is None:
         raise ValueError("No dataset_path entered.")
     if isinstance(path, str) and path.startswith("synthetic:"):
         from custom_dataset.img_dataset import SyntheticImages
-        return SyntheticImages(path)
+        return SyntheticImages(path, raw_uint8=raw_uint8)
     if flavour == "doodle":
         from custom_dataset.doodle_dataset import DoodleImgDataset
-        return DoodleImgDataset(dataset_path=path)
+        return DoodleImgDataset(dataset_path=path, shuffle_seed=shuffle_seed, raw_uint8=raw_uint8)
     if cfg.get("use_conditional"):
         from custom_dataset.conditional_img_dataset import ConditionalImgDataset
-        return ConditionalImgDataset(dataset_path=path)
+        return ConditionalImgDataset(dataset_path=path, shuffle_seed=shuffle_seed, raw_uint8=raw_uint8)
     from custom_dataset.img_dataset import ImageDataset
     img_list = glob.glob(path)
     if len(img_list) <= 0:
         raise Exception("No dataset found!")
-    return ImageDataset(img_paths=img_list)
+    return ImageDataset(img_paths=img_list, raw_uint8=raw_uint8)
+
+
+def rank_seed(base_seed, rank):
+    """Seed of torch's CPU and CUDA generators on `rank` (torch.manual_seed seeds both)."""
+    return int(base_seed) + int(rank)
 
 
 def _flip_per_image(x):
     """torchvision RandomHorizontalFlip(p=0.5) applied image by image, as the reference does
-    (train_diffusion.py:312-314): one CPU-generator draw per image, flip on the device."""
-    flips = torch.tensor([bool(torch.rand(1) < 0.5) for _ in range(x.shape[0])], device=x.device)
-    return torch.where(flips[:, None, None, None], x.flip(-1), x)
+    (train_diffusion.py:312-314): one CPU-generator draw per image, flipped by one kernel on the device."""
+    from .image_io import draw_flip_flags, flip_images
+    return flip_images(x, draw_flip_flags(x.shape[0]))
 
 
 def run_training(flavour, raw_args=None):
@@ -125,6 +132,15 @@ def run_training(flavour, raw_args=None):
     device = torch.device("cuda", local)
     if world > 1 and not torch.distributed.is_initialized():
         torch.distributed.init_process_group("nccl", device_id=device)
+    # Random streams.  Single process: untouched, like the reference (seed it from outside for reproducibility).  Data
+    # parallel: every rank needs its OWN stream for eps / t / flips -- otherwise the global batch repeats one (t, eps) draw
+    # world-size times -- and the SAME dataset row order (rank_seed / shuffle_seed below); "seed" in the JSON is an addition.
+    base_seed = cfg.get("seed")
+    shuffle_seed = None
+    if world > 1 or base_seed is not None:
+        base_seed = int(base_seed if base_seed is not None else 0)
+        torch.manual_seed(rank_seed(base_seed, rank))
+        shuffle_seed = base_seed
 
     log = logging.getLogger(f"b200.{flavour}.{rank}")
     log.setLevel(logging.DEBUG)
@@ -138,12 +154,25 @@ def run_training(flavour, raw_args=None):
     else:
         log.addHandler(logging.NullHandler())
 
-    dataset = _dataset(flavour, cfg)
+    # "gpu_input_pipeline" (addition, default on): the dataset hands out the decoded uint8 HWC bytes; normalisation to [-1, 1],
+    # HWC -> CHW and the random flips are one kernel on the device, fed by a pinned double-buffered prefetcher
+    # (b200/image_io.py) -- bit-identical to the reference's host-side numpy arithmetic
+    raw_input = bool(cfg.get("gpu_input_pipeline", True))
+    dataset = _dataset(flavour, cfg, shuffle_seed, raw_uint8=raw_input)
     batch_size = cfg["batch_size"]
     sampler = torch.utils.data.distributed.DistributedSampler(dataset, world, rank, shuffle=True) if world > 1 else None
     loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, num_workers=cfg.get("num_workers", 4),
                                          shuffle=sampler is None, sampler=sampler, pin_memory=True, drop_last=world > 1)
     plot_batch = next(iter(torch.utils.data.DataLoader(dataset, batch_size=max(plot_img_count, 1), num_workers=0, shuffle=False)))
+    if raw_input:
+        from .image_io import DeviceImageLoader, draw_flip_flags, u8_to_image
+        as_float = lambda t: u8_to_image(t.to(device)) if torch.is_tensor(t) and t.dtype == torch.uint8 else t
+        plot_batch = [as_float(t) for t in plot_batch] if isinstance(plot_batch, (list, tuple)) else as_float(plot_batch)
+        # the flips ride in the conversion kernel; their per-image CPU draws happen when the batch is handed out, in order
+        flips_here = flip_imgs and flavour != "doodle"
+        batches = DeviceImageLoader(loader, device, flip_fn=draw_flip_flags if flips_here else None)
+    else:
+        batches, flips_here = loader, False
     plot_labels, plot_cond = None, None
     if flavour == "doodle":
         plot_imgs, plot_cond = plot_batch
@@ -167,9 +196,13 @@ def run_training(flavour, raw_args=None):
         net.custom_load_state_dict(ckpt["model"])
     net = net.to(device).set_precision(cfg.get("precision", "bf16"))
     dp = DataParallel(net, device=device)            # flattens the parameters; a no-op collective-wise when world == 1
-    use_graph = os.environ.get("SDM_B200_CUDA_GRAPH", "1") != "0"
+    # "grad_scaler": true (addition) runs the reference's GradScaler protocol (train_diffusion.py:130, 358-364) around the
+    # eager step; it is numerically a no-op in bf16 and costs the CUDA-graph replay, hence off by default
+    scaler = torch.amp.GradScaler("cuda") if cfg.get("grad_scaler") else None
+    use_graph = os.environ.get("SDM_B200_CUDA_GRAPH", "1") != "0" and scaler is None
     optim = FusedAdam(net.parameters(), lr=cfg["diffusion_lr"], betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=use_graph)
-    dp.attach_optimizer(optim)
+    if scaler is None:
+        dp.attach_optimizer(optim)
     if ckpt is not None and cfg.get("load_diffusion_optim"):
         optim.load_state_dict(ckpt["optimizer"])
     if cfg.get("config_checkpoint") is not None:
@@ -181,7 +214,13 @@ def run_training(flavour, raw_args=None):
         starting_epoch, global_steps = cc["starting_epoch"], cc["global_steps"]
 
     degrader = NoiseDegradation(beta_1, beta_T, max_t, device) if scheduling == NoiseScheduler.LINEAR else CosineNoiseDegradation(max_t)
-    graphed = GraphedTrainStep(net, degrader, optim, kind=spec["kind"]) if use_graph else None
+    graphed = None                      # built at the first batch (the Philox stream needs the per-rank element count)
+    # "philox_noise": <seed> (addition): eps is drawn inside the q-sample kernel -- and re-drawn inside the loss kernel for the
+    # eps-prediction flavours -- from Philox keyed on (seed, optimisation step, global element index) instead of by a separate
+    # torch.randn_like launch.  Off by default: the default keeps the reference's RNG stream.
+    philox_seed = cfg.get("philox_noise")
+    if philox_seed is True:
+        philox_seed = int(cfg.get("seed") or 0)
 
     log.info("#" * 100)
     log.info("Train Parameters:")
@@ -232,7 +271,7 @@ def run_training(flavour, raw_args=None):
         imgs = plot_imgs.to(device)
         if spec["sampler"] == "ddpm_ddim":
             if max_actual_t < max_t:
-                x_t = degrader(img=imgs, steps=torch.tensor([max_actual_t], device=device), eps=torch.randn((imgs.shape[0], c, h, w), device=device))
+                x_t = degrader(img=imgs, steps=torch.tensor([max_actual_t]), eps=torch.randn((imgs.shape[0], c, h, w), device=device))
             else:
                 x_t = torch.randn((plot_img_count, c, h, w), device=device)
             if diffusion_alg == DiffusionAlg.DDPM:
@@ -246,9 +285,9 @@ def run_training(flavour, raw_args=None):
             cond_in, base = None, 0.0
             if flavour == "sr":
                 base = lr_condition(imgs)
-                cond_in = degrader(img=base, steps=torch.tensor([cond_t], device=device), eps=noise)
+                cond_in = degrader(img=base, steps=torch.tensor([cond_t]), eps=noise)
             if max_actual_t < max_t and flavour != "sr":      # the SR trainer always starts from pure noise (train_SR:441)
-                x_t = degrader(img=imgs, steps=torch.tensor([max_actual_t], device=device), eps=noise)
+                x_t = degrader(img=imgs, steps=torch.tensor([max_actual_t]), eps=noise)
             else:
                 x_t = 1 * noise
             out = samplers.cold_diffusion_sampling(net, degrader, x_t, noise, min_noise=min_t, max_noise=max_actual_t,
@@ -263,7 +302,7 @@ def run_training(flavour, raw_args=None):
         if sampler is not None:
             sampler.set_epoch(epoch)
         total_loss, count = 0.0, 0
-        for index, data in enumerate(loader):
+        for index, data in enumerate(batches):
             count += 1
             labels, cond_img, target = None, None, None
             if flavour == "doodle":
@@ -274,22 +313,38 @@ def run_training(flavour, raw_args=None):
                 x0 = (data[0] if isinstance(data, (list, tuple)) else data).to(device, non_blocking=True)
             n, c, h, w = x0.shape
             # order of the random draws: the base/doodle trainers draw eps before the flips, cold/SR after
+            draw = (lambda like: None) if philox_seed is not None else torch.randn_like
             if flavour in ("base", "doodle"):
-                eps = torch.randn_like(x0)
-                if flip_imgs and flavour == "base":
+                eps = draw(x0)
+                if flip_imgs and flavour == "base" and not flips_here:
                     x0 = _flip_per_image(x0)
             else:
-                if flip_imgs:
+                if flip_imgs and not flips_here:
                     x0 = _flip_per_image(x0)
-                eps = torch.randn_like(x0)
+                eps = draw(x0)
+            first_elem = rank * batch_size * c * h * w        # this rank's slice of the global Philox stream
+            if philox_seed is not None and not use_graph:
+                from degraders import PhiloxNoise
+                eps = PhiloxNoise(philox_seed, global_steps, None, first_elem)
             if flavour == "sr":
                 lr = lr_condition(x0)
                 target = x0 - lr
-                cond_img = degrader(img=lr, steps=torch.tensor([cond_t], device=device), eps=eps)
+                if philox_seed is not None and use_graph:
+                    cond_img = lr                              # noised at cond_t inside the captured step, with the same eps
+                elif philox_seed is not None:
+                    cond_img = degrader.forward_philox(lr, torch.tensor([cond_t]), eps)
+                else:
+                    cond_img = degrader(img=lr, steps=torch.tensor([cond_t]), eps=eps)
             t = torch.randint(low=min_t, high=max_actual_t, size=(n,), device=device)
             net.train()
+            if use_graph and graphed is None:
+                graphed = GraphedTrainStep(net, degrader, optim, kind=spec["kind"], philox_seed=philox_seed,
+                                           philox_first_elem=first_elem, cond_t=cond_t if flavour == "sr" else None)
             if graphed is not None:
                 loss = graphed(x0, t, eps, labels, cond_img, target)
+            elif scaler is not None:
+                from .steps import scaled_step
+                loss = scaled_step(net, degrader, optim, scaler, x0, t, eps, labels, cond_img, target, kind=spec["kind"])
             else:
                 from .steps import eps_prediction_step, x0_prediction_step
                 if spec["kind"] == "eps":

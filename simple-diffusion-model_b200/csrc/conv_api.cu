@@ -10,22 +10,41 @@
 namespace b2 {
 int launch_igemm_nt(int dtype, const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& p, int block_n, cudaStream_t st);
 int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, int C, int groups, int pre_swish, int dtype,
-                    cudaStream_t st);
+                    cudaStream_t st, bool deterministic);
 }
 using namespace b2;
 
 // ---- tiling: N tile width and split-K factor -------------------------------------------------------------------
 // Workspace for split-K partial sums, registered once by the host side (b2_set_workspace): [1024 int counters | fp32].
-static float* g_ws = nullptr;
-static int* g_ws_counters = nullptr;
-static long long g_ws_floats = 0;
+// One workspace PER DEVICE (keyed by the current device of the calling thread), each split in two halves so that the NT
+// kernel (forward / data gradients, main stream) and the TN kernel (weight gradients, possibly on the side stream of
+// SDM_B200_OVERLAP_WGRAD) never share partial-sum slices or counters.  Kernels that use one half are still ordered among
+// themselves by their stream.
+struct Workspace { int* counters; float* ws; long long floats; };
+static constexpr int kMaxDevices = 64;
+static Workspace g_wtab[kMaxDevices][2];
+
+static const Workspace& workspace(int half) {
+    static const Workspace none = {nullptr, nullptr, 0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
+    return g_wtab[dev][half];
+}
+
+extern "C" int b2_set_deterministic(int on) { set_deterministic_mode(on); return 0; }
 
 extern "C" int b2_set_workspace(void* ws, long long bytes) {
-    if (!ws || bytes < (1 << 20)) { g_ws = nullptr; g_ws_counters = nullptr; g_ws_floats = 0; return 0; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return set_error("b2_set_workspace: no current device");
+    if (!ws || bytes < (2 << 20)) { g_wtab[dev][0] = g_wtab[dev][1] = Workspace{nullptr, nullptr, 0}; return 0; }
     if ((uintptr_t)ws % 256) return set_error("b2_set_workspace: pointer must be 256-byte aligned");
-    g_ws_counters = reinterpret_cast<int*>(ws);
-    g_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 4096);
-    g_ws_floats = (bytes - 4096) / 4;
+    const long long half = (bytes / 2) & ~255LL;
+    for (int h = 0; h < 2; ++h) {
+        char* base = reinterpret_cast<char*>(ws) + h * half;
+        g_wtab[dev][h].counters = reinterpret_cast<int*>(base);                      // [1024] int, zero on entry, self-resetting
+        g_wtab[dev][h].ws = reinterpret_cast<float*>(base + 4096);
+        g_wtab[dev][h].floats = (half - 4096) / 4;
+    }
     return 0;
 }
 
@@ -39,6 +58,9 @@ extern "C" int b2_set_workspace(void* ws, long long bytes) {
 // so splitting only pays with narrow tiles.
 static void pick_tiling(int cout, long long m_tiles, int groups, int k_iters, bool allow_split, int* bn_out, int* splits_out) {
     const int sms = device_sm_count();
+    const Workspace& wsp = workspace(0);
+    float* const g_ws = wsp.ws;
+    const long long g_ws_floats = wsp.floats;
     const int cands[3] = {256, 128, 64};
     const double t_light[3] = {0.33, 0.30, 0.18}, t_full[3] = {0.41, 0.33, 0.27}, slice_us[3] = {9.0, 1.5, 0.6};
     const int split_cands[8] = {1, 2, 3, 4, 6, 8, 12, 16};
@@ -131,7 +153,8 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
     p.cpg = gn_groups > 0 ? Cout / gn_groups : 0;
     // the epilogue fuses the statistics for power-of-two group widths >= 4 (every width of the reference's configs with
     // C >= 128); narrower nets get them from a separate streaming pass over the conv output
-    const bool separate_stats = gn_stats && (p.cpg < 4 || (p.cpg & (p.cpg - 1)) != 0);
+    const bool det = deterministic_mode();      // no fp atomics: statistics from the fixed-order pass (host_util.h)
+    const bool separate_stats = gn_stats && (det || p.cpg < 4 || (p.cpg & (p.cpg - 1)) != 0);
     if (separate_stats) {
         if (out_mode != 0 || mode != 0) return set_error("b2_conv2d_nhwc: unfused GroupNorm statistics only for the plain 3x3 conv");
         p.gn_stats = nullptr;
@@ -205,10 +228,10 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
     }
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     int bn, splits;
-    pick_tiling(Cout, m_tiles, p.groups, p.taps * p.kb_per_tap, true, &bn, &splits);
+    pick_tiling(Cout, m_tiles, p.groups, p.taps * p.kb_per_tap, !det, &bn, &splits);
     p.n_tiles = (Cout + bn - 1) / bn;
     p.b_mode = 0;
-    p.splits = splits; p.ws = g_ws; p.ws_counters = g_ws_counters;
+    p.splits = splits; p.ws = workspace(0).ws; p.ws_counters = workspace(0).counters;
     p.cluster = pick_cluster(dtype, bn, splits, m_tiles * p.groups * p.n_tiles, m_tiles);
 
     CUtensorMap ta, tb;
@@ -226,7 +249,7 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         if (make_tmap_4d(&tb, wpacked, eb, dims, str, box)) return 1;
     }
     if (launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;
-    if (separate_stats) return launch_gn_stats(y, ldy, gn_stats, N, H * W, Cout, gn_groups, act == 3 ? 1 : 0, dtype, (cudaStream_t)stream);
+    if (separate_stats) return launch_gn_stats(y, ldy, gn_stats, N, H * W, Cout, gn_groups, act == 3 ? 1 : 0, dtype, (cudaStream_t)stream, det);
     return 0;
 }
 
@@ -259,9 +282,9 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
     const bool batched = (batch1 > 1 || batch2 > 1);
     p.b_mode = batched ? 1 : 0;
     int bn, splits;
-    pick_tiling(Ncols, (long long)p.tiles_w * batch1 * batch2, 1, p.kb_per_tap, !batched, &bn, &splits);
+    pick_tiling(Ncols, (long long)p.tiles_w * batch1 * batch2, 1, p.kb_per_tap, !batched && !deterministic_mode(), &bn, &splits);
     p.n_tiles = (Ncols + bn - 1) / bn;
-    p.splits = splits; p.ws = g_ws; p.ws_counters = g_ws_counters;
+    p.splits = splits; p.ws = workspace(0).ws; p.ws_counters = workspace(0).counters;
     p.cluster = batched ? 1 : pick_cluster(dtype, bn, splits, (long long)p.tiles_w * p.n_tiles, p.tiles_w);
     CUtensorMap ta, tb;
     {
@@ -405,7 +428,7 @@ static int tn_block_n(int ncols, int dtype) {
 // Split-K factor of the TN kernel: work items = tiles x splits run in waves of (#SMs) persistent CTAs; a split costs
 // an fp32 atomic pass over the tile instead of plain stores.  Pick the factor with the least (waves x K boxes per item),
 // charging each extra split a few K boxes for the atomics, and prefer no split when the tiles alone fill the machine.
-static void tn_pick_splits(GemmTnParams* p, int batches) {
+static void tn_pick_splits(GemmTnParams* p, int batches, int bn) {
     const int sms = device_sm_count();
     const long long base = (long long)p->m_tiles * p->n_tiles * p->taps * batches;
     const int k_boxes = p->kt_w * p->kt_h * p->kt_n;
@@ -422,6 +445,19 @@ static void tn_pick_splits(GemmTnParams* p, int batches) {
         }
     }
     p->splits = best_s;
+    // ordered (bitwise repeatable) split-K through the TN half of the workspace, unless SDM_B200_TN_SPLITK=atomic
+    p->ws = nullptr; p->ws_counters = nullptr;
+    static int atomic_mode = -1;
+    if (atomic_mode < 0) { const char* e = getenv("SDM_B200_TN_SPLITK"); atomic_mode = (e && !strcmp(e, "atomic")) ? 1 : 0; }
+    if (p->out_mode == 0 && best_s > 1 && !atomic_mode) {
+        const Workspace& w = workspace(1);
+        if (w.ws && base <= 1024) {
+            int s = best_s;
+            while (s > 1 && base * s * 128LL * bn > w.floats) --s;       // fit the partial tiles, trading splits for capacity
+            p->splits = s;
+            if (s > 1) { p->ws = w.ws; p->ws_counters = w.counters; }
+        }
+    }
 }
 
 // Weight gradient of the three convolution flavours, accumulated (fp32 atomics) into a zero-initialised buffer in
@@ -463,7 +499,7 @@ extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int
     } else {
         p.taps = 4; p.ldc = 4LL * Cin;
     }
-    tn_pick_splits(&p, 1);
+    tn_pick_splits(&p, 1, bn);
     {   // CTA pairs sharing the activation slabs: measured neutral on B200 (weight-gradient layers at batch 32: 5.4 ms either way),
         // so off unless SDM_B200_TN_CLUSTER=2; needs an even number of M tiles and enough items
         static int tn_cl = -1;
@@ -525,7 +561,7 @@ extern "C" int b2_gemm_tn(const void* A, long long lda, long long a_s1, long lon
     p.taps = 1;
     p.out = C; p.ldc = ldc; p.tap_stride = 0; p.c_s1 = c_s1; p.c_s2 = c_s2;
     p.out_mode = out_mode; p.alpha = alpha;
-    tn_pick_splits(&p, batch1 * batch2);
+    tn_pick_splits(&p, batch1 * batch2, bn);
     const int slab = 128 / eb;
     CUtensorMap ta, tb;
     {

@@ -78,37 +78,75 @@ __device__ __forceinline__ float cosine_abar(float t, float T) {
     const float b = cosf(((0.0f / T + 0.008f) / 1.008f) * half_pi);
     return (a * a) / (b * b);
 }
+// Linear table: a timestep outside [0, max_step] poisons its image with NaN (the reference's torch.gather raises on it; here the trainer's
+// NaN check / the caller's isfinite test trips instead of an out-of-bounds table read going unnoticed).
+__device__ __forceinline__ float abar_of(long long t, const float* __restrict__ abar_table, int max_step) {
+    if (!abar_table) return cosine_abar((float)t, (float)max_step);          // closed form: defined for every t, like the reference
+    if (t < 0 || t > (long long)max_step) return __int_as_float(0x7fc00000);
+    return abar_table[t];
+}
+// kPhilox: eps is not read but drawn in-kernel (Philox4x32-10 keyed on the GLOBAL element index, so data-parallel ranks and
+// batch shards draw disjoint slices of one stream); `offset` selects the draw (the optimisation step), and when offset_dev
+// is given the value is read from device memory instead -- the captured train step keeps its Adam step count there, so a
+// replayed CUDA graph draws fresh noise every step without a separate RNG launch.  eps_out (optional) receives the draw.
+template <bool kPhilox>
 __global__ void qsample_kernel(const float* __restrict__ img, const float* __restrict__ eps, float* __restrict__ out,
-                               const long long* __restrict__ steps, int steps_count, const float* __restrict__ abar_table,
-                               int max_step, long long per_image, int vec_per_image_blocks) {
+                               float* __restrict__ eps_out, const long long* __restrict__ steps, int steps_count,
+                               const float* __restrict__ abar_table, int max_step, long long per_image, int vec_per_image_blocks,
+                               unsigned long long seed, unsigned long long offset, const float* __restrict__ offset_dev,
+                               long long first_elem) {
     pdl_launch_dependents();
     pdl_wait();
     const int n = blockIdx.x / vec_per_image_blocks, blk = blockIdx.x % vec_per_image_blocks;
     const long long t = steps[steps_count == 1 ? 0 : n];
-    const float abar = abar_table ? abar_table[t] : cosine_abar((float)t, (float)max_step);
+    const float abar = abar_of(t, abar_table, max_step);
     const float ca = sqrtf(abar), cb = sqrtf(1.0f - abar);
     const long long base = (long long)n * per_image;
     const long long nv = per_image / 4;
+    const Philox ph(seed);
+    if constexpr (kPhilox) { if (offset_dev) offset = (unsigned long long)__ldg(offset_dev); } else { (void)offset; }
     for (long long v = blk * (long long)blockDim.x + threadIdx.x; v < nv; v += (long long)vec_per_image_blocks * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(img + base) + v);
-        const float4 e = __ldg(reinterpret_cast<const float4*>(eps + base) + v);
+        float4 e;
+        if constexpr (kPhilox) {
+            e = philox_normal4(ph, (unsigned long long)((first_elem + base) / 4 + v), offset);
+            if (eps_out) reinterpret_cast<float4*>(eps_out + base)[v] = e;
+        } else {
+            e = __ldg(reinterpret_cast<const float4*>(eps + base) + v);
+        }
         float4 o;
         o.x = ca * a.x + cb * e.x; o.y = ca * a.y + cb * e.y; o.z = ca * a.z + cb * e.z; o.w = ca * a.w + cb * e.w;
         reinterpret_cast<float4*>(out + base)[v] = o;
     }
-    for (long long i = nv * 4 + blk * (long long)blockDim.x + threadIdx.x; i < per_image; i += (long long)vec_per_image_blocks * blockDim.x)
-        out[base + i] = ca * img[base + i] + cb * eps[base + i];
+    if constexpr (!kPhilox) {
+        for (long long i = nv * 4 + blk * (long long)blockDim.x + threadIdx.x; i < per_image; i += (long long)vec_per_image_blocks * blockDim.x)
+            out[base + i] = ca * img[base + i] + cb * eps[base + i];
+    }
+}
+static int qsample_blocks(int N, long long per_image) {
+    int bpi = (int)((per_image / 4 + 255) / 256);
+    const int cap = (device_sm_count() * 16 + N - 1) / N;
+    if (bpi > cap) bpi = cap;
+    return bpi < 1 ? 1 : bpi;
 }
 extern "C" int b2_qsample(const float* img, const float* eps, float* out, const long long* steps, int steps_count,
                           const float* abar_table, int max_step, int N, long long per_image, void* stream) {
     if (steps_count != 1 && steps_count != N) return set_error("b2_qsample: steps must have 1 or N entries");
     if (per_image % 4) return set_error("b2_qsample: C*H*W must be a multiple of 4");
-    int bpi = (int)((per_image / 4 + 255) / 256);
-    const int cap = (device_sm_count() * 16 + N - 1) / N;
-    if (bpi > cap) bpi = cap;
-    if (bpi < 1) bpi = 1;
-    B2_LAUNCH((qsample_kernel), N * bpi, 256, 0, (cudaStream_t)stream, img, eps, out, steps, steps_count, abar_table, max_step, per_image, bpi);
+    const int bpi = qsample_blocks(N, per_image);
+    B2_LAUNCH((qsample_kernel<false>), N * bpi, 256, 0, (cudaStream_t)stream, img, eps, out, (float*)nullptr, steps, steps_count,
+              abar_table, max_step, per_image, bpi, 0ull, 0ull, (const float*)nullptr, 0ll);
     LAUNCH_CHECK("b2_qsample");
+}
+extern "C" int b2_qsample_philox(const float* img, float* out, float* eps_out, const long long* steps, int steps_count,
+                                 const float* abar_table, int max_step, int N, long long per_image, unsigned long long seed,
+                                 unsigned long long offset, const float* offset_dev, long long first_elem, void* stream) {
+    if (steps_count != 1 && steps_count != N) return set_error("b2_qsample_philox: steps must have 1 or N entries");
+    if (per_image % 4 || first_elem % 4) return set_error("b2_qsample_philox: C*H*W and first_elem must be multiples of 4");
+    const int bpi = qsample_blocks(N, per_image);
+    B2_LAUNCH((qsample_kernel<true>), N * bpi, 256, 0, (cudaStream_t)stream, img, (const float*)nullptr, out, eps_out, steps,
+              steps_count, abar_table, max_step, per_image, bpi, seed, offset, offset_dev, first_elem);
+    LAUNCH_CHECK("b2_qsample_philox");
 }
 
 // ------------------------------------------------------------------------------------------------ sampler updates
@@ -198,15 +236,25 @@ extern "C" int b2_cold_step(const float* x_t, const float* x0_hat, const float* 
 
 // ------------------------------------------------------------------------------------------------ MSE loss + gradient
 // loss += sum((p - t)^2) * inv_n ; grad = 2 (p - t) * inv_n * grad_scale        (train_diffusion.py:350)
+// kPhilox: the target is the eps of b2_qsample_philox, re-drawn here from the same (seed, offset, element index) instead of
+// being stored by the q-sample kernel and read back (eps-prediction, train_diffusion.py:336-350).
+template <bool kPhilox>
 __global__ void mse_loss_grad_kernel(const float* __restrict__ p, const float* __restrict__ t, float* __restrict__ grad,
-                                     float* __restrict__ loss, long long n, float inv_n, float grad_scale) {
+                                     float* __restrict__ loss, long long n, float inv_n, float grad_scale,
+                                     unsigned long long seed, unsigned long long offset, const float* __restrict__ offset_dev,
+                                     long long first_elem) {
     pdl_launch_dependents();
     pdl_wait();
     float acc = 0.f;
     const long long nv = n / 4;
     const float gs = 2.0f * inv_n * grad_scale;
+    const Philox ph(seed);
+    if constexpr (kPhilox) { if (offset_dev) offset = (unsigned long long)__ldg(offset_dev); } else { (void)offset; }
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nv; v += (long long)gridDim.x * blockDim.x) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p) + v), b = __ldg(reinterpret_cast<const float4*>(t) + v);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p) + v);
+        float4 b;
+        if constexpr (kPhilox) b = philox_normal4(ph, (unsigned long long)(first_elem / 4 + v), offset);
+        else b = __ldg(reinterpret_cast<const float4*>(t) + v);
         const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
         acc += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
         if (grad) reinterpret_cast<float4*>(grad)[v] = make_float4(gs * d.x, gs * d.y, gs * d.z, gs * d.w);
@@ -227,8 +275,19 @@ extern "C" int b2_mse_loss_grad(const float* pred, const float* target, float* g
     if (n % 4) return set_error("b2_mse_loss_grad: element count must be a multiple of 4");
     cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error("b2_mse_loss_grad: memset: %s", cudaGetErrorString(e));
-    B2_LAUNCH((mse_loss_grad_kernel), ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, pred, target, grad, loss, n, 1.0f / (float)n, grad_scale);
+    B2_LAUNCH((mse_loss_grad_kernel<false>), ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, pred, target, grad, loss, n,
+              1.0f / (float)n, grad_scale, 0ull, 0ull, (const float*)nullptr, 0ll);
     LAUNCH_CHECK("b2_mse_loss_grad");
+}
+extern "C" int b2_mse_loss_grad_philox(const float* pred, float* grad, float* loss, long long n, float grad_scale,
+                                       unsigned long long seed, unsigned long long offset, const float* offset_dev,
+                                       long long first_elem, void* stream) {
+    if (n % 4 || first_elem % 4) return set_error("b2_mse_loss_grad_philox: element count and first_elem must be multiples of 4");
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error("b2_mse_loss_grad_philox: memset: %s", cudaGetErrorString(e));
+    B2_LAUNCH((mse_loss_grad_kernel<true>), ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, pred, (const float*)nullptr, grad,
+              loss, n, 1.0f / (float)n, grad_scale, seed, offset, offset_dev, first_elem);
+    LAUNCH_CHECK("b2_mse_loss_grad_philox");
 }
 
 // ------------------------------------------------------------------------------------------------ area resample

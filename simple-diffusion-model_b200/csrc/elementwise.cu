@@ -531,11 +531,74 @@ __global__ void gn_stats_kernel(const T* __restrict__ y, long long ldy, float* _
     __syncthreads();
     for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(stats + (long long)n * groups * 2 + i, gsum[i]);
 }
+// Deterministic (and batch-size invariant) variant for SDM_B200_DETERMINISTIC / b2_set_deterministic: one CTA per (image, block
+// of CB channels) walks all pixels of its image in a fixed order; the per-thread partial sums are combined by fixed-order
+// shared-memory passes and the (sum, sum of squares) pairs are STORED -- no atomics anywhere, so the statistics of an image do
+// not depend on launch shape, batch size or timing (sharded sampling == unsharded sampling bit for bit).
+template <typename T>
+__global__ void gn_stats_det_kernel(const T* __restrict__ y, long long ldy, float* __restrict__ stats, int HW, int C, int groups,
+                                    int CB, int rows_per_block, int pre_swish) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float red[];                   // [rows_per_block][CB] partials, then [2][CB] column sums
+    constexpr int V = V16<T>::N;
+    const int cvb = CB / V;
+    const int blocks_per_image = C / CB;
+    const int n = blockIdx.x / blocks_per_image, cb0 = (blockIdx.x % blocks_per_image) * CB;
+    const int cl = (threadIdx.x % cvb) * V, prow = threadIdx.x / cvb;
+    const int cpg = C / groups;
+    float s1[V], s2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    for (int p = prow; p < HW; p += rows_per_block) {
+        float v[V];
+        unpack16<T>(ldg16(y + ((long long)n * HW + p) * ldy + cb0 + cl), v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float x = pre_swish ? swish_t<sizeof(T) == 2>(v[j]) : v[j];
+            s1[j] += x; s2[j] = fmaf(x, x, s2[j]);
+        }
+    }
+    float* csum = red + rows_per_block * CB;
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) red[prow * CB + cl + j] = pass == 0 ? s1[j] : s2[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < CB; c += blockDim.x) {
+            float a = 0.f;
+            for (int r = 0; r < rows_per_block; ++r) a += red[r * CB + c];
+            csum[pass * CB + c] = a;
+        }
+        __syncthreads();
+    }
+    const int g_local = CB / cpg;                     // groups owned by this CTA (CB is a multiple of cpg)
+    for (int i = threadIdx.x; i < g_local * 2; i += blockDim.x) {
+        const int g = i >> 1, which = i & 1;
+        float a = 0.f;
+        for (int c = 0; c < cpg; ++c) a += csum[which * CB + g * cpg + c];
+        stats[((long long)n * groups + cb0 / cpg + g) * 2 + which] = a;
+    }
+}
 namespace b2 {
 int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, int C, int groups, int pre_swish, int dtype,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool deterministic) {
     const int V = dtype == 0 ? 8 : 4;
     if (C % V || ldy % V || C % groups) return set_error("gn_stats: channel count / stride must be 16-byte aligned and divisible by groups");
+    if (deterministic) {
+        const int cpg = C / groups;
+        int CB = 64;                                  // channel block per CTA: a multiple of V and of the group width
+        while (CB % cpg) CB *= 2;
+        if (CB > C || C % CB) CB = C;
+        const int cvb = CB / V;
+        int k = 256 / cvb; if (k < 1) k = 1;
+        const size_t smem = (size_t)(k + 2) * CB * sizeof(float);
+        const int grid = N * (C / CB);
+        if (dtype == 0) B2_LAUNCH((gn_stats_det_kernel<bf16>), grid, cvb * k, smem, st, (const bf16*)y, ldy, stats, HW, C, groups, CB, k, pre_swish);
+        else B2_LAUNCH((gn_stats_det_kernel<float>), grid, cvb * k, smem, st, (const float*)y, ldy, stats, HW, C, groups, CB, k, pre_swish);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_error("gn_stats (deterministic): %s", cudaGetErrorString(e));
+        return 0;
+    }
     const int cv = C / V;
     int k = 256 / cv; if (k < 1) k = 1;
     int slabs = (4 * device_sm_count() + N - 1) / N;
@@ -552,7 +615,7 @@ int launch_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, i
 }  // namespace b2
 extern "C" int b2_gn_stats(const void* y, long long ldy, float* stats, int N, int HW, int C, int groups, int pre_swish, int dtype,
                            void* stream) {
-    return b2::launch_gn_stats(y, ldy, stats, N, HW, C, groups, pre_swish, dtype, (cudaStream_t)stream);
+    return b2::launch_gn_stats(y, ldy, stats, N, HW, C, groups, pre_swish, dtype, (cudaStream_t)stream, b2::deterministic_mode());
 }
 
 // ------------------------------------------------------------------------------------------------ attention helpers

@@ -63,6 +63,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+    volatile int* flag_s = reinterpret_cast<volatile int*>(tmem_holder + 1);      // ordered split-K: arrival order of this CTA's split
 
     pdl_launch_dependents();               // the next kernel may be scheduled (and run its prologue) while this one works
     const int warp = threadIdx.x >> 5;
@@ -193,6 +194,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
+        const int epi_tid = threadIdx.x - 64;
+        const bool ordered = p.out_mode == 0 && p.splits > 1 && p.ws != nullptr;
         int acc = 0; uint32_t acc_ph = 0;
         for (int item = item0; item < total_items; item += item_step) {
             const TnWork wk = decode(item);
@@ -203,6 +206,70 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
+            if (ordered) {
+                // ---- ordered split-K: publish this split's partial tile, then only the split that arrives last reduces
+                // (never batched, so the tile index is the item index without its split digit -- also in cluster mode, where
+                // the two CTAs of a pair see the same item but different M tiles: give each its own tile id)
+                const int tile = (item / p.splits) * CL + (CL > 1 ? crank : 0);
+                float* ws_row = p.ws + (((long long)tile * p.splits) * 128 + (q * 32 + lane)) * BLOCK_N;
+                float* mine = ws_row + (long long)wk.split * 128 * BLOCK_N;
+#pragma unroll 1
+                for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
+                    if (wk.nt_in_tap * BLOCK_N + ch * 32 >= p.Ncols) break;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            __stcg(reinterpret_cast<float4*>(mine + ch * 32) + i,
+                                   kb1 > kb0 ? make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
+                }
+                tc_fence_before();
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(kTnEpiWarps * 32) : "memory");
+                if (epi_tid == 0) {
+                    mbar_arrive_n(&tempty[acc], kTnEpiWarps);         // the accumulator stage is free again
+                    *flag_s = atomicAdd(p.ws_counters + tile, 1);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kTnEpiWarps * 32) : "memory");
+                const bool last = (*flag_s == p.splits - 1);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                if (!last) continue;
+                __threadfence();
+                if (epi_tid == 0) p.ws_counters[tile] = 0;
+#pragma unroll 1
+                for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
+                    const int col0 = wk.nt_in_tap * BLOCK_N + ch * 32;
+                    if (col0 >= p.Ncols) break;
+                    if (!valid) continue;
+                    float4 a4[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int sp = 0; sp < p.splits; ++sp) {            // fixed order: bitwise repeatable
+                        const float4* src = reinterpret_cast<const float4*>(ws_row + (long long)sp * 128 * BLOCK_N + ch * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 x = __ldcg(src + i);
+                            a4[i].x += x.x; a4[i].y += x.y; a4[i].z += x.z; a4[i].w += x.w;
+                        }
+                    }
+                    const int ncols = min(32, p.Ncols - col0);
+                    float* o = reinterpret_cast<float*>(p.out) + off + col0;
+                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            reinterpret_cast<float4*>(o)[i] = make_float4(a4[i].x * p.alpha, a4[i].y * p.alpha, a4[i].z * p.alpha, a4[i].w * p.alpha);
+                    } else {
+                        const float* f = reinterpret_cast<const float*>(a4);
+                        for (int i = 0; i < ncols; ++i) o[i] = f[i] * p.alpha;
+                    }
+                }
+                continue;
+            }
             if (kb1 > kb0) {
 #pragma unroll 1
                 for (int ch = half; ch < BLOCK_N / 32; ch += 2) {

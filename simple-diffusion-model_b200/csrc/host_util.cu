@@ -79,4 +79,14 @@ bool pdl_enabled() {
     return v == 1;
 }
 
+static int g_det = -1;
+bool deterministic_mode() {
+    if (g_det < 0) {
+        const char* e = getenv("SDM_B200_DETERMINISTIC");
+        g_det = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_det == 1;
+}
+void set_deterministic_mode(int on) { g_det = on ? 1 : 0; }
+
 }  // namespace b2

@@ -24,6 +24,12 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
 // plain stream order -- graph replay already hides the launch gap -- so it is OFF unless SDM_B200_PDL=1.
 bool pdl_enabled();
 
+// Deterministic mode (SDM_B200_DETERMINISTIC=1 or b2_set_deterministic): no floating-point atomics and no batch-size dependent
+// tiling on the forward path -- GroupNorm statistics come from the fixed-order statistics kernel instead of the conv epilogue's
+// atomics, split-K is off for the NT kernel -- so an image's result does not depend on what else is in the batch.
+bool deterministic_mode();
+void set_deterministic_mode(int on);
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};

@@ -64,8 +64,13 @@ struct GemmTnParams {
     int M, Ncols;                // valid rows / valid columns per tap
     void* out;                   // C; row stride ldc, tap stride tap_stride (elements), batch strides c_s1 (h) / c_s2 (n)
     long long ldc, tap_stride, c_s1, c_s2;
-    int out_mode;                // 0: fp32 atomicAdd (gradient accumulation), 1: store in the operand dtype
+    int out_mode;                // 0: fp32 gradient written into a zero-initialised buffer, 1: store in the operand dtype
     float alpha;
+    // out_mode 0 with splits > 1: ws != NULL -> ORDERED split-K (bitwise repeatable): every split stores its fp32 partial tile to
+    // ws ([tile][split][128][BLOCK_N]); the split that arrives last (per-tile counter, self-resetting) sums the slices in split
+    // order and stores the tile.  ws == NULL -> fp32 vector atomics straight into the output (order-dependent rounding).
+    float* ws;
+    int* ws_counters;
 };
 
 }  // namespace b2

@@ -16,6 +16,8 @@ from b200._lib import B200Error, call, ptr, stream
 def _qsample(img, steps, eps, abar_table, max_step):
     if not img.is_cuda:
         raise B200Error("degrader.forward needs CUDA tensors: this build has no CPU path")
+    if abar_table is not None:
+        _check_steps(steps, max_step)
     if eps is None:
         eps = torch.randn_like(img)
     img_c = img.contiguous().float()
@@ -25,6 +27,41 @@ def _qsample(img, steps, eps, abar_table, max_step):
     n = img_c.shape[0]
     call("b2_qsample", ptr(img_c), ptr(eps_c), ptr(out), ptr(steps_c), steps_c.numel(), ptr(abar_table), int(max_step), n,
          img_c.numel() // n, stream())
+    return out
+
+
+def _check_steps(steps, max_step):
+    """The reference's `torch.gather` raises on t < 0 or t > max_noise_step (degraders.py:44-49).  Timesteps that live on the
+    host are validated here; device-resident ones (the trainer's randint) are checked inside the kernel, which poisons the
+    image with NaN instead of reading outside the table."""
+    if torch.is_tensor(steps) and steps.is_cuda:
+        return
+    idx = torch.as_tensor(steps, dtype=torch.int64).reshape(-1)
+    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) > int(max_step)):
+        raise IndexError(f"timestep out of range [0, {int(max_step)}]: {idx.tolist()}")
+
+
+class PhiloxNoise:
+    """Where the in-kernel eps of `forward_philox` comes from: Philox4x32-10 keyed on (seed, offset, first_elem + element
+    index).  `offset` is the draw number (the optimisation step); `offset_dev` (a 1-element fp32 CUDA tensor, e.g. the fused
+    optimiser's device-side step count) overrides it so that CUDA-graph replays draw fresh noise; `first_elem` is the global
+    index of this process's first element (rank * N * C * H * W under data parallelism)."""
+
+    def __init__(self, seed, offset=0, offset_dev=None, first_elem=0):
+        self.seed, self.offset, self.offset_dev, self.first_elem = int(seed), int(offset), offset_dev, int(first_elem)
+
+
+def _qsample_philox(img, steps, noise, abar_table, max_step, eps_out=None):
+    if not img.is_cuda:
+        raise B200Error("degrader.forward_philox needs CUDA tensors: this build has no CPU path")
+    if abar_table is not None:
+        _check_steps(steps, max_step)
+    img_c = img.contiguous().float()
+    steps_c = steps.to(device=img.device, dtype=torch.int64).contiguous()
+    out = torch.empty_like(img_c)
+    n = img_c.shape[0]
+    call("b2_qsample_philox", ptr(img_c), ptr(out), ptr(eps_out), ptr(steps_c), steps_c.numel(), ptr(abar_table), int(max_step),
+         n, img_c.numel() // n, noise.seed, noise.offset, ptr(noise.offset_dev), noise.first_elem, stream())
     return out
 
 
@@ -51,6 +88,7 @@ class NoiseDegradation(nn.Module):
 
     def host_params(self, step):
         """(beta, alpha, alpha_bar) of integer step(s) as fp32 CPU tensors."""
+        _check_steps(step, self.max_noise_step)
         idx = torch.as_tensor(step, dtype=torch.int64).reshape(-1)
         return self._host_beta[idx], self._host_alpha[idx], self._host_abar[idx]
 
@@ -59,6 +97,13 @@ class NoiseDegradation(nn.Module):
             self.beta, self.alpha = self.beta.to(img.device), self.alpha.to(img.device)
             self.alpha_cumulative_prod = self.alpha_cumulative_prod.to(img.device)
         return _qsample(img, steps, eps, self.alpha_cumulative_prod, self.max_noise_step)
+
+    def forward_philox(self, img, steps, noise, eps_out=None):
+        """`forward` with eps drawn inside the kernel (PhiloxNoise) instead of by a separate `randn_like` launch."""
+        if self.alpha_cumulative_prod.device != img.device:
+            self.beta, self.alpha = self.beta.to(img.device), self.alpha.to(img.device)
+            self.alpha_cumulative_prod = self.alpha_cumulative_prod.to(img.device)
+        return _qsample_philox(img, steps, noise, self.alpha_cumulative_prod, self.max_noise_step, eps_out)
 
 
 class CosineNoiseDegradation(nn.Module):
@@ -84,3 +129,7 @@ class CosineNoiseDegradation(nn.Module):
 
     def forward(self, img, steps, eps=None):
         return _qsample(img, steps, eps, None, self.max_noise_step)
+
+    def forward_philox(self, img, steps, noise, eps_out=None):
+        """`forward` with eps drawn inside the kernel (PhiloxNoise) instead of by a separate `randn_like` launch."""
+        return _qsample_philox(img, steps, noise, None, self.max_noise_step, eps_out)

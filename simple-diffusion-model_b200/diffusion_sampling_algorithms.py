@@ -15,6 +15,29 @@ from utils.utils import printProgressBar
 
 REFERENCE_RNG = True
 PHILOX_SEED = None
+_SHARD = None           # (lo, hi, total): this process samples images [lo, hi) of a `total`-image job (generate_* under torchrun)
+
+
+def set_shard(lo=None, hi=None, total=None):
+    """Declares that the x_t handed to the samplers holds images [lo, hi) of a `total`-image job.  Per-step noise is then
+    drawn for the WHOLE job from the (identically seeded) generator and sliced -- or, with PHILOX_SEED, keyed on the global
+    element index -- so that the union of the shards equals the single-process result.  `set_shard()` clears it."""
+    global _SHARD
+    _SHARD = None if lo is None or total is None or (lo == 0 and hi == total) else (int(lo), int(hi), int(total))
+
+
+def _step_noise(x_t):
+    """`torch.randn(x_t.shape)` of the reference (:43, :129), shard-consistent (see set_shard)."""
+    if _SHARD is None or x_t.shape[0] != _SHARD[1] - _SHARD[0]:
+        return torch.randn(x_t.shape, device=x_t.device)
+    lo, hi, total = _SHARD
+    return torch.randn((total,) + tuple(x_t.shape[1:]), device=x_t.device)[lo:hi].contiguous()
+
+
+def _first_elem(x_t):
+    if _SHARD is None or x_t.shape[0] != _SHARD[1] - _SHARD[0]:
+        return 0
+    return _SHARD[0] * (x_t.numel() // x_t.shape[0])
 
 
 def skip_schedule(min_noise, max_noise, step_size):
@@ -61,10 +84,10 @@ def ddpm_sampling(diffusion_net, noise_degradation, x_t, min_noise=1, max_noise=
                 if PHILOX_SEED is not None:
                     use_philox = 1
                 else:
-                    z = torch.randn(x_t.shape, device=x_t.device)
+                    z = _step_noise(x_t)
             out = torch.empty_like(x_t)
             call("b2_ddpm_step", ptr(x_t), ptr(eps_hat), ptr(z), ptr(out), n_elem, _f(scale_1), _f(scale_2), _f(sigma),
-                 use_philox, int(PHILOX_SEED or 0), int(step), 0, stream())
+                 use_philox, int(PHILOX_SEED or 0), int(step), _first_elem(x_t), stream())
             x_t = out
             printProgressBar(iteration=max_noise - step, total=max_noise - min_noise, prefix='Iterations:',
                              suffix='Complete', length=50, log=log)
@@ -90,7 +113,7 @@ def ddim_sampling(diffusion_net, noise_degradation, x_t, min_noise=1, max_noise=
             if not last:
                 abar_n = noise_degradation.host_params(steps[count + 1])[2]
                 sigma = eta * (((1 - abar_n) / (1 - abar_t)) ** 0.5 * (1 - (abar_t / abar_n)) ** 0.5)
-                noise = torch.randn_like(x_t) if REFERENCE_RNG else None      # drawn by the reference even though eta = 0
+                noise = _step_noise(x_t) if REFERENCE_RNG else None           # drawn by the reference even though eta = 0
                 out = torch.empty_like(x_t)
                 call("b2_ddim_step", ptr(x_t), ptr(eps_hat), ptr(noise) if _f(sigma) != 0.0 else None, ptr(out), None, n_elem,
                      _f(c_scale), _f(c_s), _f(abar_n ** 0.5), _f((1 - abar_n - sigma ** 2) ** 0.5), _f(sigma), 0, stream())

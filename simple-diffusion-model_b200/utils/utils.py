@@ -16,15 +16,24 @@ def printProgressBar(iteration, total, prefix='', suffix='', decimals=1, length=
 
 
 def plot_sampled_images(sampled_imgs, file_name, dest_path=None, log=print):
-    """BGR -> RGB, 5-per-row grid normalised from [-1, 1], written as <dest>/plots/<file_name>.jpg."""
-    import torchvision
-    grid = torchvision.utils.make_grid(sampled_imgs[:, [2, 1, 0]], nrow=5, normalize=True, value_range=(-1, 1))
+    """BGR -> RGB, 5-per-row grid normalised from [-1, 1], written as <dest>/plots/<file_name>.jpg (reference
+    utils/utils.py:39-65).  Samples that live on the GPU never travel as fp32: channel swap, make_grid and save_image's
+    quantisation are one kernel (b200.image_io.image_grid_u8) and only the uint8 picture is copied back for JPEG encoding --
+    the bytes handed to the encoder are identical to torchvision's."""
     base = os.path.dirname(os.path.abspath(__file__)) if dest_path is None else dest_path
     out_dir = os.path.join(base, "plots")
     os.makedirs(out_dir, exist_ok=True)
     try:
         path = os.path.join(out_dir, str(file_name) + ".jpg")
-        torchvision.utils.save_image(grid, path)
+        if sampled_imgs.is_cuda and sampled_imgs.shape[1] in (1, 3):
+            from PIL import Image
+            from b200.image_io import image_grid_u8
+            picture = image_grid_u8(sampled_imgs, nrow=5, padding=2, value_range=(-1, 1), swap_rb=True).cpu().numpy()
+            Image.fromarray(picture[:, :, 0] if picture.shape[2] == 1 else picture).save(path)
+        else:
+            import torchvision
+            grid = torchvision.utils.make_grid(sampled_imgs[:, [2, 1, 0]], nrow=5, normalize=True, value_range=(-1, 1))
+            torchvision.utils.save_image(grid, path)
         log(f"Saving generated image: {path}")
     except Exception as e:  # same forgiving behaviour as the reference
         log(f"An error occured while plotting reconstructed image: {e}")

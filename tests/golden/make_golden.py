@@ -32,7 +32,13 @@ UNET_CASES = {
     "gpu_cond": (dict(num_resnet_blocks=2, in_channel=6, time_dim=64, cond_dim=10, num_layers=3, attn_layers=[1, 2], num_heads=2,
                       dim_per_head=64, min_channel=128, max_channel=256, image_recon=True), 3, 32, 32),
     "default64": (dict(), 2, 64, 64),
+    # BASELINE configs[2] / configs[3] shapes on the class-default net: S = 1024 attention (multi-tile softmax fix-up inside the
+    # full net) with labels at 128x128; 6-channel image_recon (SR) net at 256x256 (S = 4096 attention).  Gradients are kept as
+    # 1024 strided samples per tensor to bound the fixture size.
+    "default128_cond": (dict(cond_dim=10), 2, 128, 128),
+    "default256_sr": (dict(in_channel=6, image_recon=True), 1, 256, 256),
 }
+SAMPLES = {"default128_cond": 1024, "default256_sr": 1024}
 
 
 def unet_case(name, kwargs, n, h, w):
@@ -59,18 +65,19 @@ def unet_case(name, kwargs, n, h, w):
             no_grad.append(pname)
             continue
         gflat = p.grad.detach().flatten()
-        # large tensors: 4096 evenly strided samples (index i * numel // 4096) instead of the whole gradient
-        idx = (torch.arange(4096, dtype=torch.int64) * gflat.numel()) // 4096 if gflat.numel() > 4096 else None
+        # large tensors: `ns` evenly strided samples (index i * numel // ns) instead of the whole gradient
+        ns = SAMPLES.get(name, 4096)
+        idx = (torch.arange(ns, dtype=torch.int64) * gflat.numel()) // ns if gflat.numel() > ns else None
         grads[pname] = {"norm": float(gflat.norm()), "sum": float(gflat.sum()),
                         "head": gflat[:64].clone(),
                         "sample": gflat[idx].clone() if idx is not None else None,
-                        "full": p.grad.detach().clone() if gflat.numel() <= 4096 else None}
+                        "full": p.grad.detach().clone() if gflat.numel() <= ns else None}
     # batch-1 timestep broadcast (samplers pass t of shape [1])
     net.eval()
     with torch.no_grad():
         out_t1 = net(x, t[:1], cond[0] if cond is not None else None)
     fx = dict(kwargs=kwargs, shapes=shapes, seed=seed, x=x, t=t, cond=cond, target=target, out=out.detach(),
-              loss=float(loss), grads=grads, no_grad=sorted(no_grad), out_t1=out_t1)
+              loss=float(loss), grads=grads, no_grad=sorted(no_grad), out_t1=out_t1, n_samples=SAMPLES.get(name, 4096))
     torch.save(fx, os.path.join(HERE, f"unet_{name}.pt"))
     print(name, "params", sum(int(torch.tensor(s).prod()) for s in shapes.values()), "loss", float(loss), "no-grad params", len(no_grad))
 

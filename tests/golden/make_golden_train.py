@@ -77,7 +77,7 @@ def sample(t):
     return flat[idx].clone()
 
 
-def run(name, module, net_kw, size, overrides, work):
+def run(name, module, net_kw, size, overrides, work, keep_ckpt=None):
     seed = 4321
     shapes = {k: tuple(v.shape) for k, v in U_Net(**net_kw).state_dict().items()}
     init = os.path.join(work, f"{name}_init.pt")
@@ -167,6 +167,13 @@ def run(name, module, net_kw, size, overrides, work):
                           eps=opt["param_groups"][0]["eps"], weight_decay=opt["param_groups"][0]["weight_decay"],
                           n_state=len(opt["state"]),
                           adam_step=float(next(iter(opt["state"].values()))["step"])))
+    if keep_ckpt is not None:                        # the checkpoint FILES the reference wrote, byte for byte
+        import shutil
+        dest, which = keep_ckpt
+        os.makedirs(dest, exist_ok=True)
+        for k in which:
+            for stem in ("diffusion", "config"):
+                shutil.copyfile(os.path.join(out_dir, "checkpoint", f"{stem}_{k}.pt"), os.path.join(dest, f"{stem}_{k}.pt"))
     return dict(module=module, kwargs=net_kw, shapes=shapes, seed=seed, config=cfg, steps=steps, checkpoints=ckpts,
                 samples=SAMPLES)
 

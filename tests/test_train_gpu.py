@@ -22,7 +22,7 @@ def _build(fx, precision):
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
-@pytest.mark.parametrize("name", ["gpu_small", "gpu_cond", "default64"])
+@pytest.mark.parametrize("name", ["gpu_small", "gpu_cond", "default64", "default128_cond", "default256_sr"])
 def test_unet_backward_matches_reference(name, precision):
     fx = load_golden(f"unet_{name}.pt")
     net = _build(fx, precision)
@@ -42,7 +42,8 @@ def test_unet_backward_matches_reference(name, precision):
         if g["full"] is not None:
             want, have = g["full"].flatten(), got
         else:
-            idx = (torch.arange(4096, dtype=torch.int64) * got.numel()) // 4096
+            ns = fx.get("n_samples", 4096)
+            idx = (torch.arange(ns, dtype=torch.int64) * got.numel()) // ns
             want, have = g["sample"], got[idx]
         got_all.append(have)
         want_all.append(want)

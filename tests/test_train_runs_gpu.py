@@ -1,0 +1,105 @@
+"""GPU replay of the UNMODIFIED reference trainers' recorded runs (tests/golden/train_runs.pt, written by
+tests/golden/make_golden_train.py): the four train-step bodies of SURVEY A18 on the CUDA path --
+  base    train_diffusion.py:295-366              input x_t,                              target eps
+  cold    train_noise_cold_diffusion.py:330-352   input x_t,                              target x0
+  sr      train_SR_diffusion.py:320-374           input cat(x_t, q(area_up(area_down x0), cond_t)), target x0 - lr
+  doodle  train_doodle_diffusion.py:304-315       input cat(x_t, condition image),        target eps
+Every step feeds the recorded (x0, t, eps) through this repo's degrader / area_resize / U_Net / fused MSE / backward /
+FusedAdam and asserts the network input, the target, the prediction, the loss, the weights the reference checkpointed after
+the step and the learning-rate halving.  Both execution modes: the eager step functions and the CUDA-graph replay the
+trainers use.  fp32-accumulate (TF32) parity mode; tolerances are written beside each assert."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from oracle.weights import synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+KIND = {"base": "eps", "cold": "x0", "sr": "target", "doodle": "eps"}
+
+
+def _sample(t, n):
+    flat = t.detach().float().flatten().cpu()
+    return flat[(torch.arange(n, dtype=torch.int64) * flat.numel()) // n]
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph"])
+@pytest.mark.parametrize("name", ["base", "cold", "sr", "doodle"])
+def test_reference_trainer_run_replays_on_gpu(name, mode):
+    from b200.functional import area_resize
+    from b200.graph import GraphedTrainStep
+    from b200.optim import FusedAdam
+    from b200.steps import eps_prediction_step, x0_prediction_step
+    from degraders import CosineNoiseDegradation, NoiseDegradation
+    from models.U_Net import U_Net
+
+    fx = load_golden("train_runs.pt")[name]
+    cfg, kw = fx["config"], fx["kwargs"]
+    dev = torch.device("cuda")
+    sd0 = synth_state_dict(fx["shapes"], fx["seed"])
+    net = U_Net(**kw)
+    net.load_state_dict(sd0)
+    net = net.to(dev).train().set_precision("tf32")
+    net.engine().grad_layout(dev).flatten_params()
+    lr = cfg["diffusion_lr"]
+    opt = FusedAdam(net.parameters(), lr=lr, betas=(0.5, 0.999), capturable=(mode == "graph"))
+    if cfg["noise_scheduler"] == "LINEAR":
+        deg = NoiseDegradation(cfg["beta1"], cfg["betaT"], cfg["max_noise_step"], device=dev)
+    else:
+        deg = CosineNoiseDegradation(cfg["max_noise_step"])
+    graphed = GraphedTrainStep(net, deg, opt, kind=KIND[name]) if mode == "graph" else None
+    start = torch.cat([_sample(v, fx["samples"]) for _, v in sorted(sd0.items())])
+
+    for gstep, (rec, ck) in enumerate(zip(fx["steps"], fx["checkpoints"])):
+        calls = rec["degrader_calls"]
+        x0, t, eps = calls[0]["img"].to(dev), calls[0]["steps"].to(dev), calls[0]["eps"].to(dev)
+        x_t = deg(x0, t, eps)
+        assert rel_l2(x_t.cpu(), calls[0]["out"]) < 1e-6                       # q-sample kernel vs the reference degrader
+        cond_img, target = None, None
+        if name == "sr":
+            low = area_resize(area_resize(x0, (cfg["lr_dim"],) * 2), (cfg["sr_dim"],) * 2)
+            assert rel_l2(low.cpu(), calls[1]["img"]) < 1e-6                   # F.interpolate(area) down + up
+            cond_img = deg(low, torch.tensor([cfg["cond_t"]], device=dev), eps)
+            assert rel_l2(cond_img.cpu(), calls[1]["out"]) < 1e-6
+            target = x0 - low
+            want_target = target
+        elif name == "doodle":
+            cond_img = rec["net_input"]["x"][:, 3:].to(dev)
+            want_target = eps
+        else:
+            want_target = eps if name == "base" else x0
+        assert rel_l2(want_target.cpu(), rec["target"]) < 1e-6
+        inp = torch.cat((x_t, cond_img), dim=1) if cond_img is not None else x_t
+        assert rel_l2(inp.cpu(), rec["net_input"]["x"]) < 1e-6                 # what the reference's U_Net received
+        with torch.no_grad():
+            pred = net(inp, t, None)
+        err_pred = rel_l2(pred.cpu(), rec["pred"])
+        assert err_pred < 1e-3, err_pred                                       # north-star bound, fp32-accumulate mode
+
+        if graphed is not None:
+            loss = graphed(x0, t, eps, None, cond_img, target)
+        elif KIND[name] == "eps":
+            loss = eps_prediction_step(net, deg, opt, x0, t, eps, None, cond_img)
+        else:
+            loss = x0_prediction_step(net, deg, opt, x0, t, eps, None, cond_img, target)
+        loss = float(loss)
+        assert abs(loss - rec["loss"]) < 1e-3 * max(1.0, abs(rec["loss"])), (gstep, loss, rec["loss"])
+
+        named = dict(net.named_parameters())
+        got = torch.cat([_sample(named[k] if k in named else net.state_dict()[k], fx["samples"]) for k in sorted(ck["weights"])])
+        want = torch.cat([ck["weights"][k] for k in sorted(ck["weights"])])
+        err = rel_l2(got - start, want - start)                                # compared on the UPDATE, not the weight
+        print(f"{name}/{mode} step {gstep}: pred {err_pred:.2e} loss {loss:.6f} (ref {rec['loss']:.6f}) update rel_l2 {err:.2e}")
+        # Adam normalises the gradient (update ~ lr * m / sqrt(v)): entries whose gradient is near zero flip with TF32 noise,
+        # so the bound on the update is looser than on the prediction
+        assert err < 3e-2, (gstep, err)
+        # the reference halves the rate AFTER the step when global_steps % lr_steps == 0 and > 0 (train_diffusion.py:368-371)
+        if gstep % cfg["lr_steps"] == 0 and gstep > 0:
+            lr *= 0.5
+            for group in opt.param_groups:
+                group["lr"] = group["lr"] * 0.5
+        assert ck["lr"] == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12)
+    st = opt.state_dict()["state"]
+    assert len(st) == fx["checkpoints"][-1]["n_state"]
+    assert float(next(iter(st.values()))["step"]) == fx["checkpoints"][-1]["adam_step"]

@@ -19,8 +19,11 @@ def _build(fx, precision):
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
-@pytest.mark.parametrize("name", ["gpu_small", "gpu_cond", "default64"])
+@pytest.mark.parametrize("name", ["gpu_small", "gpu_cond", "default64", "default128_cond", "default256_sr"])
 def test_unet_forward_matches_reference(name, precision):
+    """default128_cond / default256_sr: the class-default 610.7 M net at BASELINE configs[2] / configs[3] shapes (labels at
+    128x128 -> S = 1024 attention, multi-tile softmax fix-up inside the full net; 6 input channels + tanh at 256x256 -> S =
+    4096), fixtures from the unmodified reference."""
     fx = load_golden(f"unet_{name}.pt")
     net = _build(fx, precision)
     cond = fx["cond"].cuda() if fx["cond"] is not None else None
