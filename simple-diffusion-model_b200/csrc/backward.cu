@@ -44,13 +44,34 @@ __device__ __forceinline__ void block_colsum_atomic(const float (&v)[V], float* 
 // Launch shape shared by the streaming passes: each thread owns one 16-byte channel vector for the whole kernel
 // (so per-channel partial sums live in registers) and strides over the pixels of one slab of one image.
 struct SlabLaunch { int threads, rows_per_block, slabs; };
-static SlabLaunch slab_launch(int N, int HW, int cv) {
+// ctas_per_sm: resident CTAs per SM of the kernel being launched (its __launch_bounds__).  The grid is sized to (just under) a
+// whole number of waves of sms * ctas_per_sm CTAs: N * slabs = 592 CTAs on 444 slots ran 1.33 waves, i.e. a third of the
+// machine idled through the second one.
+static SlabLaunch slab_launch(int N, int HW, int cv, int ctas_per_sm = 0) {
     SlabLaunch s;
     int k = 256 / cv; if (k < 1) k = 1;
     s.threads = cv * k;
     s.rows_per_block = k;
-    int slabs = (4 * device_sm_count() + N - 1) / N;
     const int max_slabs = (HW + 4 * k - 1) / (4 * k);
+    int slabs;
+    if (ctas_per_sm <= 0) {
+        slabs = (4 * device_sm_count() + N - 1) / N;
+    } else {
+        // the slab count (<= ~4 waves) whose last wave is fullest; ties go to more slabs (finer balance)
+        const int slots = device_sm_count() * ctas_per_sm;
+        int hi = (4 * slots) / N + 1;
+        if (hi > max_slabs) hi = max_slabs;
+        if (hi < 1) hi = 1;
+        slabs = 1;
+        double best = -1.0;
+        for (int cand = 1; cand <= hi; ++cand) {
+            const long long total = (long long)N * cand;
+            const long long waves = (total + slots - 1) / slots;
+            double eff = (double)total / (double)(waves * slots);
+            if (total < slots) eff *= 0.5;                        // under one wave: idle SMs for the whole kernel
+            if (eff >= best - 1e-9) { best = eff; slabs = cand; }
+        }
+    }
     if (slabs > max_slabs) slabs = max_slabs;
     s.slabs = slabs < 1 ? 1 : slabs;
     return s;
@@ -58,27 +79,27 @@ static SlabLaunch slab_launch(int N, int HW, int cv) {
 
 // ------------------------------------------------------------------------------------------------ AdaGN backward
 // Forward (custom_layers.py:35-45, :240-245): y = swish(z); xh = (y - mean) * rstd; out = s*(gamma*xh + beta) + s.
-// Pass 1: a1[n][c] = sum_p dout, a2[n][c] = sum_p dout * xh.
-template <typename T>
-__global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
-                                        const float* __restrict__ stats, float* __restrict__ a1, float* __restrict__ a2,
-                                        int HW, int C, int groups, float eps, int slabs, int rows_per_block) {
+// Pass 1: a1[n][c] = sum_p dout, a2[n][c] = sum_p dout * xh.  The loop only accumulates (sum d, sum d*y): the statistics enter
+// once per CTA, a2 = rstd * (sum d*y - mean * sum d), so neither mean nor rstd occupies registers while streaming.
+// U = independent 16-byte row loads per tensor per thread in flight (x2 by the software pipeline): the kernels are bound by
+// memory-level parallelism, so registers are spent on loads in flight, not on per-channel constants.
+template <typename T, int U>
+__global__ void __launch_bounds__(256, U == 4 ? 2 : 3)
+adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
+                        const float* __restrict__ stats, float* __restrict__ a1, float* __restrict__ a2,
+                        int HW, int C, int groups, float eps, int slabs, int rows_per_block) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
     const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
-    const int cpg = C / groups;
-    const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
-    float mean[V], rstd[V], s1[V], s2[V];
-    gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
+    float s1[V], s2[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    constexpr int U = 2;
     constexpr bool kFast = sizeof(T) == 2;
     struct Buf { uint4 d[U], z[U]; };
     const long long k = rows_per_block;
@@ -97,14 +118,19 @@ __global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ld
                 unpack16<T>(b.d[u], d);
                 unpack16<T>(b.z[u], zz);
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const float xh = (swish_t<kFast>(zz[j]) - mean[j]) * rstd[j];
-                    s1[j] += d[j]; s2[j] = fmaf(d[j], xh, s2[j]);
-                }
+                for (int j = 0; j < V; ++j) { s1[j] += d[j]; s2[j] = fmaf(d[j], swish_t<kFast>(zz[j]), s2[j]); }
             }
         }
     };
     pipelined_rows<Buf>(p0 + prow, p1, U * k, load, proc);
+    {
+        const int cpg = C / groups;
+        const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
+        float mean[V], rstd[V];
+        gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
+#pragma unroll
+        for (int j = 0; j < V; ++j) s2[j] = rstd[j] * (s2[j] - mean[j] * s1[j]);
+    }
     extern __shared__ float red[];
     block_colsum_atomic<V>(s1, red, C, c0, prow, rows_per_block, a1 + (long long)n * C);
     block_colsum_atomic<V>(s2, red, C, c0, prow, rows_per_block, a2 + (long long)n * C);
@@ -115,14 +141,18 @@ __global__ void adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ld
 //   m[n][g] = (sum_{c in g} s*gamma*a1, sum_{c in g} s*gamma*a2) / (cpg*HW)          (C loads from L2, shared-memory adds),
 // and the first slab of each image also emits ds[n][c] += gamma*a2 + (beta+1)*a1, dgamma[c] += s*a2, dbeta[c] += s*a1 --
 // a separate finalize launch per layer (100 latency-bound launches per backward pass) is not needed.
-template <typename T>
-__global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
-                                       const float* __restrict__ stats, const float* __restrict__ a1,
-                                       const float* __restrict__ a2, const float* __restrict__ s, long long s_bstride,
-                                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ds,
-                                       long long ds_bstride, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       T* __restrict__ dz, long long lddz, float* __restrict__ dbias, int HW, int C,
-                                       int groups, float eps, int slabs, int rows_per_block) {
+// With xh = (y - mean) * rstd the normalisation gradient is affine in (dout, y) per channel,
+//   dy = A*dout + B + Cc*y,  A = rstd*s*gamma,  Cc = -rstd^2*m2,  B = -rstd*m1 - Cc*mean,
+// so three constants per channel stay in registers instead of five.
+template <typename T, int U>
+__global__ void __launch_bounds__(256, U == 4 ? 2 : 3)
+adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
+                       const float* __restrict__ stats, const float* __restrict__ a1,
+                       const float* __restrict__ a2, const float* __restrict__ s, long long s_bstride,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ds,
+                       long long ds_bstride, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       T* __restrict__ dz, long long lddz, float* __restrict__ dbias, int HW, int C,
+                       int groups, float eps, int slabs, int rows_per_block) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float red[];
@@ -147,17 +177,19 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
         atomicAdd(&gs[(c / cpg) * 2 + 1], sc * ga * x2);
     }
     __syncthreads();
-    float mean[V], rstd[V], sg[V], m1[V], m2[V], db[V];
-    gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
+    float A[V], B[V], Cc[V], db[V];
     {
-        float sc[V], ga[V];
+        float mean[V], rstd[V], sc[V], ga[V];
+        gn_mean_rstd<V>(stats + (long long)n * groups * 2, c0, cpg, inv_cnt, eps, mean, rstd);
         ldg_f32<V>(s + (long long)n * s_bstride + c0, sc);
         ldg_f32<V>(gamma + c0, ga);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const int g = (c0 + j) / cpg;
-            sg[j] = sc[j] * ga[j];
-            m1[j] = gs[g * 2] * inv_cnt; m2[j] = gs[g * 2 + 1] * inv_cnt;
+            const float m1 = gs[g * 2] * inv_cnt, m2 = gs[g * 2 + 1] * inv_cnt;
+            A[j] = rstd[j] * sc[j] * ga[j];
+            Cc[j] = -rstd[j] * rstd[j] * m2;
+            B[j] = -rstd[j] * m1 - Cc[j] * mean[j];
             db[j] = 0.f;
         }
     }
@@ -165,7 +197,6 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
     const int p_per = (HW + slabs - 1) / slabs;
     const int p0 = slab * p_per, p1 = min(HW, p0 + p_per);
     const long long base = (long long)n * HW;
-    constexpr int U = 2;
     constexpr bool kFast = sizeof(T) == 2;
     struct Buf { uint4 d[U], z[U]; };
     const long long k = rows_per_block;
@@ -188,8 +219,7 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
                 for (int j = 0; j < V; ++j) {
                     const float zv = zz[j];
                     const float sig = sigmoid_t<kFast>(zv);
-                    const float xh = (zv * sig - mean[j]) * rstd[j];
-                    const float dy = rstd[j] * (sg[j] * d[j] - m1[j] - xh * m2[j]);
+                    const float dy = fmaf(A[j], d[j], fmaf(Cc[j], zv * sig, B[j]));
                     o[j] = dy * (sig * (1.0f + zv * (1.0f - sig)));
                     db[j] += o[j];
                 }
@@ -201,18 +231,37 @@ __global__ void adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd
     if (dbias) block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
 }
 
-// Optional L2 blocking of the two passes (SDM_B200_BWD_L2_CHUNK_MB=<MiB>, default off): both passes read dout and z, so
-// running them over groups of images whose (dout, z) fit in the 126 MB L2 lets pass 2 hit L2 instead of HBM
-// (10 -> 6 algorithmic DRAM bytes per element).  Images are independent in both kernels, so the result is unchanged.
+// L2 blocking of the two passes (SDM_B200_BWD_L2_CHUNK_MB=<MiB>; 0 disables): both passes read dout and z, so running them over
+// groups of images whose (dout, z) fit in a share of the 126 MB L2 lets pass 2 hit L2 instead of HBM (10 -> 6 DRAM bytes per
+// element, the algorithmic minimum).  Images are independent in both kernels, so the result is unchanged.
 static int adagn_bwd_chunk_images(int N, long long bytes_per_image) {
     static const long long budget = [] {
         const char* e = getenv("SDM_B200_BWD_L2_CHUNK_MB");
-        return e ? atoll(e) * (1LL << 20) : 0LL;
+        return (e ? atoll(e) : 64LL) * (1LL << 20);
     }();
     if (budget <= 0 || bytes_per_image <= 0) return N;
+    if ((long long)N * bytes_per_image <= budget) return N;
     long long nc = budget / bytes_per_image;
     if (nc < 1) nc = 1;
-    return nc < N ? (int)nc : N;
+    // equal-sized chunks: ceil(N / ceil(N / nc))
+    const long long chunks = (N + nc - 1) / nc;
+    nc = (N + chunks - 1) / chunks;
+    return (int)nc;
+}
+
+template <typename T>
+static void adagn_bwd_launch(int U, int grid, int threads, size_t red_bytes, cudaStream_t st, const void* d_c, long long ldd,
+                             const void* z_c, long long ldz, const float* stats_c, float* a1, float* a2, const float* s_c,
+                             long long s_bstride, const float* gamma, const float* beta, float* ds_c, long long ds_bstride,
+                             float* dgamma, float* dbeta, void* dz_c, long long lddz, float* dbias, int HW, int C, int groups,
+                             float eps, int slabs, int rows_per_block) {
+    if (U == 4) {
+        B2_LAUNCH((adagn_bwd_reduce_kernel<T, 4>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, slabs, rows_per_block);
+        B2_LAUNCH((adagn_bwd_apply_kernel<T, 4>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (T*)dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block);
+    } else {
+        B2_LAUNCH((adagn_bwd_reduce_kernel<T, 2>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, slabs, rows_per_block);
+        B2_LAUNCH((adagn_bwd_apply_kernel<T, 2>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (T*)dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block);
+    }
 }
 
 extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
@@ -227,6 +276,7 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
     cudaStream_t st = (cudaStream_t)stream;
     const long long eb = dtype == 0 ? 2 : 4;
     const int chunk = adagn_bwd_chunk_images(N, 2LL * HW * C * eb);
+    static const int u_env = [] { const char* e = getenv("SDM_B200_BWD_U"); return e ? atoi(e) : 0; }();
     for (int n0 = 0; n0 < N; n0 += chunk) {
         const int nc = N - n0 < chunk ? N - n0 : chunk;
         // work: [2][N][C] fp32 (a1, a2), zeroed by the caller
@@ -238,17 +288,16 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
         const float* stats_c = stats + (long long)n0 * groups * 2;
         const float* s_c = s + (long long)n0 * s_bstride;
         float* ds_c = ds ? ds + (long long)n0 * ds_bstride : nullptr;
-        const SlabLaunch sl = slab_launch(nc, HW, cv);
+        // big images: four loads per tensor in flight (2 CTAs / SM at <= 128 registers); otherwise the two-load form (3 CTAs / SM)
+        const int k0 = 256 / cv > 0 ? 256 / cv : 1;
+        const int U = u_env == 2 || u_env == 4 ? u_env : ((long long)nc * HW / k0 >= 64LL * 2 * device_sm_count() ? 4 : 2);
+        const SlabLaunch sl = slab_launch(nc, HW, cv, U == 4 ? 2 : 3);
         size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
         if (red_bytes < (size_t)groups * 2 * sizeof(float)) red_bytes = (size_t)groups * 2 * sizeof(float);
         if (dtype == 0)
-            B2_LAUNCH((adagn_bwd_reduce_kernel<bf16>), nc * sl.slabs, sl.threads, red_bytes, st, (const bf16*)d_c, ldd, (const bf16*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+            adagn_bwd_launch<bf16>(U, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
         else
-            B2_LAUNCH((adagn_bwd_reduce_kernel<float>), nc * sl.slabs, sl.threads, red_bytes, st, (const float*)d_c, ldd, (const float*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
-        if (dtype == 0)
-            B2_LAUNCH((adagn_bwd_apply_kernel<bf16>), nc * sl.slabs, sl.threads, red_bytes, st, (const bf16*)d_c, ldd, (const bf16*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (bf16*)dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
-        else
-            B2_LAUNCH((adagn_bwd_apply_kernel<float>), nc * sl.slabs, sl.threads, red_bytes, st, (const float*)d_c, ldd, (const float*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (float*)dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+            adagn_bwd_launch<float>(U, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     }
     LAUNCH_CHECK("b2_adagn_bwd");
 }

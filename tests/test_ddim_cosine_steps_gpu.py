@@ -53,7 +53,7 @@ def test_ddim_cosine_every_step(name, batch, size):
     assert len(steps) == 51 and [int(c[1][0]) for c in probe.calls] == steps           # bit-exact schedule, t of shape [1]
     assert all(tuple(c[1].shape) == (1,) and c[1].dtype == torch.int64 for c in probe.calls)
     assert torch.equal(probe.calls[0][0], x_T)
-    worst_net, worst_upd = (0.0, None), (0.0, None)
+    worst_net, worst_upd = (-1.0, 0), (-1.0, 0)
     with torch.no_grad():
         for i, (x_in, t, eps_gpu) in enumerate(probe.calls):
             assert torch.isfinite(eps_gpu).all(), steps[i]

@@ -80,6 +80,7 @@ def test_device_image_loader_prefetches_and_matches_the_host_pipeline():
     got = list(DeviceImageLoader(loader, "cuda", flip_fn=draw_flip_flags))
     assert [b[0].shape[0] for b in got] == [4, 4, 2] and len(DeviceImageLoader(loader, "cuda")) == 3
     torch.manual_seed(11)
+    iter(loader)             # a DataLoader iterator draws its base seed from the CPU generator when it is created: same stream position
     for i, (img, cond) in enumerate(got):
         assert img.is_cuda and img.dtype == torch.float32 and tuple(img.shape[1:]) == (3, 16, 16) and cond.shape == img.shape
         host = [raw[j] for j in range(4 * i, min(4 * i + 4, 10))]
