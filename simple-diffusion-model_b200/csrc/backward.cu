@@ -57,7 +57,8 @@ static SlabLaunch slab_launch(int N, int HW, int cv, int ctas_per_sm = 0) {
     if (ctas_per_sm <= 0) {
         slabs = (4 * device_sm_count() + N - 1) / N;
     } else {
-        // the slab count (<= ~4 waves) whose last wave is fullest; ties go to more slabs (finer balance)
+        // the FEWEST slabs whose waves are >= 92 % full (every CTA pays a per-image prologue: statistics, group terms), else the
+        // fullest; 592 CTAs on 444 slots ran 1.33 waves
         const int slots = device_sm_count() * ctas_per_sm;
         int hi = (4 * slots) / N + 1;
         if (hi > max_slabs) hi = max_slabs;
@@ -67,9 +68,9 @@ static SlabLaunch slab_launch(int N, int HW, int cv, int ctas_per_sm = 0) {
         for (int cand = 1; cand <= hi; ++cand) {
             const long long total = (long long)N * cand;
             const long long waves = (total + slots - 1) / slots;
-            double eff = (double)total / (double)(waves * slots);
-            if (total < slots) eff *= 0.5;                        // under one wave: idle SMs for the whole kernel
-            if (eff >= best - 1e-9) { best = eff; slabs = cand; }
+            const double eff = (double)total / (double)(waves * slots);
+            if (eff > best + 1e-9) { best = eff; slabs = cand; }
+            if (eff >= 0.92) { slabs = cand; break; }
         }
     }
     if (slabs > max_slabs) slabs = max_slabs;
@@ -83,8 +84,8 @@ static SlabLaunch slab_launch(int N, int HW, int cv, int ctas_per_sm = 0) {
 // once per CTA, a2 = rstd * (sum d*y - mean * sum d), so neither mean nor rstd occupies registers while streaming.
 // U = independent 16-byte row loads per tensor per thread in flight (x2 by the software pipeline): the kernels are bound by
 // memory-level parallelism, so registers are spent on loads in flight, not on per-channel constants.
-template <typename T, int U>
-__global__ void __launch_bounds__(256, U == 4 ? 2 : 3)
+template <typename T, int U, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
                         const float* __restrict__ stats, float* __restrict__ a1, float* __restrict__ a2,
                         int HW, int C, int groups, float eps, int slabs, int rows_per_block) {
@@ -144,8 +145,8 @@ adagn_bwd_reduce_kernel(const T* __restrict__ dout, long long ldd, const T* __re
 // With xh = (y - mean) * rstd the normalisation gradient is affine in (dout, y) per channel,
 //   dy = A*dout + B + Cc*y,  A = rstd*s*gamma,  Cc = -rstd^2*m2,  B = -rstd*m1 - Cc*mean,
 // so three constants per channel stay in registers instead of five.
-template <typename T, int U>
-__global__ void __launch_bounds__(256, U == 4 ? 2 : 3)
+template <typename T, int U, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ z, long long ldz,
                        const float* __restrict__ stats, const float* __restrict__ a1,
                        const float* __restrict__ a2, const float* __restrict__ s, long long s_bstride,
@@ -231,13 +232,15 @@ adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __res
     if (dbias) block_colsum_atomic<V>(db, red, C, c0, prow, rows_per_block, dbias);
 }
 
-// L2 blocking of the two passes (SDM_B200_BWD_L2_CHUNK_MB=<MiB>; 0 disables): both passes read dout and z, so running them over
-// groups of images whose (dout, z) fit in a share of the 126 MB L2 lets pass 2 hit L2 instead of HBM (10 -> 6 DRAM bytes per
-// element, the algorithmic minimum).  Images are independent in both kernels, so the result is unchanged.
+// L2 blocking of the two passes (SDM_B200_BWD_L2_CHUNK_MB=<MiB>, default 0 = off): both passes read dout and z, so running them
+// over groups of images whose (dout, z) fit in a share of the 126 MB L2 could let pass 2 hit L2 instead of HBM.  MEASURED on B200
+// (tools/bench_adagn_bwd.py, profiles/r02b_adagn_bwd_l2_chunk.log): it does not -- 32 / 64 / 96 MiB chunks are all SLOWER than the
+// unblocked passes (7.3 ms -> 11.5 / 11.0 / 9.9 ms per backward pass at 128x128, batch 32): the re-read still misses and the
+// extra, smaller launches cost more than they save.  Kept as a knob only.
 static int adagn_bwd_chunk_images(int N, long long bytes_per_image) {
     static const long long budget = [] {
         const char* e = getenv("SDM_B200_BWD_L2_CHUNK_MB");
-        return (e ? atoll(e) : 64LL) * (1LL << 20);
+        return (e ? atoll(e) : 0LL) * (1LL << 20);
     }();
     if (budget <= 0 || bytes_per_image <= 0) return N;
     if ((long long)N * bytes_per_image <= budget) return N;
@@ -249,19 +252,25 @@ static int adagn_bwd_chunk_images(int N, long long bytes_per_image) {
     return (int)nc;
 }
 
+template <typename T, int U, int OCC>
+static void adagn_bwd_launch2(int grid, int threads, size_t red_bytes, cudaStream_t st, const void* d_c, long long ldd,
+                              const void* z_c, long long ldz, const float* stats_c, float* a1, float* a2, const float* s_c,
+                              long long s_bstride, const float* gamma, const float* beta, float* ds_c, long long ds_bstride,
+                              float* dgamma, float* dbeta, void* dz_c, long long lddz, float* dbias, int HW, int C, int groups,
+                              float eps, int slabs, int rows_per_block) {
+    B2_LAUNCH((adagn_bwd_reduce_kernel<T, U, OCC>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, slabs, rows_per_block);
+    B2_LAUNCH((adagn_bwd_apply_kernel<T, U, OCC>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (T*)dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block);
+}
+#define ADAGN_BWD_ARGS grid, threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block
 template <typename T>
-static void adagn_bwd_launch(int U, int grid, int threads, size_t red_bytes, cudaStream_t st, const void* d_c, long long ldd,
+static void adagn_bwd_launch(int U, int occ, int grid, int threads, size_t red_bytes, cudaStream_t st, const void* d_c, long long ldd,
                              const void* z_c, long long ldz, const float* stats_c, float* a1, float* a2, const float* s_c,
                              long long s_bstride, const float* gamma, const float* beta, float* ds_c, long long ds_bstride,
                              float* dgamma, float* dbeta, void* dz_c, long long lddz, float* dbias, int HW, int C, int groups,
                              float eps, int slabs, int rows_per_block) {
-    if (U == 4) {
-        B2_LAUNCH((adagn_bwd_reduce_kernel<T, 4>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, slabs, rows_per_block);
-        B2_LAUNCH((adagn_bwd_apply_kernel<T, 4>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (T*)dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block);
-    } else {
-        B2_LAUNCH((adagn_bwd_reduce_kernel<T, 2>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, slabs, rows_per_block);
-        B2_LAUNCH((adagn_bwd_apply_kernel<T, 2>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (T*)dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block);
-    }
+    if (U == 4) adagn_bwd_launch2<T, 4, 2>(ADAGN_BWD_ARGS);
+    else if (occ == 3) adagn_bwd_launch2<T, 2, 3>(ADAGN_BWD_ARGS);
+    else adagn_bwd_launch2<T, 2, 2>(ADAGN_BWD_ARGS);
 }
 
 extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
@@ -277,6 +286,7 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
     const long long eb = dtype == 0 ? 2 : 4;
     const int chunk = adagn_bwd_chunk_images(N, 2LL * HW * C * eb);
     static const int u_env = [] { const char* e = getenv("SDM_B200_BWD_U"); return e ? atoi(e) : 0; }();
+    static const int occ_env = [] { const char* e = getenv("SDM_B200_BWD_OCC"); return e ? atoi(e) : 0; }();
     for (int n0 = 0; n0 < N; n0 += chunk) {
         const int nc = N - n0 < chunk ? N - n0 : chunk;
         // work: [2][N][C] fp32 (a1, a2), zeroed by the caller
@@ -291,13 +301,14 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
         // big images: four loads per tensor in flight (2 CTAs / SM at <= 128 registers); otherwise the two-load form (3 CTAs / SM)
         const int k0 = 256 / cv > 0 ? 256 / cv : 1;
         const int U = u_env == 2 || u_env == 4 ? u_env : ((long long)nc * HW / k0 >= 64LL * 2 * device_sm_count() ? 4 : 2);
-        const SlabLaunch sl = slab_launch(nc, HW, cv, U == 4 ? 2 : 3);
+        const int occ = U == 4 ? 2 : (occ_env == 3 ? 3 : 2);
+        const SlabLaunch sl = slab_launch(nc, HW, cv, occ);
         size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
         if (red_bytes < (size_t)groups * 2 * sizeof(float)) red_bytes = (size_t)groups * 2 * sizeof(float);
         if (dtype == 0)
-            adagn_bwd_launch<bf16>(U, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+            adagn_bwd_launch<bf16>(U, occ, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
         else
-            adagn_bwd_launch<float>(U, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+            adagn_bwd_launch<float>(U, occ, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
     }
     LAUNCH_CHECK("b2_adagn_bwd");
 }

@@ -14,7 +14,7 @@
 namespace b2 {
 
 constexpr int kTnEpiWarps = 8;
-constexpr int kTnThreads = 64 + kTnEpiWarps * 32 + 32;     // + a second TMA producer warp (warp 10)
+constexpr int kTnThreads = 64 + kTnEpiWarps * 32;          // warp 0: TMA producers (one lane per slab), warp 1: MMA issuer, 8 epilogue warps
 constexpr int kTnBK = 64;     // pixel rows per pipeline stage
 
 template <int BLOCK_N, int STAGES>
@@ -108,12 +108,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int k_boxes = p.kt_w * p.kt_h * p.kt_n;
     const uint32_t box_rows = static_cast<uint32_t>(p.wb * p.hb * p.nb);
 
-    if (warp == 0 || warp == kTnThreads / 32 - 1) {
-        // Two TMA producer warps: a stage is 2 + BLOCK_N/64 slab loads (one 128-byte-wide box each: the SWIZZLE_128B limit),
-        // and a single thread could not issue them fast enough to keep the 4-stage ring full (ncu: the producer sat on
-        // UTMALDG while the MMA warp starved).  Producer 0 takes the even slabs and posts the byte count, producer 1 the odd.
-        const int prod = warp == 0 ? 0 : 1;
-        if (lane == 0) {
+    if (warp == 0) {
+        // TMA producer WARP: a stage is 2 + BLOCK_N/64 slab loads (one 128-byte-wide box each: the SWIZZLE_128B limit) and lane L
+        // issues slab L of every stage.  One issuing thread could not keep the 4-stage ring full (ncu: the producer sat on UTMALDG
+        // while the MMA warp starved: tensor pipe 46 %); two threads reached 62 %; with one lane per slab the per-box issue
+        // latency overlaps across all boxes of a stage.  Lane 0 posts the stage's byte count -- the mbarrier's transaction count
+        // may go negative until it does, the phase cannot complete before that arrival.
+        constexpr int SLABS = A_SLABS + B_SLABS;
+        const bool mine = lane < SLABS && (CL == 1 || lane < A_SLABS || ((lane - A_SLABS) % CL) == crank);
+        if (lane < SLABS) {
             int s = 0; uint32_t ph = 0;
             for (int item = item0; item < total_items; item += item_step) {
                 const TnWork wk = decode(item);
@@ -128,32 +131,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
                     uint8_t* b_dst = a_dst + A_BYTES;
-                    if (prod == 0) mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
-                    const int bw = w0 + p.tap_dw[wk.tap];
-                    const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
-                    const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
-                    if constexpr (CL > 1) {
-                        // producer 0: this CTA's own A slabs; producer 1: its share of the B slabs, multicast to the pair
-                        if (prod == 0) {
-#pragma unroll
-                            for (int sl = 0; sl < A_SLABS; ++sl)
-                                tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
+                    if (lane == 0) mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
+                    if (mine) {
+                        if (lane < A_SLABS) {
+                            tma_load_4d(a_dst + lane * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + lane * SLAB, w0, h0, n0);
                         } else {
-#pragma unroll
-                            for (int sl = 0; sl < B_SLABS; ++sl) {
-                                if ((sl % CL) != crank) continue;
+                            const int sl = lane - A_SLABS;
+                            const int bw = w0 + p.tap_dw[wk.tap];
+                            const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
+                            const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
+                            if constexpr (CL > 1)
                                 tma_load_4d_mc(b_dst + sl * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + sl * SLAB, bw, bh, bn, kMask);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int sl = 0; sl < A_SLABS + B_SLABS; ++sl) {
-                            if ((sl & 1) != prod) continue;
-                            if (sl < A_SLABS)
-                                tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
                             else
-                                tma_load_4d(b_dst + (sl - A_SLABS) * SLAB_BYTES, &tmB, &full[s],
-                                            wk.nt_in_tap * BLOCK_N + (sl - A_SLABS) * SLAB, bw, bh, bn);
+                                tma_load_4d(b_dst + sl * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + sl * SLAB, bw, bh, bn);
                         }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
