@@ -23,10 +23,13 @@ extern "C" {
 const char* b2_last_error(void);
 int b2_version(void);
 
+/* Zero-fills `bytes` of device memory on `stream` (the flat gradient buffer before a backward pass; the reference's
+ * optimizer.zero_grad(), train_diffusion.py:317). */
+int b2_zero(void* ptr, long long bytes, void* stream);
 /* Deterministic mode (also SDM_B200_DETERMINISTIC=1): GroupNorm statistics from a fixed-order pass instead of the conv
  * epilogue's fp32 atomics and no split-K on the forward kernel, so an image's result is bitwise independent of batch size,
- * sharding and timing (sharded sampling == unsharded sampling).  Weight-gradient split-K is ordered
- * (bitwise repeatable) in every mode.  Returns 0. */
+ * sharding and timing (sharded sampling == unsharded sampling); the weight-gradient kernel's split-K becomes
+ * ordered (per-split partial tiles summed in split order: bitwise repeatable) instead of fp32 atomics.  Returns 0. */
 int b2_set_deterministic(int on);
 /* Optional split-K workspace for the tensor-core kernels: a device buffer (256-byte aligned, >= 2 MiB, ZEROED: each half
  * starts with 4 KiB of per-tile arrival counters) owned by the caller and registered for the CURRENT device (one per device).

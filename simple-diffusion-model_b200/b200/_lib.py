@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsdm_b200.so")
+# SDM_B200_LIB: an alternative build of the same library (kernel A/B runs from tools/); the product path is the in-tree one
+LIB_PATH = os.environ.get("SDM_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsdm_b200.so")
 
 _P, _I, _L, _F, _U, _D = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_ulonglong,
                           ctypes.c_double)
@@ -18,6 +19,7 @@ _P, _I, _L, _F, _U, _D = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctyp
 SIGNATURES = {
     "b2_set_workspace": [_P, _L],
     "b2_set_deterministic": [_I],
+    "b2_zero": [_P, _L, _P],
     "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
     "b2_conv3x3_first": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_conv3x3_last": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -122,7 +124,8 @@ def call(name, *args):
     handle = lib()
     if name in _WORKSPACE_USERS and torch.cuda.current_device() not in _WORKSPACE:
         _ensure_workspace()
-    LAUNCHES += 1
+    if name != "b2_zero":          # a memset node, not a kernel: not part of the gpu_launches claim
+        LAUNCHES += 1
     if _HOOK is not None:
         with _HOOK(name, args):
             rc = getattr(handle, name)(*args)

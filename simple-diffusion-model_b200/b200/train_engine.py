@@ -486,7 +486,7 @@ class UNetTrainEngine(UNetEngine):
         net = self.net
         dev = dout.device
         lay = self.grad_layout(dev)
-        lay.flat.zero_()
+        call("b2_zero", ptr(lay.flat), lay.flat.numel() * 4, stream())
         need = sum(2 * e[2][2].shape[0] * e[2][2].shape[3] + 2 * e[1][2].shape[0] * e[1][2].shape[3] + 8
                    for e in tape if e[0] == "res")
         self._work_arena, self._work_used = torch.zeros((max(need, 4),), dtype=torch.float32, device=dev), 0
@@ -631,6 +631,18 @@ class UNetTrainEngine(UNetEngine):
         ops.gemm_nt(dqkv, wp_t, rows, c, ldq, ldq, ldq, dx, c, residual=dout, ldr=ldd)
         return dx
 
+    def _ones(self, n, device):
+        """[n, 1] fp32 ones (column sums as a small GEMM), cached: nothing is allocated or filled inside a captured step."""
+        cache = getattr(self, "_ones_cache", None)
+        if cache is None:
+            cache = self._ones_cache = {}
+        key = (n, str(device))
+        if key not in cache:
+            if torch.cuda.is_current_stream_capturing():
+                return torch.ones((n, 1), dtype=torch.float32, device=device)
+            cache[key] = torch.ones((n, 1), dtype=torch.float32, device=device)
+        return cache[key]
+
     def _bwd_embedding(self, rec, ctx):
         (rec_t, rec_c, bt) = rec
         lay = self.layout
@@ -647,7 +659,8 @@ class UNetTrainEngine(UNetEngine):
             dw_all = torch.zeros((total, dim), dtype=torch.float32, device=dev)
             db_all = torch.zeros((total,), dtype=torch.float32, device=dev)
         ops.small_gemm(ds_all, emb, total, dim, be, total, dim, dw_all, dim, ta=1, tb=1, accumulate=True)
-        db_all.add_(ds_all.sum(dim=0)) if be > 1 else db_all.add_(ds_all[0])
+        # bias gradient = column sums of ds_all: the same kernel against a vector of ones (no ATen reduce + add in the step)
+        ops.small_gemm(ds_all, self._ones(be, dev), total, 1, be, total, 1, db_all, 1, ta=1, tb=1, accumulate=True)
         if not lay.dense_adagn:
             o = 0
             for m in mods:
@@ -665,7 +678,7 @@ class UNetTrainEngine(UNetEngine):
                 lin, h_in = lins[i], acts[i]
                 n_out, n_in = lin.weight.shape
                 ops.small_gemm(dy, h_in, n_out, n_in, b, n_out, n_in, lay.view(lin.weight), n_in, ta=1, tb=1, accumulate=True)
-                lay.view(lin.bias).add_(dy.sum(dim=0))
+                ops.small_gemm(dy, self._ones(b, dev), n_out, 1, b, n_out, 1, lay.view(lin.bias), 1, ta=1, tb=1, accumulate=True)
                 if i == 0:
                     break
                 dh = torch.empty((b, n_in), dtype=torch.float32, device=dev)

@@ -164,18 +164,28 @@ adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __res
     const int c0 = (threadIdx.x % cv) * V, prow = threadIdx.x / cv;
     const int cpg = C / groups;
     const float inv_cnt = 1.0f / ((float)cpg * (float)HW);
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gs[i] = 0.f;
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float x1 = a1[(long long)n * C + c], x2 = a2[(long long)n * C + c];
-        const float sc = __ldg(s + (long long)n * s_bstride + c), ga = __ldg(gamma + c);
-        if (slab == 0) {
-            atomicAdd(ds + (long long)n * ds_bstride + c, ga * x2 + (__ldg(beta + c) + 1.0f) * x1);
-            atomicAdd(dgamma + c, sc * x2);
-            atomicAdd(dbeta + c, sc * x1);
+    // group terms: warp w folds groups w, w + #warps, ...; lanes stride over the group's channels, shuffle reduction (the
+    // previous shared-memory atomics were a 32-way same-address pile-up per group and dominated the small deep layers)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int g = warp; g < groups; g += nwarps) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int j = lane; j < cpg; j += 32) {
+                const int c = g * cpg + j;
+                const float x1 = a1[(long long)n * C + c], x2 = a2[(long long)n * C + c];
+                const float sc = __ldg(s + (long long)n * s_bstride + c), ga = __ldg(gamma + c);
+                if (slab == 0) {
+                    atomicAdd(ds + (long long)n * ds_bstride + c, ga * x2 + (__ldg(beta + c) + 1.0f) * x1);
+                    atomicAdd(dgamma + c, sc * x2);
+                    atomicAdd(dbeta + c, sc * x1);
+                }
+                t1 = fmaf(sc * ga, x1, t1);
+                t2 = fmaf(sc * ga, x2, t2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o); }
+            if (lane == 0) { gs[g * 2] = t1; gs[g * 2 + 1] = t2; }
         }
-        atomicAdd(&gs[(c / cpg) * 2], sc * ga * x1);
-        atomicAdd(&gs[(c / cpg) * 2 + 1], sc * ga * x2);
     }
     __syncthreads();
     float A[V], B[V], Cc[V], db[V];
@@ -300,7 +310,10 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
         float* ds_c = ds ? ds + (long long)n0 * ds_bstride : nullptr;
         // big images: four loads per tensor in flight (2 CTAs / SM at <= 128 registers); otherwise the two-load form (3 CTAs / SM)
         const int k0 = 256 / cv > 0 ? 256 / cv : 1;
-        const int U = u_env == 2 || u_env == 4 ? u_env : ((long long)nc * HW / k0 >= 64LL * 2 * device_sm_count() ? 4 : 2);
+        // MEASURED (profiles/r02c_adagn_bwd_variants.log, 100 layers at 128x128 batch 32): U=4 / 2 CTAs per SM 5.35 ms,
+        // U=2 / 2 CTAs 5.61 ms, U=2 / 3 CTAs 6.36 ms
+        (void)k0;
+        const int U = u_env == 2 ? 2 : 4;
         const int occ = U == 4 ? 2 : (occ_env == 3 ? 3 : 2);
         const SlabLaunch sl = slab_launch(nc, HW, cv, occ);
         size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);

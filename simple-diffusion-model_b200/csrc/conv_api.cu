@@ -226,9 +226,50 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         (void)oeb;
         p.vec_ok = ok ? 1 : 0;
     }
-    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     int bn, splits;
     pick_tiling(Cout, m_tiles, p.groups, p.taps * p.kb_per_tap, !det, &bn, &splits);
+    // ---- halo mode (igemm.h): stride-1 3x3 convs with 128 / 256 input channels, whose 18 / 36 K steps per tile are too few to
+    // amortise re-fetching the A box once per tap.  SDM_B200_HALO=0 keeps the per-tap loads.
+    uint32_t a_box[4] = {(uint32_t)bk, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
+    {
+        static int halo_env = -1;
+        if (halo_env < 0) { const char* e = getenv("SDM_B200_HALO"); halo_env = e ? atoi(e) : 1; }
+        // MEASURED (profiles/r02g_halo_ab.log): with ONE 128-row tile per weights stage the halo kernel is slower than per-tap
+        // loads (C128 64x64 batch 256: 854 -> 700 TFLOP/s) although it moves 2x fewer bytes -- the main loop is bound by TMA
+        // latency x ring depth in STAGES, not by bytes.  What pays is doing twice the MMA work per weights stage: two 128-row
+        // sub-tiles per item (256 flattened positions), which needs 2 x 2 x BLOCK_N TMEM columns, i.e. BLOCK_N = 128 = Cout.
+        const bool shape_ok = mode == 0 && dtype == 0 && out_mode == 0 && (Cin == 128 || Cin == 256) && Cout == 128 &&
+                              W >= 16 && W + 1 <= 256;
+        if (halo_env && shape_ok) {
+            const int hbn = 128, msub = 2;
+            const int b_bytes = hbn * 128;
+            const int max_b = 6;
+            int halo, P = W + 1, BW, R;
+            long long tw, th;
+            int hb_dec = 1;
+            if (W == 128 && H % 2 == 0) { halo = 2; BW = 130; R = 4; tw = 1; th = H / 2; hb_dec = 2; }       // rows h, h+1 of one image
+            else { halo = 1; BW = P; R = (128 * msub + 2 * P + 1) / P + 2; tw = ((long long)H * P + 128 * msub - 1) / (128 * msub); th = 1; }
+            const int a_buf = ((BW * R * 128) + 1023) & ~1023;
+            const int avail = 227 * 1024 - 1024 - 256 - 2 * hbn * 4 - 1024;
+            // the weights ring first (a stage is 512 MMA cycles of work against ~2000+ cycles of TMA latency), then two A boxes
+            int b_stages = max_b;
+            int a_slots = (avail - b_stages * b_bytes) / a_buf;
+            while (a_slots < 2 && b_stages > 3) { --b_stages; a_slots = (avail - b_stages * b_bytes) / a_buf; }
+            if (a_slots > 4) a_slots = 4;
+            const long long h_tiles = tw * th * N;
+            if (a_slots >= 2 && b_stages >= 3 && BW <= 256 && R <= 256 && h_tiles >= device_sm_count()) {
+                p.halo = halo; p.halo_P = P; p.halo_BW = BW; p.halo_R = R; p.halo_msub = msub;
+                p.a_buf_bytes = a_buf; p.a_slots = a_slots; p.b_stages = b_stages;
+                p.halo_bar_off = a_slots * a_buf + b_stages * b_bytes;
+                p.wb = halo == 1 ? 128 * msub : 128; p.hb = hb_dec; p.nb = 1;
+                p.tiles_w = (int)tw; p.tiles_h = (int)th; p.tiles_n = N;
+                m_tiles = h_tiles;
+                bn = hbn; splits = 1;
+                a_box[1] = (uint32_t)BW; a_box[2] = (uint32_t)R; a_box[3] = 1;
+            }
+        }
+    }
     p.n_tiles = (Cout + bn - 1) / bn;
     p.b_mode = 0;
     p.splits = splits; p.ws = workspace(0).ws; p.ws_counters = workspace(0).counters;
@@ -238,8 +279,7 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)a_images};
         uint64_t str[3] = {(uint64_t)ldx * eb, (uint64_t)W * ldx * eb, (uint64_t)H * W * ldx * eb};
-        uint32_t box[4] = {(uint32_t)bk, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
-        if (make_tmap_4d(&ta, x, eb, dims, str, box)) return 1;
+        if (make_tmap_4d(&ta, x, eb, dims, str, a_box)) return 1;
     }
     {
         const uint64_t ktot = (uint64_t)p.taps * Cin;
@@ -445,11 +485,14 @@ static void tn_pick_splits(GemmTnParams* p, int batches, int bn) {
         }
     }
     p->splits = best_s;
-    // ordered (bitwise repeatable) split-K through the TN half of the workspace, unless SDM_B200_TN_SPLITK=atomic
+    // Split-K reduction of the weight gradients.  Default: fp32 vector atomics straight into the gradient buffer.  Ordered
+    // (bitwise repeatable: per-split partial tiles, the last arriver sums them in split order) in deterministic mode or with
+    // SDM_B200_TN_SPLITK=ordered: MEASURED 10 % slower over the weight gradients of a 128x128 batch-32 step (24.5 vs 22.3 ms;
+    // up to 1.6x on the small deep layers, where the hand-off latency is not hidden), hence opt-in.
     p->ws = nullptr; p->ws_counters = nullptr;
-    static int atomic_mode = -1;
-    if (atomic_mode < 0) { const char* e = getenv("SDM_B200_TN_SPLITK"); atomic_mode = (e && !strcmp(e, "atomic")) ? 1 : 0; }
-    if (p->out_mode == 0 && best_s > 1 && !atomic_mode) {
+    static int ordered_env = -1;
+    if (ordered_env < 0) { const char* e = getenv("SDM_B200_TN_SPLITK"); ordered_env = (e && !strcmp(e, "ordered")) ? 1 : 0; }
+    if (p->out_mode == 0 && best_s > 1 && (ordered_env || deterministic_mode())) {
         const Workspace& w = workspace(1);
         if (w.ws && base <= 1024) {
             int s = best_s;

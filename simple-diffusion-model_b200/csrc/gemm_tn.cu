@@ -14,7 +14,11 @@
 namespace b2 {
 
 constexpr int kTnEpiWarps = 8;
-constexpr int kTnThreads = 64 + kTnEpiWarps * 32;          // warp 0: TMA producers (one lane per slab), warp 1: MMA issuer, 8 epilogue warps
+#ifndef TN_PRODUCERS
+#define TN_PRODUCERS 3
+#endif
+constexpr int kTnMaxProducers = TN_PRODUCERS;             // TMA producer warps (slab sl is issued by producer sl % TN_PRODUCERS); measured 2 / 3 / 6: 927 / 953 / 906 TFLOP/s
+constexpr int kTnThreads = 64 + kTnEpiWarps * 32 + (kTnMaxProducers - 1) * 32;   // warp 0 + warps 10.. : TMA producers, warp 1: MMA issuer, warps 2..9: epilogue
 constexpr int kTnBK = 64;     // pixel rows per pipeline stage
 
 template <int BLOCK_N, int STAGES>
@@ -41,7 +45,9 @@ __device__ __forceinline__ TnWork tn_decode(const GemmTnParams& p, int item) {
 // T = bf16: 64 elements per 128-byte slab row; T = float (tf32): 32 elements per slab row.
 // CL == 2: the two CTAs of a cluster take M tiles 2q and 2q+1 of the same (split, N tile, tap); the B slabs of a stage are
 // identical for them, so each fetches half of the slabs and TMA-multicasts them to both (same scheme as igemm_nt.cu).
-template <typename T, int BLOCK_N, int STAGES, int CL>
+// ORDERED: a separate instantiation, so that the default (atomic) kernel carries none of the ordered epilogue's code or
+// registers (measured: the mere presence of the branch cost the atomic path 6 %).
+template <typename T, int BLOCK_N, int STAGES, int CL, bool ORDERED = false>
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmTnParams p) {
@@ -108,15 +114,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int k_boxes = p.kt_w * p.kt_h * p.kt_n;
     const uint32_t box_rows = static_cast<uint32_t>(p.wb * p.hb * p.nb);
 
-    if (warp == 0) {
-        // TMA producer WARP: a stage is 2 + BLOCK_N/64 slab loads (one 128-byte-wide box each: the SWIZZLE_128B limit) and lane L
-        // issues slab L of every stage.  One issuing thread could not keep the 4-stage ring full (ncu: the producer sat on UTMALDG
-        // while the MMA warp starved: tensor pipe 46 %); two threads reached 62 %; with one lane per slab the per-box issue
-        // latency overlaps across all boxes of a stage.  Lane 0 posts the stage's byte count -- the mbarrier's transaction count
-        // may go negative until it does, the phase cannot complete before that arrival.
-        constexpr int SLABS = A_SLABS + B_SLABS;
-        const bool mine = lane < SLABS && (CL == 1 || lane < A_SLABS || ((lane - A_SLABS) % CL) == crank);
-        if (lane < SLABS) {
+    if (warp == 0 || warp >= 2 + kTnEpiWarps) {
+        // TMA producer warps (lane 0 of each): a stage is 2 + BLOCK_N/64 slab loads (one 128-byte-wide box each: the
+        // SWIZZLE_128B limit), and a single thread could not issue them fast enough to keep the 4-stage ring full (ncu: the
+        // producer sat on UTMALDG while the MMA warp starved).  Producer q takes the slabs sl with sl % n_prod == q; producer 0
+        // posts the stage's byte count.  MEASURED alternative, rejected: one warp issuing one slab per LANE ran 40 % slower
+        // (wgrad 970 -> 600 TFLOP/s at batch 32) -- TMA issue from several lanes of one warp serialises.
+        constexpr int n_prod = kTnMaxProducers;       // compile-time: a runtime count put an integer division per slab into the issue loop (-35 %)
+        const int prod = warp == 0 ? 0 : warp - (2 + kTnEpiWarps) + 1;
+        if (prod < n_prod) {       // warp-uniform loop: all lanes wait, one elected lane issues (ptx.cuh: elect_one)
             int s = 0; uint32_t ph = 0;
             for (int item = item0; item < total_items; item += item_step) {
                 const TnWork wk = decode(item);
@@ -131,28 +137,41 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
                     uint8_t* b_dst = a_dst + A_BYTES;
-                    if (lane == 0) mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
-                    if (mine) {
-                        if (lane < A_SLABS) {
-                            tma_load_4d(a_dst + lane * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + lane * SLAB, w0, h0, n0);
+                    const int bw = w0 + p.tap_dw[wk.tap];
+                    const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
+                    const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
+                    if (elect_one()) {
+                    if (prod == 0) mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
+#pragma unroll
+                    for (int sl = 0; sl < A_SLABS + B_SLABS; ++sl) {
+                        if ((sl % n_prod) != prod) continue;
+                        if (sl < A_SLABS) {
+                            tma_load_4d(a_dst + sl * SLAB_BYTES, &tmA, &full[s], wk.mt * 128 + sl * SLAB, w0, h0, n0);
                         } else {
-                            const int sl = lane - A_SLABS;
-                            const int bw = w0 + p.tap_dw[wk.tap];
-                            const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
-                            const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
-                            if constexpr (CL > 1)
-                                tma_load_4d_mc(b_dst + sl * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + sl * SLAB, bw, bh, bn, kMask);
-                            else
-                                tma_load_4d(b_dst + sl * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + sl * SLAB, bw, bh, bn);
+                            const int bs = sl - A_SLABS;
+                            if constexpr (CL > 1) {
+                                // each CTA of the pair fetches half of the B slabs and multicasts them to both
+                                if ((bs % CL) != crank) continue;
+                                tma_load_4d_mc(b_dst + bs * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + bs * SLAB, bw, bh, bn, kMask);
+                            } else {
+                                tma_load_4d(b_dst + bs * SLAB_BYTES, &tmB, &full[s], wk.nt_in_tap * BLOCK_N + bs * SLAB, bw, bh, bn);
+                            }
                         }
                     }
+                    }
+                    __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            // warp-uniform issue loop (ptx.cuh: elect_one): all lanes wait and compute the descriptors, one elected lane issues
             constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 1, 1);
+            // bf16: 8-row atoms (1024 B) of 16-byte chunks; tf32: 4-row atoms (512 B) of 32-byte chunks
+            const uint64_t desc0 = umma_desc_sw128(0, SLAB_BYTES, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
+            const uint32_t smem0 = smem_u32(smem);
+            constexpr uint32_t K_STEP = (UMMA_K * 128) >> 4;                 // descriptor units (16 B) per MMA K step
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             const int k_steps = (int)(box_rows + UMMA_K - 1) / UMMA_K;      // rows beyond the box are never touched
@@ -166,18 +185,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + A_BYTES;
-                    for (int k = 0; k < k_steps; ++k) {
-                        // bf16: 8-row atoms (1024 B) of 16-byte chunks; tf32: 4-row atoms (512 B) of 32-byte chunks
-                        const uint64_t ad = umma_desc_sw128(a_addr + k * UMMA_K * 128, SLAB_BYTES, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
-                        const uint64_t bd = umma_desc_sw128(b_addr + k * UMMA_K * 128, SLAB_BYTES, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
-                        umma_ss<kTF32>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    const uint64_t ad0 = desc0 + ((smem0 + s * STAGE_BYTES) >> 4);
+                    const uint64_t bd0 = ad0 + (A_BYTES >> 4);
+                    if (elect_one()) {
+                        constexpr int MAX_K = kTnBK / UMMA_K;
+#pragma unroll
+                        for (int k = 0; k < MAX_K; ++k)
+                            if (k < k_steps) umma_ss<kTF32>(d_tmem, ad0 + k * K_STEP, bd0 + k * K_STEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
                     }
-                    if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
+                    __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                if (elect_one()) umma_commit(&tfull[acc]);
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             }
         }
@@ -185,7 +206,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int epi_tid = threadIdx.x - 64;
-        const bool ordered = p.out_mode == 0 && p.splits > 1 && p.ws != nullptr;
+        constexpr bool ordered = ORDERED;
         int acc = 0; uint32_t acc_ph = 0;
         for (int item = item0; item < total_items; item += item_step) {
             const TnWork wk = decode(item);
@@ -196,7 +217,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
-            if (ordered) {
+            if constexpr (ordered) {
                 // ---- ordered split-K: publish this split's partial tile, then only the split that arrives last reduces
                 // (never batched, so the tile index is the item index without its split digit -- also in cluster mode, where
                 // the two CTAs of a pair see the same item but different M tiles: give each its own tile id)
@@ -336,13 +357,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <typename T, int BLOCK_N, int STAGES, int CL>
+template <typename T, int BLOCK_N, int STAGES, int CL, bool ORDERED = false>
 static int launch_tn_cfg(const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int num_sms, cudaStream_t st) {
     constexpr int SLAB = 128 / sizeof(T);
     constexpr int stage_bytes = (128 / SLAB + BLOCK_N / SLAB) * kTnBK * 128;
     constexpr int total = STAGES * stage_bytes + (2 * STAGES + 4) * 8 + 16 + 1024;
     static_assert(total <= 227 * 1024, "shared memory budget");
-    auto kern = gemm_tn_kernel<T, BLOCK_N, STAGES, CL>;
+    auto kern = gemm_tn_kernel<T, BLOCK_N, STAGES, CL, ORDERED>;
     static bool attr_set = false;
     static int max_clusters = 0;
     cudaLaunchConfig_t cfg = {};
@@ -393,6 +414,19 @@ static int launch_tn_cfg(const CUtensorMap& a, const CUtensorMap& b, const GemmT
 int launch_gemm_tn(int dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int block_n, cudaStream_t st) {
     const int sms = device_sm_count();
     const bool pair = p.cluster == 2 && !p.batch_mode && p.m_tiles % 2 == 0 && dtype == 0 && block_n >= 128;
+    const bool ordered = p.out_mode == 0 && p.splits > 1 && p.ws != nullptr;
+    if (ordered) {          // opt-in (deterministic mode): unclustered kernels only
+        if (dtype == 0) {
+            if (block_n == 256) return launch_tn_cfg<__nv_bfloat16, 256, 4, 1, true>(a, b, p, sms, st);
+            if (block_n == 128) return launch_tn_cfg<__nv_bfloat16, 128, 6, 1, true>(a, b, p, sms, st);
+            if (block_n == 64)  return launch_tn_cfg<__nv_bfloat16, 64, 8, 1, true>(a, b, p, sms, st);
+        } else {
+            if (block_n == 128) return launch_tn_cfg<float, 128, 3, 1, true>(a, b, p, sms, st);
+            if (block_n == 64)  return launch_tn_cfg<float, 64, 4, 1, true>(a, b, p, sms, st);
+            if (block_n == 32)  return launch_tn_cfg<float, 32, 5, 1, true>(a, b, p, sms, st);
+        }
+        return set_error("gemm_tn: unsupported block_n %d for dtype %d", block_n, dtype);
+    }
     if (dtype == 0) {
         if (pair) {
             if (block_n == 256) return launch_tn_cfg<__nv_bfloat16, 256, 4, 2>(a, b, p, sms, st);

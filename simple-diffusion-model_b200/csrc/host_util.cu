@@ -90,3 +90,11 @@ bool deterministic_mode() {
 void set_deterministic_mode(int on) { g_det = on ? 1 : 0; }
 
 }  // namespace b2
+
+// Zero-fill of a device range on `stream` (the flat gradient buffer at the start of every backward pass): a memset node, no kernel.
+extern "C" int b2_zero(void* ptr, long long bytes, void* stream) {
+    if (!ptr || bytes <= 0) return 0;
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return b2::set_error("b2_zero: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -45,6 +45,21 @@ struct IgemmParams {
     long long vN, vH, vW;
     float* gn_stats;             // optional [N][Cout/cpg][2] (sum, sum of squares), accumulated atomically
     int cpg;                     // channels per GroupNorm group
+    // Halo mode (3x3 stride-1 convs with few input channels: Cin = 128 / 256, whose K loop is too short to amortise the operand
+    // traffic).  Instead of re-fetching the 128-pixel A box once per filter tap (9x), ONE box per 64-channel block is fetched
+    // that covers the tile plus its halo, and every tap reads it through a descriptor whose start address is shifted by whole
+    // 128-byte rows (the SWIZZLE_128B pattern is a function of the absolute shared-memory address, so a row shift is legal:
+    // tools/exp_halo_desc.cu).  For the shift to be uniform the M tile is a run of 128 consecutive positions of a FLATTENED
+    // image with one shared zero column per row (pitch P = W + 1: position f = h*P + w, w == W is the pad, produced by TMA's
+    // out-of-bounds fill and skipped by the epilogue), halo = 1: tiles_w = ceil(H*P / 128), wb = 128;
+    // or, for W % 128 == 0, one 128-pixel run of one image row, halo = 2 (box 130 x 3 rows, no pad positions).
+    int halo;                    // 0 off, 1 flattened, 2 row-aligned
+    int halo_P;                  // flattened pitch W + 1 (halo 1)
+    int halo_msub;               // 128-row sub-tiles per work item (2: both share every weights stage; BLOCK_N = 128 only)
+    int halo_BW, halo_R;         // A box: BW columns x R rows of pixels (x 64 channels); shared-memory row = (h - h_lo)*BW + (w - w_lo)
+    int a_buf_bytes, a_slots;    // A buffers (one box each), 1024-byte multiples
+    int b_stages;                // depth of the B (weights) ring, <= the kernel's STAGES
+    int halo_bar_off;            // byte offset of the barrier block behind the A buffers and the B ring
 };
 
 // C[m, n] (+)= alpha * sum_k A[k, m] * B[k + tap shift, n]  -- both operands MN-major ("TN" GEMM).

@@ -108,7 +108,11 @@ __device__ __forceinline__ void gn_partial(const float (&v)[32], bool valid, boo
 // CL > 1: thread-block cluster of CL CTAs that work on CL consecutive M tiles of the SAME N tile.  The B (weight) tile
 // of every K step is identical for them, so each CTA fetches 1/CL of it and TMA-multicasts that piece to all: the L2 -> SM
 // operand traffic per CTA drops from A + B to A + B/CL (the main loop is bound by exactly that traffic, not by the MMA).
-template <typename T, int BLOCK_N, int STAGES, int CL>
+// HALO: see IgemmParams::halo -- the A operand of a tile is ONE box per 64-channel block (tile + halo) that all 9 taps read
+// through row-shifted descriptors; B (weights) streams through a ring of p.b_stages stages, one stage per (channel block, tap).
+constexpr int kMaxASlots = 4;
+
+template <typename T, int BLOCK_N, int STAGES, int CL, bool HALO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ IgemmParams p) {
@@ -117,16 +121,25 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                  : (2 * BLOCK_N <= 256) ? 256 : 512;
     static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+    // HALO, BLOCK_N = 128: an item is TWO 128-row sub-tiles (p.halo_msub = 2) that share every weights stage, i.e. an accumulator
+    // stage is 2 x 128 columns and both stages fill the 512 TMEM columns
+    constexpr uint32_t TMEM_ALLOC = HALO ? 512u : TMEM_COLS;
+    const int msub = HALO ? p.halo_msub : 1;
+    const int acc_cols = msub * BLOCK_N;                 // TMEM columns of one accumulator stage
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint8_t* bar_base = HALO ? smem + p.halo_bar_off : smem + S::BAR_OFF;
+    uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
     volatile int* flag_s = reinterpret_cast<volatile int*>(tmem_holder + 1);      // split-K: arrival order of this CTA's split
-    float* bias_s = reinterpret_cast<float*>(smem + S::BIAS_OFF);
+    uint64_t* afull = tempty + 3;                                                   // HALO: A-buffer barriers
+    uint64_t* aempty = afull + kMaxASlots;
+    float* bias_s = HALO ? reinterpret_cast<float*>(bar_base + 256) : reinterpret_cast<float*>(smem + S::BIAS_OFF);
+    uint8_t* b_ring = smem + (HALO ? p.a_slots * p.a_buf_bytes : 0);                // HALO: weights ring behind the A buffers
 
     pdl_launch_dependents();               // the next kernel may be scheduled (and run its prologue) while this one works
     const int warp = threadIdx.x >> 5;
@@ -138,9 +151,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // a stage may be refilled (by multicasts from every CTA of the cluster) once ALL CL consumers released it
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
+        if constexpr (HALO) for (int i = 0; i < kMaxASlots; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_holder);
+    if (warp == 1) tmem_alloc<TMEM_ALLOC>(tmem_holder);
     tc_fence_before();
     __syncthreads();
     if constexpr (CL > 1) cluster_sync_all();          // peers' barriers are initialised before anyone signals them
@@ -180,7 +194,58 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // One thread issuing both boxes of every stage could not keep the ring full on the short-K layers (ncu source
         // sampling: the producer sat on UTMALDG while the MMA warp waited for data; same finding as in gemm_tn.cu).
         const bool load_a = warp == 0;
-        if (lane == 0) {
+        if constexpr (HALO) {
+            if (load_a) {
+                // ---- A: one box per (tile, 64-channel block): the tile's 128 positions plus their halo
+                // (producer loops are warp-uniform too: all lanes wait, one elected lane issues -- coordinates stay uniform)
+                int slot = 0; uint32_t aph = 0;
+                const uint32_t box_bytes = static_cast<uint32_t>(p.halo_BW * p.halo_R) * 128u;
+                for (int item = item0; item < total_tiles; item += item_step) {
+                    const TileCoord tc = decode_tile_cl<CL>(p, tile_of(item), m_groups);
+                    int w_lo, h_lo;
+                    if (p.halo == 1) {                    // flattened: rows floor((f0 - P - 1) / P) .. of the image, all P columns
+                        const int t = tc.w0 - p.halo_P - 1;
+                        h_lo = t >= 0 ? t / p.halo_P : -((-t + p.halo_P - 1) / p.halo_P);
+                        w_lo = 0;
+                    } else {                              // row-aligned: rows h-1 .. h+1, columns w0-1 .. w0+128
+                        h_lo = tc.h0 - 1; w_lo = tc.w0 - 1;
+                    }
+                    for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+                        mbar_wait(&aempty[slot], aph ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&afull[slot], box_bytes);
+                            tma_load_4d(smem + slot * p.a_buf_bytes, &tmA, &afull[slot], cb * 64, w_lo, h_lo, tc.n0);
+                        }
+                        __syncwarp();
+                        if (++slot == p.a_slots) { slot = 0; aph ^= 1; }
+                    }
+                }
+            } else {
+                // ---- B: one stage per (64-channel block, tap), K coordinate tap*Cin + cb*64 of the packed weights
+                int s = 0; uint32_t ph = 0;
+                for (int item = item0; item < total_tiles; item += item_step) {
+                    const TileCoord tc = decode_tile_cl<CL>(p, tile_of(item), m_groups);
+                    for (int cb = 0; cb < p.kb_per_tap; ++cb)
+                        for (int t = 0; t < 9; ++t) {
+                            const int it = t * p.kb_per_tap + cb;
+                            mbar_wait(&empty[s], ph ^ 1);
+                            uint8_t* b_dst = b_ring + s * S::B_BYTES;
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&full[s], S::B_BYTES);
+                                if constexpr (CL > 1) {
+                                    constexpr int PIECE = BLOCK_N / CL;
+                                    tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], it * 64, tc.nt * BLOCK_N + crank * PIECE, 0, 0, kMask);
+                                } else {
+                                    tma_load_4d(b_dst, &tmB, &full[s], it * 64, tc.nt * BLOCK_N, 0, 0);
+                                }
+                            }
+                            __syncwarp();
+                            if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                        }
+                }
+            }
+        } else
+        {
             int s = 0; uint32_t ph = 0;
             for (int item = item0; item < total_tiles; item += item_step) {
                 const int split = CL > 1 ? 0 : item % splits;
@@ -195,24 +260,85 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + S::A_BYTES;
-                    if (load_a) {
-                        mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
-                        tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
-                    } else if constexpr (CL > 1) {
-                        constexpr int PIECE = BLOCK_N / CL;         // rows of the B tile this CTA fetches for the whole cluster
-                        tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N + crank * PIECE,
-                                       bb2, bb3, kMask);
-                    } else {
-                        tma_load_4d(b_dst, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N, bb2, bb3);
+                    if (elect_one()) {
+                        if (load_a) {
+                            mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
+                            tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
+                        } else if constexpr (CL > 1) {
+                            constexpr int PIECE = BLOCK_N / CL;         // rows of the B tile this CTA fetches for the whole cluster
+                            tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N + crank * PIECE,
+                                           bb2, bb3, kMask);
+                        } else {
+                            tma_load_4d(b_dst, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N, bb2, bb3);
+                        }
                     }
+                    __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        if constexpr (HALO) {
+            {
+                constexpr uint32_t idesc = umma_idesc(1u, 128, BLOCK_N, 0, 0);
+                const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);          // descriptor without its address field
+                const uint32_t smem0 = smem_u32(smem);
+                const uint32_t ring0 = smem_u32(b_ring);
+                int s = 0; uint32_t ph = 0;
+                int slot = 0; uint32_t aph = 0;
+                int acc = 0; uint32_t acc_ph = 0;
+                for (int item = item0; item < total_tiles; item += item_step) {
+                    const TileCoord tc = decode_tile_cl<CL>(p, tile_of(item), m_groups);
+                    int row0;                              // shared-memory row of the tile's position 0 under the centre tap
+                    if (p.halo == 1) {
+                        const int t = tc.w0 - p.halo_P - 1;
+                        const int h_lo = t >= 0 ? t / p.halo_P : -((-t + p.halo_P - 1) / p.halo_P);
+                        row0 = tc.w0 - h_lo * p.halo_P;
+                    } else {
+                        row0 = p.halo_BW + 1;
+                    }
+                    mbar_wait(&tempty[acc], acc_ph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                    const uint32_t sub_rows = p.halo == 1 ? 128u : static_cast<uint32_t>(p.halo_BW);   // rows between the two sub-tiles
+                    for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+                        mbar_wait(&afull[slot], aph);
+                        tc_fence_after();
+                        const uint32_t a_base = smem0 + slot * p.a_buf_bytes;
+                        for (int t = 0; t < 9; ++t) {
+                            const int dh = t / 3 - 1, dw = t % 3 - 1;
+                            mbar_wait(&full[s], ph);
+                            tc_fence_after();
+                            const uint64_t ad0 = desc0 + ((a_base + static_cast<uint32_t>(row0 + dh * p.halo_BW + dw) * 128u) >> 4);
+                            const uint64_t bd0 = desc0 + ((ring0 + s * S::B_BYTES) >> 4);
+                            if (elect_one()) {
+                                for (int sub = 0; sub < msub; ++sub) {            // the sub-tiles share this weights stage
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_ss<false>(d_tmem + sub * BLOCK_N, ad0 + sub * (sub_rows * 8u) + 2 * k, bd0 + 2 * k, idesc,
+                                                       (cb > 0 || t > 0 || k != 0) ? 1u : 0u);
+                                }
+                                if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
+                            }
+                            __syncwarp();
+                            if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                        }
+                        if (elect_one()) umma_commit(&aempty[slot]);          // every MMA that read this box has completed
+                        __syncwarp();
+                        if (++slot == p.a_slots) { slot = 0; aph ^= 1; }
+                    }
+                    if (elect_one()) umma_commit(&tfull[acc]);
+                    __syncwarp();
+                    if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                }
+            }
+        } else
+        {
+            // warp-uniform issue loop (see elect_one): all lanes wait and compute, one elected lane issues
             constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, 0);
+            const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);              // descriptor without its address field
+            const uint32_t smem0 = smem_u32(smem);
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             for (int item = item0; item < total_tiles; item += item_step) {
@@ -224,18 +350,19 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int it = it0; it < it1; ++it) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + S::A_BYTES;
+                    const uint64_t ad0 = desc0 + ((smem0 + s * S::STAGE_BYTES) >> 4);
+                    const uint64_t bd0 = ad0 + (S::A_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_ss<kTF32>(d_tmem, ad, bd, idesc, (it > it0 || k != 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)
+                            umma_ss<kTF32>(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (it > it0 || k != 0) ? 1u : 0u);
+                        if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
                     }
-                    if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
+                    __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                if (elect_one()) umma_commit(&tfull[acc]);
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             }
         }
@@ -251,17 +378,28 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int G = p.gn_stats ? (p.Cout / p.cpg) : 0;
         const bool f32out = kTF32 || p.out_fp32;
         int acc = 0; uint32_t acc_ph = 0;
-        for (int item = item0; item < total_tiles; item += item_step) {
+        for (int item = item0; item < total_tiles; item += item_step)
+        for (int sub = 0; sub < msub; ++sub) {
             const int tile = tile_of(item);
-            const TileCoord tc = decode_tile_cl<CL>(p, tile, m_groups);
-            const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
+            TileCoord tc = decode_tile_cl<CL>(p, tile, m_groups);
+            if (HALO && sub) { if (p.halo == 1) tc.w0 += 128; else tc.h0 += 1; }      // second 128-row sub-tile of the item
+            const uint32_t acc_col = static_cast<uint32_t>(acc * acc_cols + sub * BLOCK_N);
+            int w = tc.w0 + w_in, h = tc.h0 + h_in;
+            const int n = tc.n0 + n_in;
+            if (HALO && p.halo == 1) {                  // flattened position f = h*P + w; w == W is the shared pad column
+                const int f = w;
+                h = f / p.halo_P;
+                w = f - h * p.halo_P;
+            }
             const bool valid = (n_in < p.nb) && (w < p.W) && (h < p.H) && (n < p.N);
             const long long o_off = n * p.oN + h * p.oH + w * p.oW + p.goff[tc.g];
             const long long r_off = n * p.rN + h * p.rH + w * p.rW;
             const int n_lane0 = __shfl_sync(0xffffffffu, n, 0);
-            const bool uniform = __all_sync(0xffffffffu, n == n_lane0 || !valid) && __shfl_sync(0xffffffffu, (int)valid, 0);
+            // HALO: a tile never leaves its image, so the warp-wide reduction is always legal (pad positions contribute zeros)
+            const bool uniform = HALO ? (n_lane0 < p.N)
+                                      : (__all_sync(0xffffffffu, n == n_lane0 || !valid) && __shfl_sync(0xffffffffu, (int)valid, 0));
             // stage this tile's bias slice once (all epilogue warps), then meet at a named barrier
-            float* bs = bias_s + acc * BLOCK_N;
+            float* bs = bias_s + (acc & 1) * BLOCK_N;
             if (epi_tid < BLOCK_N) {
                 const int c = tc.nt * BLOCK_N + epi_tid;
                 bs[epi_tid] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
@@ -280,7 +418,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
                     if (tc.nt * BLOCK_N + ch * 32 >= p.Cout) break;
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + ch * 32, r);
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
@@ -310,7 +448,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // softmax over the QUERY axis (custom_layers.py:147) is a purely in-thread reduction over TMEM columns.
                 if (half == 0) {
                     const int ncols_tile = min(BLOCK_N, p.Cout - tc.nt * BLOCK_N);
-                    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+                    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col;
                     // exp(x) = exp2(x * log2 e).  The scaled score is rounded ONCE (__fmul_rn, never contracted into an FMA
                     // with the subtraction): the row maximum must map to exactly exp2(0) even for logits of 1e14, which
                     // the first DDIM steps of the cosine schedule produce on an untrained net (1/sqrt(abar_T) = 2e7).
@@ -397,7 +535,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         r[4 * i + 2] = __float_as_uint(a4[i].z); r[4 * i + 3] = __float_as_uint(a4[i].w);
                     }
                 } else {
-                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + ch * 32, r);
                     tmem_ld_wait();
                 }
                 const int ncols = min(32, p.Cout - col0);
@@ -518,8 +656,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (splits > 1) continue;                 // accumulator already released right after the partials were published
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            if (sub == msub - 1) {                    // the accumulator stage is free once its last sub-tile has been read
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
         }
     }
 
@@ -528,20 +668,24 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if constexpr (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / signal its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        tmem_dealloc<TMEM_ALLOC>(tmem_base);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <typename T, int BLOCK_N, int STAGES, int CL>
+template <typename T, int BLOCK_N, int STAGES, int CL, bool HALO = false>
 static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& p, int num_sms, cudaStream_t st) {
     using S = IgemmSmem<BLOCK_N, STAGES>;
-    auto kern = igemm_nt_kernel<T, BLOCK_N, STAGES, CL>;
+    auto kern = igemm_nt_kernel<T, BLOCK_N, STAGES, CL, HALO>;
     static bool attr_set = false;
     static int max_clusters = 0;
+    constexpr int kHaloMax = 227 * 1024;               // halo mode sizes its buffers per layer: opt in to the maximum once
+    const int smem_bytes = HALO ? p.halo_bar_off + 256 + 2 * BLOCK_N * 4 + 1024 : S::TOTAL;
+    if (HALO && (smem_bytes > kHaloMax || p.b_stages > STAGES || p.a_slots > kMaxASlots || p.a_slots < 1 || p.b_stages < 2))
+        return set_error("igemm_nt (halo): buffers do not fit (%d bytes, %d A slots, %d B stages)", smem_bytes, p.a_slots, p.b_stages);
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attrs[2];
     int na = 0;
@@ -558,7 +702,7 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmPar
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO ? kHaloMax : S::TOTAL);
         if (e != cudaSuccess) return set_error("igemm_nt: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         if (CL > 1) {
             // clusters must sit inside one GPC: ask how many fit on this device with one 200 KB CTA per SM
@@ -591,6 +735,14 @@ int launch_igemm_nt(int dtype /*0 bf16, 1 fp32(tf32)*/, const CUtensorMap& a, co
     const int sms = device_sm_count();
     const int cl = p.cluster > 1 ? p.cluster : 1;
     if (cl > 1 && (p.splits != 1 || p.b_mode || p.act == 4)) return set_error("igemm_nt: cluster multicast needs an unsplit, unbatched GEMM");
+    if (p.halo) {
+        if (dtype != 0 || p.splits != 1 || p.b_mode || p.taps != 9) return set_error("igemm_nt (halo): bf16 3x3 stride-1 convolutions only");
+        if (cl == 1 && block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 1, true>(a, b, p, sms, st);
+        if (cl == 1 && block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 1, true>(a, b, p, sms, st);
+        if (cl == 2 && block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 2, true>(a, b, p, sms, st);
+        if (cl == 2 && block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 2, true>(a, b, p, sms, st);
+        return set_error("igemm_nt (halo): unsupported block_n %d / cluster %d", block_n, cl);
+    }
     if (dtype == 0) {
         if (cl == 1) {
             if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 1>(a, b, p, sms, st);

@@ -151,6 +151,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
     d |= static_cast<uint64_t>(layout) << 61;
     return d;
 }
+// One lane of the (converged) warp: the MMA-issuing warp runs its loop warp-uniformly -- every lane waits on the barriers and
+// computes the (uniform) descriptors, so they live in uniform registers -- and only the tcgen05 instructions are predicated
+// on the elected lane.  Running the whole loop under `if (lane == 0)` instead makes every descriptor a per-thread value that has
+// to be moved to the uniform datapath before each MMA (ELECT + R2UR.BROADCAST in SASS): ncu showed the issuing thread spending
+// ~600 cycles per K step on that, more than the 256 cycles of tensor work of a 128-column step.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate.
 //  fmt: 1 = bf16, 2 = tf32. a_mn / b_mn: 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {

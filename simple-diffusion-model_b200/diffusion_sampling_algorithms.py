@@ -65,6 +65,15 @@ def _f(t):
     return float(t.reshape(-1)[0])
 
 
+def _eval(diffusion_net, x, t, labels):
+    """One network evaluation.  A U_Net with CUDA graphs enabled hands out the graph's own output buffer (no per-step clone):
+    every caller below consumes it with the update kernel -- stream-ordered before the next replay overwrites it."""
+    graphed = getattr(diffusion_net, "_graphed", None)
+    if graphed is not None and x.is_cuda and not torch.is_grad_enabled():
+        return graphed(x, t, labels)
+    return diffusion_net(x, t, labels).contiguous()
+
+
 def ddpm_sampling(diffusion_net, noise_degradation, x_t, min_noise=1, max_noise=1_000, cond_img=None, labels_tensor=None,
                   device="cpu", log=print):
     x_t, cond_img = _prep(x_t, cond_img, device)
@@ -75,7 +84,7 @@ def ddpm_sampling(diffusion_net, noise_degradation, x_t, min_noise=1, max_noise=
     with torch.no_grad():
         for i, step in enumerate(steps):
             beta, alpha, abar = noise_degradation.host_params(step)
-            eps_hat = diffusion_net(_net_input(x_t, cond_img), ts[i:i + 1], labels_tensor).contiguous()
+            eps_hat = _eval(diffusion_net, _net_input(x_t, cond_img), ts[i:i + 1], labels_tensor)
             sigma = beta ** 0.5
             scale_1 = 1 / (alpha ** 0.5)
             scale_2 = (1 - alpha) / ((1 - abar) ** 0.5)
@@ -105,7 +114,7 @@ def ddim_sampling(diffusion_net, noise_degradation, x_t, min_noise=1, max_noise=
     x0_approx = None
     with torch.no_grad():
         for count, step in enumerate(steps):
-            eps_hat = diffusion_net(_net_input(x_t, cond_img), ts[count:count + 1], labels_tensor).contiguous()
+            eps_hat = _eval(diffusion_net, _net_input(x_t, cond_img), ts[count:count + 1], labels_tensor)
             abar_t = noise_degradation.host_params(step)[2]
             c_scale = 1 / abar_t ** 0.5
             c_s = (1 - abar_t) ** 0.5
@@ -140,7 +149,7 @@ def cold_diffusion_sampling(diffusion_net, noise_degradation, x_t, noise, min_no
     x0_hat = None
     with torch.no_grad():
         for count, step in enumerate(steps):
-            x0_hat = diffusion_net(_net_input(x_t, cond_img), ts[count:count + 1], labels_tensor).contiguous()
+            x0_hat = _eval(diffusion_net, _net_input(x_t, cond_img), ts[count:count + 1], labels_tensor)
             if count < len(steps) - 1:
                 abar_t = noise_degradation.host_params(step)[2]
                 abar_n = noise_degradation.host_params(steps[count + 1])[2]
@@ -150,4 +159,6 @@ def cold_diffusion_sampling(diffusion_net, noise_degradation, x_t, noise, min_no
                 x_t = out
                 printProgressBar(iteration=max_noise - step, total=max_noise - min_noise, prefix='Iterations:',
                                  suffix='Complete', length=50, log=log)
+    if getattr(diffusion_net, "_graphed", None) is not None:
+        x0_hat = x0_hat.clone()                  # the caller keeps it: detach it from the graph's output buffer
     return x0_hat

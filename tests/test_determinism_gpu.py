@@ -1,10 +1,10 @@
 """Run-to-run and shard-to-shard reproducibility.
 
+Deterministic mode (b2_set_deterministic / SDM_B200_DETERMINISTIC=1):
   * the weight-gradient GEMM's split-K is ORDERED (per-split partial tiles, last arriver sums them in split order): repeated
-    launches on the same operands are bitwise equal -- with fp32 atomics they were not;
-  * deterministic mode (b2_set_deterministic / SDM_B200_DETERMINISTIC=1): GroupNorm statistics without atomics and no split-K
-    on the forward kernel, so an image's result does not depend on batch size -- batch-sharded DDIM sampling from Philox x_T
-    is bitwise identical to the unsharded run."""
+    launches on the same operands are bitwise equal -- with the default fp32 atomics they are not;
+  * GroupNorm statistics without atomics and no split-K on the forward kernel, so an image's result does not depend on batch
+    size -- batch-sharded DDIM sampling from Philox x_T is bitwise identical to the unsharded run."""
 import pytest
 import torch
 
@@ -14,8 +14,16 @@ from oracle.weights import synth_state_dict
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture
+def deterministic():
+    import b200
+    b200.set_deterministic(True)
+    yield
+    b200.set_deterministic(False)
+
+
 @pytest.mark.parametrize("shape", [(4, 64, 64, 128, 128), (32, 16, 16, 256, 512), (2, 8, 8, 512, 512)])
-def test_weight_gradient_split_k_is_bitwise_repeatable(shape):
+def test_weight_gradient_split_k_is_bitwise_repeatable(deterministic, shape):
     from b200 import ops
     n, h, w, cin, cout = shape
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -33,14 +41,6 @@ def test_weight_gradient_split_k_is_bitwise_repeatable(shape):
     want = torch.nn.grad.conv2d_weight(xf, (cout, cin, 3, 3), dzf, padding=1).permute(0, 2, 3, 1).reshape(cout, 9 * cin)
     err = float((outs[0] - want).norm() / want.norm())
     assert err < 2e-3, err
-
-
-@pytest.fixture
-def deterministic():
-    import b200
-    b200.set_deterministic(True)
-    yield
-    b200.set_deterministic(False)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "tf32"])

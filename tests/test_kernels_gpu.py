@@ -298,3 +298,37 @@ def test_shadow_derived_weight_layouts_match_generic_pack():
         out = torch.zeros((cin, 9 * cout), dtype=torch.bfloat16, device="cuda")
         call("b2_transpose_weight_cl", ptr(wcl), ptr(out), cout, cin, stream())
         assert torch.equal(out, ops.pack_weight(1, w, cout, cin, cout, ops.BF16))
+
+
+# (N, C, H, W): 64x64 / 32x32 / 48x80 / 20x24 take the flattened halo scheme (pitch W + 1, 256 positions per work item), 128-wide
+# images the row-aligned one (two image rows per item); every shape has >= 148 items so that the halo kernel is selected
+# (b2_conv2d_nhwc falls back to per-tap loads below that); odd sizes leave partial last items and pad positions mid-tile
+@pytest.mark.parametrize("shape", [(10, 128, 64, 64), (40, 128, 32, 32), (3, 128, 128, 128), (12, 128, 48, 80), (75, 128, 20, 24)])
+def test_halo_conv_matches_reference(shape):
+    """3x3 stride-1 conv with 128 / 256 input channels in halo mode (one A box per 64-channel block, taps as row-shifted
+    descriptors; csrc/igemm.h) with the full epilogue: bias + Swish + GroupNorm sums + residual -- against torch fp32 on the
+    same bf16-rounded operands; the fused GroupNorm sums against sums of the reference output."""
+    from b200 import ops
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((n, c, h, w), device="cuda", generator=g)
+    wt = torch.randn((c, c, 3, 3), device="cuda", generator=g) * (1.0 / (c * 9) ** 0.5)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.1
+    res = torch.randn((n, c, h, w), device="cuda", generator=g)
+    xq, rq = _nhwc(x, torch.bfloat16), _nhwc(res, torch.bfloat16)
+    wp = ops.pack_weight(0, wt, c, c, c, 0)
+    ref_pre = swish(F.conv2d(_nchw(xq), wt.bfloat16().float(), bias, padding=1))
+    # epilogue variant 1: bias + Swish + GroupNorm sums (what every residual-block conv of the forward pass uses)
+    stats = torch.zeros((n, 32, 2), device="cuda")
+    y = ops.conv2d(0, xq, wp, bias, c, act=1, gn_stats=stats, groups=32)
+    assert rel_l2(_nchw(y), ref_pre) < 1e-2
+    grp = ref_pre.reshape(n, 32, -1)
+    assert rel_l2(stats[..., 0], grp.sum(-1)) < 2e-2 and rel_l2(stats[..., 1], (grp * grp).sum(-1)) < 1e-2
+    # epilogue variant 2: no activation + residual add (the data-gradient form)
+    y2 = ops.conv2d(0, xq, wp, None, c, act=0, residual=rq)
+    ref2 = F.conv2d(_nchw(xq), wt.bfloat16().float(), None, padding=1) + _nchw(rq)
+    assert rel_l2(_nchw(y2), ref2) < 1e-2
+    # channel-slice output (zero-copy concat): written into the right half of a wider buffer, left half untouched
+    wide = torch.full((n, h, w, 2 * c), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.conv2d(0, xq, wp, bias, c, act=1, out=wide[..., c:])
+    assert rel_l2(_nchw(wide[..., c:]), ref_pre) < 1e-2 and bool((wide[..., :c] == 7.0).all())

@@ -38,6 +38,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--wgrad-only", action="store_true")
     ap.add_argument("--scale", type=int, default=1, help="spatial scale (2 = 128x128 input)")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
@@ -60,13 +61,15 @@ def main():
 
         sets = [mk() for _ in range(reps)]
         res = {"C": c, "hw": hw, "count": count, "gflop": flops / 1e9}
-        t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d(0, x, w, b, c, act=1, out=y, gn_stats=st, groups=32), sets)
-        res["fwd_us"], res["fwd_tflops"] = t * 1e3, flops / t / 1e9
-        tot["fwd"] += t * count
+        if not args.wgrad_only:
+            t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d(0, x, w, b, c, act=1, out=y, gn_stats=st, groups=32), sets)
+            res["fwd_us"], res["fwd_tflops"] = t * 1e3, flops / t / 1e9
+            tot["fwd"] += t * count
         if not args.fwd_only:
-            t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d(0, dz, w, None, c, act=0, out=y), sets)
-            res["dgrad_us"], res["dgrad_tflops"] = t * 1e3, flops / t / 1e9
-            tot["dgrad"] += t * count
+            if not args.wgrad_only:
+                t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d(0, dz, w, None, c, act=0, out=y), sets)
+                res["dgrad_us"], res["dgrad_tflops"] = t * 1e3, flops / t / 1e9
+                tot["dgrad"] += t * count
             t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d_wgrad(0, x, dz, c, gw), sets)
             res["wgrad_us"], res["wgrad_tflops"] = t * 1e3, flops / t / 1e9
             tot["wgrad"] += t * count

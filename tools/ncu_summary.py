@@ -1,5 +1,8 @@
 """Summarises an .ncu-rep (`ncu --set full`) into a markdown table: duration, DRAM traffic, achieved GB/s, tensor-pipe and
-L2 utilisation per launch.   python tools/ncu_summary.py report.ncu-rep > profiles/xxx.md"""
+L2 utilisation per launch.   python tools/ncu_summary.py report.ncu-rep > profiles/xxx.md
+With `--traffic ID BATCH ALGORITHMIC_BYTES`: also writes profiles/roofline_traffic.json (dram read + write bytes of launch ID),
+which bench.py reports as roofline.traffic:
+    python tools/ncu_summary.py report.ncu-rep --traffic 0 256 287e6 > profiles/xxx.md"""
 import csv
 import io
 import re
@@ -26,6 +29,11 @@ def to_sec(v, unit):
     return float(v.replace(",", "")) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}.get(unit, 1)
 
 
+traffic = None
+if "--traffic" in sys.argv:
+    i = sys.argv.index("--traffic")
+    traffic = (sys.argv[i + 1], int(sys.argv[i + 2]), float(sys.argv[i + 3]))
+
 for r in rows[2:]:
     name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("void ", "").replace("b2::", "")[:60]
     vals = [r[col[m]] for m, _ in want if m in col]
@@ -34,6 +42,13 @@ for r in rows[2:]:
         wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
         t = to_sec(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]])
         gbs = f"{(rd + wr) / t / 1e9:.0f}"
+        if traffic is not None and r[col["ID"]] == traffic[0]:
+            import json
+            import os
+            out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "roofline_traffic.json")
+            json.dump({"kernel": name, "batch": traffic[1], "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+                       "algorithmic_bytes": traffic[2], "duration_s": t,
+                       "source": f"ncu --set full, launch ID {traffic[0]} of {os.path.basename(sys.argv[1])}"}, open(out, "w"), indent=1)
     except Exception:
         gbs = "-"
     print(f"| {r[col['ID']]} | {name} | " + " | ".join(v[:10] for v in vals) + f" | {gbs} |")
