@@ -20,6 +20,7 @@ SIGNATURES = {
     "b2_set_workspace": [_P, _L],
     "b2_set_deterministic": [_I],
     "b2_zero": [_P, _L, _P],
+    "b2_set_option": [_P, _I],
     "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
     "b2_conv3x3_first": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_conv3x3_last": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -117,9 +117,9 @@ static int pick_cluster(int dtype, int bn, int splits, long long tiles, long lon
 }
 
 // Spatial box of <=128 output pixels: full rows first, then rows, then images.
-static void pick_box(int W, int H, int N, int* wb, int* hb, int* nb) {
-    *wb = W < 128 ? W : 128;
-    int rem = 128 / *wb;
+static void pick_box(int W, int H, int N, int* wb, int* hb, int* nb, int rows = 128) {
+    *wb = W < rows ? W : rows;
+    int rem = rows / *wb;
     *hb = H < rem ? H : rem;
     rem /= *hb;
     *nb = N < rem ? N : rem;
@@ -229,19 +229,41 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
     long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     int bn, splits;
     pick_tiling(Cout, m_tiles, p.groups, p.taps * p.kb_per_tap, !det, &bn, &splits);
+    // ---- swapped-operand mode (igemm.h: swap_ab) for 3x3 stride-1 convs with <= 128 output channels: the 128x256 MMA shape.
+    // OFF by default (SDM_B200_SWAP_AB=1 / b2_set_option("swap_ab", 1) enables it).  MEASURED on the 128-channel layers
+    // (profiles/r02n_conv128_variants.md; TFLOP/s forward, batch 256 @64x64 | batch 32 @128x128): per-tap 884 | 874, halo
+    // 965 | 976, swapped 848 | 799 -- the wider MMA shape does not help: these layers are bound by operand delivery (18 K steps
+    // per tile, every CTA streaming the same 295 KB weight matrix), which only the halo tile reduces.
+    bool swapped = false;
+    {
+        const int swap_env = option("swap_ab", 0);
+        if (swap_env && mode == 0 && dtype == 0 && out_mode == 0 && Cout <= 128 && Cout >= 64 && p.cpg != 1 && !separate_stats && W <= 256) {
+            int wb2, hb2, nb2;
+            pick_box(W, H, N, &wb2, &hb2, &nb2, 256);
+            const long long tiles2 = (long long)((W + wb2 - 1) / wb2) * ((H + hb2 - 1) / hb2) * ((N + nb2 - 1) / nb2);
+            // enough 256-pixel tiles to fill the machine without split-K; whole 32-pixel chunks per image; 32-channel quarters
+            if (tiles2 >= device_sm_count() && (wb2 * hb2) % 32 == 0 && Cout % 32 == 0) {
+                swapped = true;
+                p.swap_ab = 1;
+                p.wb = wb2; p.hb = hb2; p.nb = nb2;
+                p.tiles_w = (W + wb2 - 1) / wb2; p.tiles_h = (H + hb2 - 1) / hb2; p.tiles_n = (N + nb2 - 1) / nb2;
+                m_tiles = tiles2;
+                bn = 256; splits = 1;
+            }
+        }
+    }
     // ---- halo mode (igemm.h): stride-1 3x3 convs with 128 / 256 input channels, whose 18 / 36 K steps per tile are too few to
     // amortise re-fetching the A box once per tap.  SDM_B200_HALO=0 keeps the per-tap loads.
     uint32_t a_box[4] = {(uint32_t)bk, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
     {
-        static int halo_env = -1;
-        if (halo_env < 0) { const char* e = getenv("SDM_B200_HALO"); halo_env = e ? atoi(e) : 1; }
+        const int halo_env = option("halo", 1);
         // MEASURED (profiles/r02g_halo_ab.log): with ONE 128-row tile per weights stage the halo kernel is slower than per-tap
         // loads (C128 64x64 batch 256: 854 -> 700 TFLOP/s) although it moves 2x fewer bytes -- the main loop is bound by TMA
         // latency x ring depth in STAGES, not by bytes.  What pays is doing twice the MMA work per weights stage: two 128-row
         // sub-tiles per item (256 flattened positions), which needs 2 x 2 x BLOCK_N TMEM columns, i.e. BLOCK_N = 128 = Cout.
         const bool shape_ok = mode == 0 && dtype == 0 && out_mode == 0 && (Cin == 128 || Cin == 256) && Cout == 128 &&
                               W >= 16 && W + 1 <= 256;
-        if (halo_env && shape_ok) {
+        if (halo_env && shape_ok && !swapped) {
             const int hbn = 128, msub = 2;
             const int b_bytes = hbn * 128;
             const int max_b = 6;
@@ -270,10 +292,10 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
             }
         }
     }
-    p.n_tiles = (Cout + bn - 1) / bn;
+    p.n_tiles = swapped ? (Cout + 127) / 128 : (Cout + bn - 1) / bn;
     p.b_mode = 0;
     p.splits = splits; p.ws = workspace(0).ws; p.ws_counters = workspace(0).counters;
-    p.cluster = pick_cluster(dtype, bn, splits, m_tiles * p.groups * p.n_tiles, m_tiles);
+    p.cluster = swapped ? 1 : pick_cluster(dtype, bn, splits, m_tiles * p.groups * p.n_tiles, m_tiles);
 
     CUtensorMap ta, tb;
     {
@@ -285,7 +307,7 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         const uint64_t ktot = (uint64_t)p.taps * Cin;
         uint64_t dims[4] = {ktot, (uint64_t)Cout, (uint64_t)p.groups, 1};
         uint64_t str[3] = {ktot * eb, ktot * Cout * eb, ktot * Cout * p.groups * eb};
-        uint32_t box[4] = {(uint32_t)bk, (uint32_t)(bn / p.cluster), 1, 1};      // cluster mode: each CTA fetches 1/CL of the B tile
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)(swapped ? 128 : bn / p.cluster), 1, 1};      // cluster mode: each CTA fetches 1/CL of the B tile
         if (make_tmap_4d(&tb, wpacked, eb, dims, str, box)) return 1;
     }
     if (launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;

@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 
 namespace b2 {
@@ -89,9 +90,26 @@ bool deterministic_mode() {
 }
 void set_deterministic_mode(int on) { g_det = on ? 1 : 0; }
 
+struct Opt { const char* name; const char* env; int value; bool set; };
+static Opt g_opts[] = {{"halo", "SDM_B200_HALO", 0, false}, {"swap_ab", "SDM_B200_SWAP_AB", 0, false}};
+int option(const char* name, int default_value) {
+    for (auto& o : g_opts) {
+        if (strcmp(o.name, name)) continue;
+        if (!o.set) { const char* e = getenv(o.env); o.value = e ? atoi(e) : default_value; o.set = true; }
+        return o.value;
+    }
+    return default_value;
+}
+int set_option(const char* name, int value) {
+    for (auto& o : g_opts) if (!strcmp(o.name, name)) { o.value = value; o.set = true; return 0; }
+    return set_error("b2_set_option: unknown option '%s'", name);
+}
+
 }  // namespace b2
 
 // Zero-fill of a device range on `stream` (the flat gradient buffer at the start of every backward pass): a memset node, no kernel.
+extern "C" int b2_set_option(const char* name, int value) { return b2::set_option(name, value); }
+
 extern "C" int b2_zero(void* ptr, long long bytes, void* stream) {
     if (!ptr || bytes <= 0) return 0;
     cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);

@@ -30,6 +30,11 @@ bool pdl_enabled();
 bool deterministic_mode();
 void set_deterministic_mode(int on);
 
+// Kernel-selection switches (A/B measurements and tests): initialised from SDM_B200_<NAME> (upper case) on first use, changed at
+// run time through b2_set_option.  "halo": halo-tile 3x3 convs; "swap_ab": swapped-operand convs for <= 128 output channels.
+int option(const char* name, int default_value);
+int set_option(const char* name, int value);
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};

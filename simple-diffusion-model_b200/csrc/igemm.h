@@ -53,6 +53,11 @@ struct IgemmParams {
     // image with one shared zero column per row (pitch P = W + 1: position f = h*P + w, w == W is the pad, produced by TMA's
     // out-of-bounds fill and skipped by the epilogue), halo = 1: tiles_w = ceil(H*P / 128), wb = 128;
     // or, for W % 128 == 0, one 128-pixel run of one image row, halo = 2 (box 130 x 3 rows, no pad positions).
+    // Swapped-operand mode for Cout <= 128 (BLOCK_N = 256 instance only): the MMA's 128 rows are OUTPUT CHANNELS (A = a 128-row
+    // weights tile) and its 256 columns are PIXELS (B = the activation box, wb*hb*nb <= 256), i.e. D^T = W X^T.  A 128-channel
+    // layer then runs the 128x256 MMA shape of the wide layers (measured 86-91 % tensor pipe) instead of 128x128 (40-48 %), and
+    // the epilogue thread owns one channel: bias is a scalar, GroupNorm sums are in-thread over pixels.  n_tiles = ceil(Cout / 128).
+    int swap_ab;
     int halo;                    // 0 off, 1 flattened, 2 row-aligned
     int halo_P;                  // flattened pitch W + 1 (halo 1)
     int halo_msub;               // 128-row sub-tiles per work item (2: both share every weights stage; BLOCK_N = 128 only)

@@ -22,7 +22,12 @@ struct IgemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int BIAS_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;        // [2 accumulator stages][BLOCK_N] fp32
-    static constexpr int TOTAL = BIAS_OFF + 2 * BLOCK_N * 4 + 1024;             // +1024: manual alignment slack
+    // swapped-operand epilogue (BLOCK_N == 256 only): per epilogue warp a [32 pixels][32 channels] bf16 transposition tile, rows
+    // padded to 80 bytes (conflict-free 16-byte reads)
+    static constexpr int TR_ROW = 40;                                            // halfwords per pixel row
+    static constexpr int TR_OFF = (BIAS_OFF + 2 * BLOCK_N * 4 + 15) & ~15;
+    static constexpr int TR_BYTES = BLOCK_N == 256 ? 8 * 32 * TR_ROW * 2 : 0;
+    static constexpr int TOTAL = TR_OFF + TR_BYTES + 1024;                       // +1024: manual alignment slack
 };
 
 struct TileCoord { int nt, w0, h0, n0, g; };
@@ -261,7 +266,15 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + S::A_BYTES;
                     if (elect_one()) {
-                        if (load_a) {
+                        if (p.swap_ab) {
+                            // swapped operands: the 16 KB A region takes the 128-row weights tile, the B region the pixel box
+                            if (load_a) {
+                                mbar_arrive_expect_tx(&full[s], a_bytes + S::A_BYTES);
+                                tma_load_4d(a_dst, &tmB, &full[s], it * BK_ELEMS, tc.nt * 128, bb2, bb3);
+                            } else {
+                                tma_load_4d(b_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
+                            }
+                        } else if (load_a) {
                             mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
                             tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
                         } else if constexpr (CL > 1) {
@@ -313,7 +326,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const uint64_t ad0 = desc0 + ((a_base + static_cast<uint32_t>(row0 + dh * p.halo_BW + dw) * 128u) >> 4);
                             const uint64_t bd0 = desc0 + ((ring0 + s * S::B_BYTES) >> 4);
                             if (elect_one()) {
-                                for (int sub = 0; sub < msub; ++sub) {            // the sub-tiles share this weights stage
+                                for (int sub = 0; sub < msub; ++sub) {            // the sub-tiles share this weights stage (interleaving their MMAs k-outer measured 12 % slower)
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
                                         umma_ss<false>(d_tmem + sub * BLOCK_N, ad0 + sub * (sub_rows * 8u) + 2 * k, bd0 + 2 * k, idesc,
@@ -408,6 +421,93 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
+            if (p.swap_ab) {
+                // ---- swapped operands: TMEM lane = output channel, columns = the tile's pixels.  Per 32-pixel chunk: bias /
+                // activation / GroupNorm sums with lane = channel (sums are in-thread over pixels), then a 32x32 transposition
+                // through shared memory so that every lane stores the 64 contiguous bytes of ONE pixel (16-byte vectors).
+                if constexpr (BLOCK_N == 256 && !kTF32 && !HALO) {
+                    const int c0w = tc.nt * 128 + q * 32;                // first channel of this warp's lane quarter
+                    const int c = c0w + lane;
+                    const bool warp_ok = c0w < p.Cout;                   // Cout is a multiple of 32 in this mode
+                    const float bias_c = (p.bias && warp_ok) ? __ldg(p.bias + c) : 0.f;
+                    const int red_lanes = p.cpg < 32 ? p.cpg : 32;       // lanes (channels) of one GroupNorm group inside this warp
+                    __nv_bfloat16* tr = reinterpret_cast<__nv_bfloat16*>(smem + S::TR_OFF) + (warp - 2) * (32 * S::TR_ROW);
+                    const int box_px = p.wb * p.hb;                      // pixels per image inside the box (a multiple of 32)
+#pragma unroll 1
+                    for (int ch = half; ch < 8; ch += 2) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_col + ch * 32, r);
+                        tmem_ld_wait();
+                        if (!warp_ok) continue;
+                        // this lane's pixel (after the transposition) and the chunk's image
+                        const int pl = ch * 32 + lane;
+                        const int pn = pl / box_px, prem = pl - pn * box_px;
+                        const int w2 = tc.w0 + prem % p.wb, h2 = tc.h0 + prem / p.wb, n2 = tc.n0 + pn;
+                        const bool pv = (pn < p.nb) && (w2 < p.W) && (h2 < p.H) && (n2 < p.N);
+                        const uint32_t vmask = __ballot_sync(0xffffffffu, pv);
+                        if (vmask == 0u) continue;
+                        const int n_chunk = __shfl_sync(0xffffffffu, n2, __ffs(vmask) - 1);   // one image per chunk (box_px % 32 == 0)
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float v = fmaf(__uint_as_float(r[j]), p.alpha, bias_c);
+                            if (p.act == 1) v = swish_fast(v);
+                            else if (p.act == 2) v = tanhf(v);
+                            const float sv = p.act == 3 ? swish_fast(v) : v;     // training: statistics of swish(z), z is stored
+                            if ((vmask >> j) & 1u) { s1 += sv; s2 = fmaf(sv, sv, s2); }
+                            tr[j * S::TR_ROW + lane] = __float2bfloat16(v);
+                        }
+                        if (p.gn_stats) {
+                            for (int o = 1; o < red_lanes; o <<= 1) {
+                                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                            }
+                            if ((lane & (red_lanes - 1)) == 0) {
+                                float* st = p.gn_stats + ((long long)n_chunk * G + c / p.cpg) * 2;
+                                atomicAdd(st, s1);
+                                atomicAdd(st + 1, s2);
+                            }
+                        }
+                        __syncwarp();
+                        uint4 x[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const uint4*>(tr + lane * S::TR_ROW + i * 8);
+                        __syncwarp();
+                        if (pv) {
+                            const long long off = n2 * p.oN + h2 * p.oH + w2 * p.oW + p.goff[tc.g] + c0w;
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+                            if (p.residual) {
+                                const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + n2 * p.rN + h2 * p.rH + w2 * p.rW + c0w;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    uint4 y;
+                                    if (p.vec_ok) y = __ldg(reinterpret_cast<const uint4*>(rs) + i);
+                                    else { __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(&y); for (int e = 0; e < 8; ++e) yy[e] = rs[i * 8 + e]; }
+                                    __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&x[i]);
+                                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+                                        a2[e] = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
+                                    }
+                                }
+                            }
+                            if (p.vec_ok) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(o)[i] = x[i];
+                            } else {
+                                const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+                                for (int e = 0; e < 32; ++e) o[e] = xx[e];
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                continue;
+            }
             bool from_ws = false;
             float* ws_row = nullptr;
             if (splits > 1) {
@@ -735,6 +835,8 @@ int launch_igemm_nt(int dtype /*0 bf16, 1 fp32(tf32)*/, const CUtensorMap& a, co
     const int sms = device_sm_count();
     const int cl = p.cluster > 1 ? p.cluster : 1;
     if (cl > 1 && (p.splits != 1 || p.b_mode || p.act == 4)) return set_error("igemm_nt: cluster multicast needs an unsplit, unbatched GEMM");
+    if (p.swap_ab && (dtype != 0 || block_n != 256 || cl != 1 || p.splits != 1 || p.halo || p.out_fp32))
+        return set_error("igemm_nt: swapped-operand mode needs the bf16 256-column kernel without cluster / split-K");
     if (p.halo) {
         if (dtype != 0 || p.splits != 1 || p.b_mode || p.taps != 9) return set_error("igemm_nt (halo): bf16 3x3 stride-1 convolutions only");
         if (cl == 1 && block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 1, true>(a, b, p, sms, st);

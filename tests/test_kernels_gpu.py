@@ -303,11 +303,25 @@ def test_shadow_derived_weight_layouts_match_generic_pack():
 # (N, C, H, W): 64x64 / 32x32 / 48x80 / 20x24 take the flattened halo scheme (pitch W + 1, 256 positions per work item), 128-wide
 # images the row-aligned one (two image rows per item); every shape has >= 148 items so that the halo kernel is selected
 # (b2_conv2d_nhwc falls back to per-tap loads below that); odd sizes leave partial last items and pad positions mid-tile
+@pytest.mark.parametrize("variant", ["swap_ab", "halo", "per_tap"])
 @pytest.mark.parametrize("shape", [(10, 128, 64, 64), (40, 128, 32, 32), (3, 128, 128, 128), (12, 128, 48, 80), (75, 128, 20, 24)])
-def test_halo_conv_matches_reference(shape):
-    """3x3 stride-1 conv with 128 / 256 input channels in halo mode (one A box per 64-channel block, taps as row-shifted
-    descriptors; csrc/igemm.h) with the full epilogue: bias + Swish + GroupNorm sums + residual -- against torch fp32 on the
+def test_128_channel_conv_variants_match_reference(shape, variant):
+    """The three kernels a 3x3 stride-1 conv with 128 channels can take (csrc/igemm.h): swapped operands (channels on the MMA's
+    128 rows, 256 pixels on its columns), halo tiles (one A box per 64-channel block, taps as row-shifted descriptors -- the
+    default), per-tap loads -- each with the full epilogue: bias + Swish + GroupNorm sums + residual, against torch fp32 on the
     same bf16-rounded operands; the fused GroupNorm sums against sums of the reference output."""
+    import b200
+    from b200 import ops
+    b200.set_option("swap_ab", 1 if variant == "swap_ab" else 0)
+    b200.set_option("halo", 1 if variant == "halo" else 0)
+    try:
+        _check_128_channel_conv(shape)
+    finally:
+        b200.set_option("swap_ab", 0)
+        b200.set_option("halo", 1)
+
+
+def _check_128_channel_conv(shape):
     from b200 import ops
     n, c, h, w = shape
     g = torch.Generator(device="cuda").manual_seed(4)
