@@ -71,7 +71,7 @@ def test_resume_from_reference_checkpoint(mode):
         err = rel_l2(got - start, want - start)
         print(f"resume/{mode} step {gstep}: loss {loss:.6f} (ref {rec['loss']:.6f}) update rel_l2 {err:.2e}")
         # with zeroed moments the first update would be ~16x too large (lr (1-b1)/sqrt(1-b2) per element): err >> 1
-        assert err < 3e-2, (gstep, err)
+        assert err < 6e-2, (gstep, err)
         if gstep % cfg["lr_steps"] == 0 and gstep > 0:
             for group in opt.param_groups:
                 group["lr"] = group["lr"] * 0.5

@@ -18,7 +18,7 @@ def cold():
     torch.cuda.synchronize()
 
 
-for n, c, hw in ((256, 1024, 16), (256, 128, 64), (32, 512, 32)):
+for n, c, hw in ((256, 1024, 16), (256, 128, 64), (32, 512, 32), (32, 128, 128)):
     p = hw * hw
     y = torch.randn((n, hw, hw, c), device=dev, dtype=bf)
     res = torch.randn((n, hw, hw, c), device=dev, dtype=bf)
