@@ -52,5 +52,13 @@ same = torch.equal(mine, full[lo:hi])
 rel = float((mine - full[lo:hi]).norm() / full[lo:hi].norm())
 print(f"rank {rank}: sharded DDIM vs unsharded: bitwise {same}, rel-L2 {rel:.2e} (GroupNorm sums use fp32 atomics: order-dependent in the last bits)", flush=True)
 assert rel < 1e-3, rel
+# deterministic mode (no fp atomics, no batch-dependent split-K): the shard IS the slice of the unsharded result, bit for bit
+import b200
+b200.set_deterministic(True)
+full_d = S.ddim_sampling(net, deg, x_T, ddim_step_size=250, device=dev, log=lambda *a, **k: None)
+mine_d = S.ddim_sampling(net, deg, x_T[lo:hi].clone(), ddim_step_size=250, device=dev, log=lambda *a, **k: None)
+b200.set_deterministic(False)
+print(f"rank {rank}: deterministic mode: sharded DDIM vs unsharded bitwise {torch.equal(mine_d, full_d[lo:hi])}", flush=True)
+assert torch.equal(mine_d, full_d[lo:hi])
 dist.barrier()
 dist.destroy_process_group()
