@@ -24,8 +24,8 @@ const char* b2_last_error(void);
 int b2_version(void);
 
 /* Kernel-selection switches for A/B measurements and tests (defaults from SDM_B200_HALO / SDM_B200_SWAP_AB): "halo" = halo-tile
- * 3x3 convolutions, "swap_ab" = swapped-operand convolutions for <= 128 output channels.  Results are the same up to the
- * order of fp32 accumulation. */
+ * 3x3 convolutions, "swap_ab" = swapped-operand convolutions for <= 128 output channels (results are the same up to the
+ * order of fp32 accumulation); "sm_limit" = number of SMs the persistent grids occupy (0 = all; SDM_B200_SM_LIMIT). */
 int b2_set_option(const char* name, int value);
 /* Zero-fills `bytes` of device memory on `stream` (the flat gradient buffer before a backward pass; the reference's
  * optimizer.zero_grad(), train_diffusion.py:317). */

@@ -20,6 +20,9 @@ def shard_range(total, rank, world):
 
 class DataParallel:
     def __init__(self, net, process_group=None, bucket_bytes=64 << 20, device=None):
+        import os
+        if os.environ.get("SDM_B200_BUCKET_MB"):
+            bucket_bytes = int(os.environ["SDM_B200_BUCKET_MB"]) << 20
         self.net = net
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -37,6 +40,13 @@ class DataParallel:
             for n_, p in net.named_parameters():                # parameters outside the flat buffer (never trained)
                 if id(p) not in self.layout.offsets:
                     dist.broadcast(p.data, src=0, group=self.group)
+        # SDM_B200_DP_RESERVE_SMS=<r>: under data parallelism the persistent tensor-core grids leave r SMs to NCCL's CTAs
+        # (0 = off, the default; see DESIGN.md section 6 for the measurement)
+        reserve = int(os.environ.get("SDM_B200_DP_RESERVE_SMS", "0"))
+        if self.world > 1 and reserve > 0:
+            import b200
+            sms = torch.cuda.get_device_properties(device).multi_processor_count
+            b200.set_option("sm_limit", max(1, sms - reserve))
         eng.on_grads_ready = self.ready
         eng.post_backward = self.finish
         self.opt = None              # FusedAdam attached with attach_optimizer(): bucket-wise updates under the backward pass

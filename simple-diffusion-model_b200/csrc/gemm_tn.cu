@@ -400,7 +400,8 @@ static int launch_tn_cfg(const CUtensorMap& a, const CUtensorMap& b, const GemmT
     int grid;
     if (CL > 1) {
         const long long pairs = (long long)p.splits * (p.m_tiles / CL) * p.n_tiles * p.taps;
-        grid = (int)(pairs < max_clusters ? pairs : max_clusters) * CL;
+        const long long cl_cap = max_clusters < num_sms / CL ? max_clusters : num_sms / CL;
+        grid = (int)(pairs < cl_cap ? pairs : cl_cap) * CL;
     } else {
         const long long items = (long long)p.splits * p.m_tiles * p.n_tiles * p.taps * batches;
         grid = (int)(items < num_sms ? items : num_sms);

@@ -18,6 +18,7 @@ int set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+static int g_sm_limit = -1;      // "sm_limit" option: persistent grids use at most this many SMs (0 = all)
 int device_sm_count() {
     static int sms[64] = {0};
     int dev = 0;
@@ -28,7 +29,8 @@ int device_sm_count() {
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         sms[dev] = v > 0 ? v : 148;
     }
-    return sms[dev];
+    if (g_sm_limit < 0) { const char* e = getenv("SDM_B200_SM_LIMIT"); g_sm_limit = e ? atoi(e) : 0; }
+    return (g_sm_limit > 0 && g_sm_limit < sms[dev]) ? g_sm_limit : sms[dev];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -101,6 +103,7 @@ int option(const char* name, int default_value) {
     return default_value;
 }
 int set_option(const char* name, int value) {
+    if (!strcmp(name, "sm_limit")) { g_sm_limit = value > 0 ? value : 0; return 0; }
     for (auto& o : g_opts) if (!strcmp(o.name, name)) { o.value = value; o.set = true; return 0; }
     return set_error("b2_set_option: unknown option '%s'", name);
 }

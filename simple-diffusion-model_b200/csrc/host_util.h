@@ -31,7 +31,9 @@ bool deterministic_mode();
 void set_deterministic_mode(int on);
 
 // Kernel-selection switches (A/B measurements and tests): initialised from SDM_B200_<NAME> (upper case) on first use, changed at
-// run time through b2_set_option.  "halo": halo-tile 3x3 convs; "swap_ab": swapped-operand convs for <= 128 output channels.
+// run time through b2_set_option.  "halo": halo-tile 3x3 convs; "swap_ab": swapped-operand convs for <= 128 output channels;
+// "sm_limit" (SDM_B200_SM_LIMIT): SMs the persistent grids may occupy (0 = all) -- data-parallel training can leave a few SMs
+// to NCCL's copy/reduce CTAs, which otherwise queue behind 148-CTA persistent GEMMs.
 int option(const char* name, int default_value);
 int set_option(const char* name, int value);
 

@@ -818,7 +818,8 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmPar
     if (CL > 1) {
         const int m_total = p.tiles_n * p.tiles_h * p.tiles_w;
         const long long groups = (long long)p.groups * ((m_total + CL - 1) / CL) * p.n_tiles;
-        const long long clusters = groups < max_clusters ? groups : max_clusters;
+        const long long cl_cap = max_clusters < num_sms / CL ? max_clusters : num_sms / CL;      // honours the sm_limit option
+        const long long clusters = groups < cl_cap ? groups : cl_cap;
         grid = (int)clusters * CL;
     } else {
         const int total_tiles = p.groups * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.splits;
