@@ -261,6 +261,13 @@ int b2_adam_flat_graph(float* p, const float* g, float* m, float* v, long long n
  * the flat buffers with the same bias corrections (bucket-wise updates overlapped with the backward pass). */
 int b2_adam_advance(float* state, double beta1, double beta2, void* stream);
 
+/* b2_adam_flat / b2_adam_flat_graph with bf16 gradients (data-parallel transport buffer, reference: none -- the reference is
+ * single-process); state == NULL: host scalars step_size / inv_bc2_sqrt / grad_scale, else the device float[8] of the graph form. */
+int b2_adam_flat_g16(float* p, const void* g_bf16, float* m, float* v, long long n, double beta1, double beta2, float eps,
+                     float step_size, float inv_bc2_sqrt, float grad_scale, float* state, void* shadow_bf16, void* stream);
+/* to_f32 == 0: dst_bf16[i] = bf16(src[i]); to_f32 != 0: src[i] = float(dst_bf16[i])  (gradient buckets around the bf16 all-reduce). */
+int b2_cast_f32_bf16(const float* src, void* dst_bf16, long long n, int to_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

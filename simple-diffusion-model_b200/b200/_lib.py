@@ -56,6 +56,8 @@ SIGNATURES = {
     "b2_adam_flat": [_P, _P, _P, _P, _L, _D, _D, _F, _F, _F, _F, _P, _P],
     "b2_adam_flat_graph": [_P, _P, _P, _P, _L, _D, _D, _F, _P, _P, _I, _P],
     "b2_adam_advance": [_P, _D, _D, _P],
+    "b2_adam_flat_g16": [_P, _P, _P, _P, _L, _D, _D, _F, _F, _F, _F, _P, _P, _P],
+    "b2_cast_f32_bf16": [_P, _P, _L, _I, _P],
     "b2_pack_weight_multi": [_P, _I, _L, _I, _P],
     "b2_transpose_weight_cl_multi": [_P, _I, _L, _P],
     "b2_transpose_weight_cl": [_P, _P, _I, _I, _P],

@@ -136,7 +136,8 @@ class FusedAdam(torch.optim.Optimizer):
         return True
 
     @torch.no_grad()
-    def step_range(self, lay, lo, hi):
+    def step_range(self, lay, lo, hi, grad16=None):
+        """grad16: the range's gradients as bf16 (data-parallel transport buffer) instead of lay.flat[lo:hi]."""
         part = getattr(self, "_partial", None)
         if part is None or part["lay"] is not lay or hi <= lo:
             return
@@ -144,6 +145,17 @@ class FusedAdam(torch.optim.Optimizer):
         m_flat, v_flat = self._flat[id(lay)]
         b1, b2 = group["betas"]
         sh = shadow[lo:hi] if shadow is not None else None
+        if grad16 is not None:
+            if self.capturable:
+                call("b2_adam_flat_g16", ptr(lay.params_flat[lo:hi]), ptr(grad16), ptr(m_flat[lo:hi]), ptr(v_flat[lo:hi]), hi - lo,
+                     float(b1), float(b2), group["eps"], 0.0, 0.0, 0.0, ptr(self._dev_state[id(lay)]), ptr(sh), stream())
+            else:
+                step = part["step"]
+                call("b2_adam_flat_g16", ptr(lay.params_flat[lo:hi]), ptr(grad16), ptr(m_flat[lo:hi]), ptr(v_flat[lo:hi]), hi - lo,
+                     float(b1), float(b2), group["eps"], group["lr"] / (1.0 - b1 ** step), 1.0 / math.sqrt(1.0 - b2 ** step),
+                     self.grad_scale, None, ptr(sh), stream())
+            part["done"].append((lo, hi))
+            return
         if self.capturable:
             call("b2_adam_flat_graph", ptr(lay.params_flat[lo:hi]), ptr(lay.flat[lo:hi]), ptr(m_flat[lo:hi]), ptr(v_flat[lo:hi]),
                  hi - lo, float(b1), float(b2), group["eps"], ptr(self._dev_state[id(lay)]), ptr(sh), 0, stream())

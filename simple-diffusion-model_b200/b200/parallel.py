@@ -19,7 +19,10 @@ def shard_range(total, rank, world):
 
 
 class DataParallel:
-    def __init__(self, net, process_group=None, bucket_bytes=64 << 20, device=None):
+    def __init__(self, net, process_group=None, bucket_bytes=64 << 20, device=None, grad_dtype=None, _force_transport=False):
+        """grad_dtype: "fp32" (default) or "bf16" (also SDM_B200_DP_GRAD_DTYPE): a bucket is cast to bf16, summed by NCCL in
+        bf16 and consumed by the fused Adam as bf16 -- half the bytes on the wire; moments, weights and the optimiser
+        arithmetic stay fp32.  `_force_transport` exercises the cast path at world size 1 (tests)."""
         import os
         if os.environ.get("SDM_B200_BUCKET_MB"):
             bucket_bytes = int(os.environ["SDM_B200_BUCKET_MB"]) << 20
@@ -49,6 +52,13 @@ class DataParallel:
             b200.set_option("sm_limit", max(1, sms - reserve))
         eng.on_grads_ready = self.ready
         eng.post_backward = self.finish
+        self.grad_dtype = grad_dtype or os.environ.get("SDM_B200_DP_GRAD_DTYPE", "fp32")
+        if self.grad_dtype not in ("fp32", "bf16"):
+            raise ValueError("grad_dtype must be 'fp32' or 'bf16'")
+        self.g16 = None              # bf16 transport buffer, same offsets as the flat gradient buffer
+        if self.grad_dtype == "bf16" and (self.world > 1 or _force_transport):
+            self.g16 = torch.zeros(self.layout.total, dtype=torch.bfloat16, device=device)
+        self._cast_back = []         # buckets to expand to fp32 when no fused optimiser consumes the bf16 sums
         self.opt = None              # FusedAdam attached with attach_optimizer(): bucket-wise updates under the backward pass
         self.opt_stream = None
         self._stepping = False
@@ -66,13 +76,20 @@ class DataParallel:
         return 1.0 / self.world
 
     def _launch(self, lay, lo, hi):
+        from ._lib import call, ptr, stream
         self.launched.append((lo, hi))
         work = None
+        g16 = None
+        if self.g16 is not None:
+            g16 = self.g16[lo:hi]
+            call("b2_cast_f32_bf16", ptr(lay.flat[lo:hi]), ptr(g16), hi - lo, 0, stream())
         if self.world > 1:
-            work = dist.all_reduce(lay.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            work = dist.all_reduce(g16 if g16 is not None else lay.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         if self.opt is None or not hasattr(self.opt, "step_range"):
             if work is not None:
                 self.pending.append(work)
+            if g16 is not None:
+                self._cast_back.append((lo, hi))
             return
         dev = lay.flat.device
         main = torch.cuda.current_stream(dev)
@@ -88,7 +105,7 @@ class DataParallel:
         with torch.cuda.stream(self.opt_stream):
             if work is not None:
                 work.wait()                                # ... and summed over the ranks
-            self.opt.step_range(lay, lo, hi)
+            self.opt.step_range(lay, lo, hi, grad16=g16)
 
     def ready(self, lay, lo, hi):
         if self.open is not None and self.open[1] == lo:
@@ -108,6 +125,11 @@ class DataParallel:
         for w in self.pending:
             w.wait()
         self.pending = []
+        if self._cast_back:                                     # no fused optimiser: hand the bf16 sums back as fp32 gradients
+            from ._lib import call, ptr, stream
+            for lo, hi in self._cast_back:
+                call("b2_cast_f32_bf16", ptr(lay.flat[lo:hi]), ptr(self.g16[lo:hi]), hi - lo, 1, stream())
+            self._cast_back = []
         if self._stepping:
             torch.cuda.current_stream(lay.flat.device).wait_stream(self.opt_stream)
             self._stepping = False
