@@ -73,13 +73,13 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
     return 0;
 }
 
+static int g_pdl = -1;
 bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) {
+    if (g_pdl < 0) {
         const char* e = getenv("SDM_B200_PDL");
-        v = (e && e[0] == '1') ? 1 : 0;
+        g_pdl = (e && e[0] == '1') ? 1 : 0;
     }
-    return v == 1;
+    return g_pdl == 1;
 }
 
 static int g_det = -1;
@@ -104,6 +104,7 @@ int option(const char* name, int default_value) {
 }
 int set_option(const char* name, int value) {
     if (!strcmp(name, "sm_limit")) { g_sm_limit = value > 0 ? value : 0; return 0; }
+    if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return 0; }
     for (auto& o : g_opts) if (!strcmp(o.name, name)) { o.value = value; o.set = true; return 0; }
     return set_error("b2_set_option: unknown option '%s'", name);
 }

@@ -20,8 +20,9 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
 // executes griddepcontrol.wait before it touches global memory, so the next kernel's CTAs may be scheduled -- and run their
 // prologue (barrier init, TMEM allocation, descriptor prefetch) -- while the previous grid drains, instead of paying the
 // full launch + ramp latency between ~1.3 k back-to-back launches per step.  The attribute survives CUDA-graph capture
-// (programmatic edges).  Measured on B200 inside CUDA-graph replay (tools/bench_train.py, bench.py): within -1 % .. 0 % of
-// plain stream order -- graph replay already hides the launch gap -- so it is OFF unless SDM_B200_PDL=1.
+// (programmatic edges).  Measured on B200 inside CUDA-graph replay: a win of 4 % for small workloads (64x64 batch 8, ~1300
+// launches of ~15 us) and a loss of 1 % for large ones (128x128 batch 32), so the host enables it per captured step by
+// workload size (b200/graph.py; b2_set_option("pdl", 0|1)); SDM_B200_PDL=0|1 forces it.
 bool pdl_enabled();
 
 // Deterministic mode (SDM_B200_DETERMINISTIC=1 or b2_set_deterministic): no floating-point atomics and no batch-size dependent

@@ -13,7 +13,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---------------------------------------------------------------- programmatic dependent launch
+// Kernels do NOT release their dependents early (B2_PDL_EARLY_TRIGGER restores that): the trigger is implicit at CTA exit, so
+// under programmatic dependent launch the next kernel's CTAs start as the previous grid's last wave drains -- instead of after
+// the full completion + launch gap -- but never occupy SM slots while the previous kernel still has waves to run.  MEASURED
+// (profiles/r02v_pdl_trigger_ab.log, train step): 64x64 batch 8: 19.40 ms without PDL, 18.89 ms early trigger, 18.67 ms implicit;
+// 128x128 batch 32: 84.9 / 86.7 / 85.8 ms -- PDL is therefore enabled per captured step only for small workloads (b200/graph.py).
+#ifdef B2_PDL_EARLY_TRIGGER
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier
