@@ -268,6 +268,21 @@ int b2_adam_flat_g16(float* p, const void* g_bf16, float* m, float* v, long long
 /* to_f32 == 0: dst_bf16[i] = bf16(src[i]); to_f32 != 0: src[i] = float(dst_bf16[i])  (gradient buckets around the bf16 all-reduce). */
 int b2_cast_f32_bf16(const float* src, void* dst_bf16, long long n, int to_f32, void* stream);
 
+/* b2_conv2d_nhwc (mode 0, bf16) whose epilogue also accumulates the pass-1 sums of the GroupNorm x AdaGN backward that will
+ * consume y as its `dout` (autograd of custom_layers.py:35-45 after :224-245): per (image, output channel)
+ * cs_s1 += sum_p y[p], cs_s2 += sum_p y[p] * swish(cs_z[p]); cs_z = that layer's pre-activation [N][H][W][Cout] (per-pixel
+ * stride cs_ldz), cs_s1 / cs_s2 = [N][Cout] fp32 zeroed by the caller.  Pair with b2_adagn_bwd_fused(sums_ready = 1). */
+int b2_conv2d_nhwc_colsum(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* wpacked,
+                          const float* bias, int Cout, void* y, long long ldy, int act, const void* residual, long long ldr,
+                          float* gn_stats, int gn_groups, int out_mode, int dtype, void* stream, const void* cs_z,
+                          long long cs_ldz, float* cs_s1, float* cs_s2);
+/* b2_adagn_bwd with sums_ready != 0: `work` = [2][N][C] already holds (sum_p dout, sum_p dout * swish(z)) from
+ * b2_conv2d_nhwc_colsum; the reduce pass is skipped (one pass of 6 bytes per element instead of 10). */
+int b2_adagn_bwd_fused(const void* dout, long long ldd, const void* z, long long ldz, const float* stats, const float* gamma,
+                       const float* beta, const float* s, long long s_bstride, float* work, float* ds, long long ds_bstride,
+                       float* dgamma, float* dbeta, void* dz, long long lddz, float* dbias, int N, int HW, int C, int groups,
+                       float eps, int sums_ready, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

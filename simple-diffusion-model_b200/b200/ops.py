@@ -32,7 +32,7 @@ def new_act(n, h, w, c, code, device):
     return torch.empty((n, h, w, c), dtype=TORCH_DTYPE[code], device=device)
 
 
-def conv2d(mode, x, wpacked, bias, cout, act=0, out=None, residual=None, gn_stats=None, groups=32, out_nchw_fp32=None):
+def conv2d(mode, x, wpacked, bias, cout, act=0, out=None, residual=None, gn_stats=None, groups=32, out_nchw_fp32=None, colsum=None):
     """mode 0: 3x3/s1; 1: 3x3/s2 (x = parity planes [4*N, H/2, W/2, C]); 2: transposed 4x4/s2;
     3: data gradient of mode 1 (x = dz); 4: data gradient of mode 2 (x = parity planes of dz)."""
     code = code_of(x)
@@ -48,6 +48,14 @@ def conv2d(mode, x, wpacked, bias, cout, act=0, out=None, residual=None, gn_stat
         y, out_mode = out, 0
         ldy = _nhwc(out)[4]
     ldr = _nhwc(residual)[4] if residual is not None else 0
+    if colsum is not None:
+        # (z, s1, s2): the epilogue also accumulates sum_p y and sum_p y * swish(z) per (image, channel) -- the pass-1 sums of
+        # the AdaGN backward that consumes y (b2_conv2d_nhwc_colsum)
+        cz, s1, s2 = colsum
+        call("b2_conv2d_nhwc_colsum", mode, ptr(x), n, h, w, cin, ldx, ptr(wpacked), ptr(bias), cout, ptr(y), ldy, act,
+             ptr(residual), ldr, ptr(gn_stats), groups if gn_stats is not None else 0, out_mode, code, stream(),
+             ptr(cz), _nhwc(cz)[4], ptr(s1), ptr(s2))
+        return y
     call("b2_conv2d_nhwc", mode, ptr(x), n, h, w, cin, ldx, ptr(wpacked), ptr(bias), cout, ptr(y), ldy, act,
          ptr(residual), ldr, ptr(gn_stats), groups if gn_stats is not None else 0, out_mode, code, stream())
     return y

@@ -187,6 +187,10 @@ class UNetTrainEngine(UNetEngine):
         self._side_stream = None
         self._side_busy = False
         self._side_keep = []               # operands of in-flight side-stream kernels (kept alive until the join)
+        # The data-gradient GEMM that produces an AdaGN layer's `dout` also emits that layer's pass-1 sums from its epilogue
+        # (b2_conv2d_nhwc_colsum), so the backward's reduce pass -- a full read of dout and z -- disappears for every layer
+        # whose gradient comes straight from a stride-1 conv.  SDM_B200_FUSE_ADAGN_SUMS=0 keeps the two-pass form.
+        self.fuse_adagn_sums = os.environ.get("SDM_B200_FUSE_ADAGN_SUMS", "1") != "0"
         self.post_backward = None          # optional callable(layout), runs when every gradient is complete
         self.on_grads_ready = None         # optional callable(layout, lo, hi): flat range [lo, hi) is final (DP buckets)
 
@@ -449,30 +453,43 @@ class UNetTrainEngine(UNetEngine):
         self._work_used += (numel + 3) // 4 * 4
         return out
 
-    def _dgrad_s1(self, conv, dz, residual=None, out=None):
+    def _dgrad_s1(self, conv, dz, residual=None, out=None, colsum=None):
         code = ops.code_of(dz)
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
         w = self.cache.get(conv.weight, 1, code, cout, cin, dz.shape[3])
-        return ops.conv2d(0, dz, w, None, cin, act=0, residual=residual, out=out)
+        return ops.conv2d(0, dz, w, None, cin, act=0, residual=residual, out=out, colsum=colsum)
 
-    def _bwd_gn_conv(self, rec, dout, ctx, residual=None, need_dx=True):
+    def _colsum_ok(self, z):
+        """Can the GEMM that produces this layer's `dout` also emit its pass-1 sums?  bf16, whole 32-channel chunks, and every
+        warp of 32 tile rows inside one image (the epilogue reduces over a warp)."""
+        n, hh, ww, c = z.shape
+        return self.fuse_adagn_sums and z.dtype == torch.bfloat16 and c % 32 == 0 and hh * ww >= 32 and (hh * ww) % 32 == 0
+
+    def _bwd_gn_conv(self, rec, dout, ctx, residual=None, need_dx=True, sums=None, next_sums=None):
+        """sums: this layer's [2][N][C] pass-1 sums, already accumulated by the GEMM that produced `dout` (raw form).
+        next_sums: (z, work) of the layer that will consume the data gradient produced here."""
         blk, x, z, stats, off = rec
         conv, gn = blk.conv_layer[0], blk.adagn.group_norm
         code = ops.code_of(z)
         n, hh, ww, c = z.shape
         lay = self.layout
-        work = self._bwd_work(2 * n * c, z.device)
+        work = sums if sums is not None else self._bwd_work(2 * n * c, z.device)
         dz = torch.empty((n, hh, ww, c), dtype=z.dtype, device=z.device)
         s = ctx["s_all"][:, off:off + c]
         ds = ctx["ds_all"][:, off:off + c]
-        call("b2_adagn_bwd", ptr(dout), dout.stride(2), ptr(z), z.stride(2), ptr(stats), ptr(gn.weight), ptr(gn.bias), ptr(s),
+        call("b2_adagn_bwd_fused", ptr(dout), dout.stride(2), ptr(z), z.stride(2), ptr(stats), ptr(gn.weight), ptr(gn.bias), ptr(s),
              ctx["s_bstride"], ptr(work), ptr(ds), ctx["total"] if ctx["be"] == n else 0, ptr(lay.view(gn.weight)),
              ptr(lay.view(gn.bias)), ptr(dz), dz.stride(2), ptr(lay.view(conv.bias)), n, hh * ww, c, gn.num_groups,
-             float(gn.eps), code, stream())
+             float(gn.eps), 1 if sums is not None else 0, code, stream())
         self._wgrad_conv(0, conv, x, dz, 0)
         if not need_dx:
             return None
-        return self._dgrad_s1(conv, dz, residual=residual)
+        colsum = None
+        if next_sums is not None:
+            zn, wn = next_sums
+            nc = zn.shape[0] * zn.shape[3]
+            colsum = (zn, wn[:nc], wn[nc:2 * nc])
+        return self._dgrad_s1(conv, dz, residual=residual, colsum=colsum)
 
     def _bwd_act(self, dy, z, dbias_view):
         code = ops.code_of(z)
@@ -498,7 +515,9 @@ class UNetTrainEngine(UNetEngine):
                 ctx = entry[2]
         d = None                     # running gradient w.r.t. the current activation (NHWC, compute dtype)
         d_skips = {}                 # level -> gradient arriving at a skip tensor through the concat buffer
-        for entry in reversed(tape):
+        order = list(reversed(tape))
+        pending = None               # pass-1 sums of the NEXT residual block's second AdaGN, filled by the GEMM that produced d
+        for pos, entry in enumerate(order):
             kind = entry[0]
             if kind == "last":
                 _, blk, h_in, y_tanh = entry
@@ -551,8 +570,19 @@ class UNetTrainEngine(UNetEngine):
                 d = d[..., :c_half]
             elif kind == "res":
                 _, rec1, rec2 = entry
-                da1 = self._bwd_gn_conv(rec2, d, ctx)
-                d = self._bwd_gn_conv(rec1, da1, ctx, residual=d)
+                z1 = rec1[2]
+                work1 = self._bwd_work(2 * z1.shape[0] * z1.shape[3], dev) if self._colsum_ok(z1) else None
+                da1 = self._bwd_gn_conv(rec2, d, ctx, sums=pending, next_sums=(z1, work1) if work1 is not None else None)
+                # does the block's input gradient go straight into another residual block (only marks in between)?
+                nxt = next((e for e in order[pos + 1:] if e[0] != "mark"), None)
+                work_next, z_next = None, None
+                if nxt is not None and nxt[0] == "res":
+                    z_next = nxt[2][2]
+                    if self._colsum_ok(z_next) and tuple(z_next.shape) == tuple(rec1[1].shape):
+                        work_next = self._bwd_work(2 * z_next.shape[0] * z_next.shape[3], dev)
+                d = self._bwd_gn_conv(rec1, da1, ctx, residual=d, sums=work1,
+                                      next_sums=(z_next, work_next) if work_next is not None else None)
+                pending = work_next
             elif kind == "attn":
                 _, blk, x_in, saved = entry
                 d = self._bwd_attention(blk, x_in, saved, d)

@@ -153,7 +153,7 @@ adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __res
                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ds,
                        long long ds_bstride, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        T* __restrict__ dz, long long lddz, float* __restrict__ dbias, int HW, int C,
-                       int groups, float eps, int slabs, int rows_per_block) {
+                       int groups, float eps, int slabs, int rows_per_block, int raw_sums) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float red[];
@@ -170,9 +170,18 @@ adagn_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __res
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         for (int g = warp; g < groups; g += nwarps) {
             float t1 = 0.f, t2 = 0.f;
+            // raw_sums: a2 arrives as sum_p dout * y from the producing GEMM's epilogue; a2 = rstd * (sum dout*y - mean * sum dout)
+            float g_mean = 0.f, g_rstd = 1.f;
+            if (raw_sums) {
+                const float2 st = __ldg(reinterpret_cast<const float2*>(stats + (long long)n * groups * 2) + g);
+                g_mean = st.x * inv_cnt;
+                g_rstd = rsqrtf(fmaxf(st.y * inv_cnt - g_mean * g_mean, 0.f) + eps);
+            }
             for (int j = lane; j < cpg; j += 32) {
                 const int c = g * cpg + j;
-                const float x1 = a1[(long long)n * C + c], x2 = a2[(long long)n * C + c];
+                const float x1 = a1[(long long)n * C + c];
+                float x2 = a2[(long long)n * C + c];
+                if (raw_sums) x2 = g_rstd * (x2 - g_mean * x1);
                 const float sc = __ldg(s + (long long)n * s_bstride + c), ga = __ldg(gamma + c);
                 if (slab == 0) {
                     atomicAdd(ds + (long long)n * ds_bstride + c, ga * x2 + (__ldg(beta + c) + 1.0f) * x1);
@@ -267,26 +276,38 @@ static void adagn_bwd_launch2(int grid, int threads, size_t red_bytes, cudaStrea
                               const void* z_c, long long ldz, const float* stats_c, float* a1, float* a2, const float* s_c,
                               long long s_bstride, const float* gamma, const float* beta, float* ds_c, long long ds_bstride,
                               float* dgamma, float* dbeta, void* dz_c, long long lddz, float* dbias, int HW, int C, int groups,
-                              float eps, int slabs, int rows_per_block) {
+                              float eps, int slabs, int rows_per_block, int sums_ready) {
+    if (!sums_ready)
     B2_LAUNCH((adagn_bwd_reduce_kernel<T, U, OCC>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, HW, C, groups, eps, slabs, rows_per_block);
-    B2_LAUNCH((adagn_bwd_apply_kernel<T, U, OCC>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (T*)dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block);
+    B2_LAUNCH((adagn_bwd_apply_kernel<T, U, OCC>), grid, threads, red_bytes, st, (const T*)d_c, ldd, (const T*)z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, (T*)dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block, sums_ready);
 }
-#define ADAGN_BWD_ARGS grid, threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block
+#define ADAGN_BWD_ARGS grid, threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, slabs, rows_per_block, sums_ready
 template <typename T>
 static void adagn_bwd_launch(int U, int occ, int grid, int threads, size_t red_bytes, cudaStream_t st, const void* d_c, long long ldd,
                              const void* z_c, long long ldz, const float* stats_c, float* a1, float* a2, const float* s_c,
                              long long s_bstride, const float* gamma, const float* beta, float* ds_c, long long ds_bstride,
                              float* dgamma, float* dbeta, void* dz_c, long long lddz, float* dbias, int HW, int C, int groups,
-                             float eps, int slabs, int rows_per_block) {
+                             float eps, int slabs, int rows_per_block, int sums_ready) {
     if (U == 4) adagn_bwd_launch2<T, 4, 2>(ADAGN_BWD_ARGS);
     else if (occ == 3) adagn_bwd_launch2<T, 2, 3>(ADAGN_BWD_ARGS);
     else adagn_bwd_launch2<T, 2, 2>(ADAGN_BWD_ARGS);
 }
 
+extern "C" int b2_adagn_bwd_fused(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
+                                  const float* gamma, const float* beta, const float* s, long long s_bstride, float* work,
+                                  float* ds, long long ds_bstride, float* dgamma, float* dbeta, void* dz, long long lddz,
+                                  float* dbias, int N, int HW, int C, int groups, float eps, int sums_ready, int dtype, void* stream);
 extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
                             const float* gamma, const float* beta, const float* s, long long s_bstride, float* work,
                             float* ds, long long ds_bstride, float* dgamma, float* dbeta, void* dz, long long lddz,
                             float* dbias, int N, int HW, int C, int groups, float eps, int dtype, void* stream) {
+    return b2_adagn_bwd_fused(dout, ldd, z, ldz, stats, gamma, beta, s, s_bstride, work, ds, ds_bstride, dgamma, dbeta, dz, lddz, dbias,
+                              N, HW, C, groups, eps, 0, dtype, stream);
+}
+extern "C" int b2_adagn_bwd_fused(const void* dout, long long ldd, const void* z, long long ldz, const float* stats,
+                                  const float* gamma, const float* beta, const float* s, long long s_bstride, float* work,
+                                  float* ds, long long ds_bstride, float* dgamma, float* dbeta, void* dz, long long lddz,
+                                  float* dbias, int N, int HW, int C, int groups, float eps, int sums_ready, int dtype, void* stream) {
     const int V = dtype == 0 ? 8 : 4;
     if (C % V || ldd % V || ldz % V || lddz % V) return set_error("b2_adagn_bwd: channel counts / strides must be 16-byte aligned");
     if (C % groups) return set_error("b2_adagn_bwd: C %% groups != 0");
@@ -319,9 +340,9 @@ extern "C" int b2_adagn_bwd(const void* dout, long long ldd, const void* z, long
         size_t red_bytes = (size_t)sl.rows_per_block * C * sizeof(float);
         if (red_bytes < (size_t)groups * 2 * sizeof(float)) red_bytes = (size_t)groups * 2 * sizeof(float);
         if (dtype == 0)
-            adagn_bwd_launch<bf16>(U, occ, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+            adagn_bwd_launch<bf16>(U, occ, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block, sums_ready);
         else
-            adagn_bwd_launch<float>(U, occ, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block);
+            adagn_bwd_launch<float>(U, occ, nc * sl.slabs, sl.threads, red_bytes, st, d_c, ldd, z_c, ldz, stats_c, a1, a2, s_c, s_bstride, gamma, beta, ds_c, ds_bstride, dgamma, dbeta, dz_c, lddz, dbias, HW, C, groups, eps, sl.slabs, sl.rows_per_block, sums_ready);
     }
     LAUNCH_CHECK("b2_adagn_bwd");
 }

@@ -126,10 +126,38 @@ static void pick_box(int W, int H, int N, int* wb, int* hb, int* nb, int rows = 
     if (*nb < 1) *nb = 1;
 }
 
+struct ColSum { const void* z; long long ldz; float* s1; float* s2; };
+static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
+                       const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
+                       const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
+                       int dtype, void* stream, const ColSum* cs);
+
 extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
                               const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
                               const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
                               int dtype, void* stream) {
+    return conv2d_impl(mode, x, N, H, W, Cin, ldx, wpacked, bias, Cout, y, ldy, act, residual, ldr, gn_stats, gn_groups, out_mode,
+                       dtype, stream, nullptr);
+}
+
+// b2_conv2d_nhwc (mode 0, bf16) whose epilogue ALSO accumulates, per (image, output channel), cs_s1 += sum_p y and
+// cs_s2 += sum_p y * swish(cs_z[p]) -- the pass-1 sums of the AdaGN backward that consumes y as its `dout` (cs_z = that layer's
+// pre-activation, [N][H][W][Cout] with per-pixel stride cs_ldz; cs_s1 / cs_s2: [N][Cout] fp32, zeroed by the caller).
+extern "C" int b2_conv2d_nhwc_colsum(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
+                                     const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
+                                     const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
+                                     int dtype, void* stream, const void* cs_z, long long cs_ldz, float* cs_s1, float* cs_s2) {
+    if (mode != 0 || dtype != 0 || out_mode != 0) return set_error("b2_conv2d_nhwc_colsum: plain bf16 3x3 stride-1 convolutions only");
+    if (!cs_z || !cs_s1 || !cs_s2 || Cout % 32 || (cs_ldz % 8) || ((uintptr_t)cs_z % 16)) return set_error("b2_conv2d_nhwc_colsum: bad column-sum arguments");
+    ColSum cs = {cs_z, cs_ldz, cs_s1, cs_s2};
+    return conv2d_impl(mode, x, N, H, W, Cin, ldx, wpacked, bias, Cout, y, ldy, act, residual, ldr, gn_stats, gn_groups, out_mode,
+                       dtype, stream, &cs);
+}
+
+static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
+                       const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
+                       const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
+                       int dtype, void* stream, const ColSum* cs) {
     const int eb = dtype == 0 ? 2 : 4;
     const int bk = 128 / eb;
     if (Cin % bk != 0) return set_error("b2_conv2d_nhwc: Cin=%d must be a multiple of %d", Cin, bk);
@@ -226,6 +254,10 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
         (void)oeb;
         p.vec_ok = ok ? 1 : 0;
     }
+    if (cs) {
+        p.cs_z = cs->z; p.cs_s1 = cs->s1; p.cs_s2 = cs->s2;
+        p.cs_zN = (long long)H * W * cs->ldz; p.cs_zH = (long long)W * cs->ldz; p.cs_zW = cs->ldz;
+    }
     long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     int bn, splits;
     pick_tiling(Cout, m_tiles, p.groups, p.taps * p.kb_per_tap, !det, &bn, &splits);
@@ -237,7 +269,7 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
     bool swapped = false;
     {
         const int swap_env = option("swap_ab", 0);
-        if (swap_env && mode == 0 && dtype == 0 && out_mode == 0 && Cout <= 128 && Cout >= 64 && p.cpg != 1 && !separate_stats && W <= 256) {
+        if (swap_env && !cs && mode == 0 && dtype == 0 && out_mode == 0 && Cout <= 128 && Cout >= 64 && p.cpg != 1 && !separate_stats && W <= 256) {
             int wb2, hb2, nb2;
             pick_box(W, H, N, &wb2, &hb2, &nb2, 256);
             const long long tiles2 = (long long)((W + wb2 - 1) / wb2) * ((H + hb2 - 1) / hb2) * ((N + nb2 - 1) / nb2);

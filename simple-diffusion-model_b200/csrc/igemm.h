@@ -53,6 +53,14 @@ struct IgemmParams {
     // image with one shared zero column per row (pitch P = W + 1: position f = h*P + w, w == W is the pad, produced by TMA's
     // out-of-bounds fill and skipped by the epilogue), halo = 1: tiles_w = ceil(H*P / 128), wb = 128;
     // or, for W % 128 == 0, one 128-pixel run of one image row, halo = 2 (box 130 x 3 rows, no pad positions).
+    // Column sums for the CONSUMER's GroupNorm x AdaGN backward (b2_conv2d_nhwc_colsum): the data-gradient GEMM that produces
+    // `dout` also emits, per (image, channel), cs_s1 += sum_p dout and cs_s2 += sum_p dout * swish(z) from its epilogue, z being
+    // the consumer's pre-activation (same pixel indexing as the output).  The backward's reduce pass (a full read of dout and z)
+    // disappears; the apply pass turns the raw sums into its a1 / a2 terms.
+    const void* cs_z;
+    long long cs_zN, cs_zH, cs_zW;
+    float* cs_s1;
+    float* cs_s2;
     // Swapped-operand mode for Cout <= 128 (BLOCK_N = 256 instance only): the MMA's 128 rows are OUTPUT CHANNELS (A = a 128-row
     // weights tile) and its 256 columns are PIXELS (B = the activation box, wb*hb*nb <= 256), i.e. D^T = W X^T.  A 128-channel
     // layer then runs the 128x256 MMA shape of the wide layers (measured 86-91 % tensor pipe) instead of 128x128 (40-48 %), and

@@ -110,6 +110,24 @@ __device__ __forceinline__ void gn_partial(const float (&v)[32], bool valid, boo
     }
 }
 
+// Column sums over the 32 lanes (pixels) of 32 per-lane values (channels): reduce-scatter butterfly, 31 shuffles; afterwards
+// a[0] of lane L is the sum of channel L.
+__device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
+#pragma unroll
+    for (int o = 16, cnt = 32; o > 0; o >>= 1, cnt >>= 1) {
+        const bool hi = (lane & o) != 0;
+        const int half = cnt / 2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < half) {
+                const float keep = hi ? a[i + half] : a[i];
+                const float send = hi ? a[i] : a[i + half];
+                a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+    }
+}
+
 // CL > 1: thread-block cluster of CL CTAs that work on CL consecutive M tiles of the SAME N tile.  The B (weight) tile
 // of every K step is identical for them, so each CTA fetches 1/CL of it and TMA-multicasts that piece to all: the L2 -> SM
 // operand traffic per CTA drops from A + B to A + B/CL (the main loop is bound by exactly that traffic, not by the MMA).
@@ -749,6 +767,41 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         } else {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) if (i < ncols) o[i * p.oC] = __float2bfloat16(v[i]);
+                        }
+                    }
+                }
+                if (p.cs_s1 && !f32out && ncols == 32) {
+                    // ---- column sums for the consumer's AdaGN backward (IgemmParams::cs_*): v holds this row's 32 final values
+                    float a[32];
+                    if (valid) {
+                        const __nv_bfloat16* zs = reinterpret_cast<const __nv_bfloat16*>(p.cs_z) + n * p.cs_zN + h * p.cs_zH + w * p.cs_zW + col0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 x = __ldg(reinterpret_cast<const uint4*>(zs) + i);
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __bfloat1622float2(h2[j]);
+                                a[8 * i + 2 * j] = v[8 * i + 2 * j] * swish_fast(f.x);
+                                a[8 * i + 2 * j + 1] = v[8 * i + 2 * j + 1] * swish_fast(f.y);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { a[i] = 0.f; v[i] = 0.f; }
+                    }
+                    if (uniform) {
+                        warp_colsum32(a, lane);
+                        warp_colsum32(v, lane);
+                        float* s1 = p.cs_s1 + (long long)n_lane0 * p.Cout + col0 + lane;
+                        float* s2 = p.cs_s2 + (long long)n_lane0 * p.Cout + col0 + lane;
+                        atomicAdd(s1, v[0]);
+                        atomicAdd(s2, a[0]);
+                    } else if (valid) {
+#pragma unroll 1
+                        for (int i = 0; i < 32; ++i) {
+                            atomicAdd(p.cs_s1 + (long long)n * p.Cout + col0 + i, v[i]);
+                            atomicAdd(p.cs_s2 + (long long)n * p.Cout + col0 + i, a[i]);
                         }
                     }
                 }

@@ -346,3 +346,42 @@ def _check_128_channel_conv(shape):
     wide = torch.full((n, h, w, 2 * c), 7.0, device="cuda", dtype=torch.bfloat16)
     ops.conv2d(0, xq, wp, bias, c, act=1, out=wide[..., c:])
     assert rel_l2(_nchw(wide[..., c:]), ref_pre) < 1e-2 and bool((wide[..., :c] == 7.0).all())
+
+
+@pytest.mark.parametrize("shape", [(10, 128, 64, 64), (4, 256, 32, 32), (3, 512, 16, 16), (2, 1024, 8, 8), (6, 512, 4, 8)])
+def test_conv_epilogue_emits_the_consumers_adagn_backward_sums(shape):
+    """b2_conv2d_nhwc_colsum: the data-gradient GEMM also accumulates sum_p y and sum_p y * swish(z) per (image, channel) for the
+    AdaGN backward that consumes y; with b2_adagn_bwd_fused(sums_ready=1) the one-pass backward must equal the two-pass one."""
+    from b200 import ops
+    from b200._lib import call, ptr, stream
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn((n, c, h, w), device="cuda", generator=g)
+    wt = torch.randn((c, c, 3, 3), device="cuda", generator=g) * (1.0 / (c * 9) ** 0.5)
+    res = torch.randn((n, c, h, w), device="cuda", generator=g)
+    z = torch.randn((n, c, h, w), device="cuda", generator=g)
+    xq, rq, zq = _nhwc(x, torch.bfloat16), _nhwc(res, torch.bfloat16), _nhwc(z, torch.bfloat16)
+    wp = ops.pack_weight(0, wt, c, c, c, 0)
+    work = torch.zeros(2 * n * c, device="cuda")
+    y = ops.conv2d(0, xq, wp, None, c, act=0, residual=rq, colsum=(zq, work[:n * c], work[n * c:]))
+    y_plain = ops.conv2d(0, xq, wp, None, c, act=0, residual=rq)
+    assert rel_l2(_nchw(y), _nchw(y_plain)) < 1e-6
+    yf, sw = _nchw(y_plain), swish(_nchw(zq))
+    assert rel_l2(work[:n * c].reshape(n, c), yf.sum(dim=(2, 3))) < 5e-3
+    assert rel_l2(work[n * c:].reshape(n, c), (yf * sw).sum(dim=(2, 3))) < 5e-3
+    # one-pass backward from the raw sums == two-pass backward
+    yy = sw.reshape(n, 32, -1)
+    stats = torch.stack((yy.sum(-1), (yy * yy).sum(-1)), dim=-1).contiguous()
+    gamma = 1 + 0.2 * torch.randn(c, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(c, device="cuda", generator=g)
+    s = torch.randn((n, c), device="cuda", generator=g)
+    outs = []
+    for ready, wk in ((1, work), (0, torch.zeros(2 * n * c, device="cuda"))):
+        ds = torch.zeros((n, c), device="cuda")
+        dgamma, dbeta, dbias = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+        dz = torch.empty_like(zq)
+        call("b2_adagn_bwd_fused", ptr(y_plain), c, ptr(zq), c, ptr(stats), ptr(gamma), ptr(beta), ptr(s), c, ptr(wk), ptr(ds), c,
+             ptr(dgamma), ptr(dbeta), ptr(dz), c, ptr(dbias), n, h * w, c, 32, 1e-5, ready, 0, stream())
+        outs.append((dz.float(), ds, dgamma, dbeta, dbias))
+    for a, b in zip(outs[0], outs[1]):
+        assert rel_l2(a, b) < 1e-2
