@@ -187,10 +187,14 @@ class UNetTrainEngine(UNetEngine):
         self._side_stream = None
         self._side_busy = False
         self._side_keep = []               # operands of in-flight side-stream kernels (kept alive until the join)
-        # The data-gradient GEMM that produces an AdaGN layer's `dout` also emits that layer's pass-1 sums from its epilogue
-        # (b2_conv2d_nhwc_colsum), so the backward's reduce pass -- a full read of dout and z -- disappears for every layer
-        # whose gradient comes straight from a stride-1 conv.  SDM_B200_FUSE_ADAGN_SUMS=0 keeps the two-pass form.
-        self.fuse_adagn_sums = os.environ.get("SDM_B200_FUSE_ADAGN_SUMS", "1") != "0"
+        # SDM_B200_FUSE_ADAGN_SUMS=1: the data-gradient GEMM that produces an AdaGN layer's `dout` also emits that layer's pass-1
+        # sums from its epilogue (b2_conv2d_nhwc_colsum), so the backward's reduce pass -- a full read of dout and z -- disappears
+        # for every layer whose gradient comes straight from a stride-1 conv (90 of 100).  Implemented, parity-tested and
+        # MEASURED SLOWER (profiles/r02x_fused_adagn_sums_ab.log, 128x128 batch 32: 90.6 ms two-pass, 92.8 ms fused everywhere,
+        # 92.1 / 91.2 ms fused only for >= 512 / 1024 channels): the extra 62 shuffles + 64 atomics + Swish per 32x32 chunk
+        # lengthen the GEMM epilogues by more than the 2 ms of memory-bound reduce passes they remove.  Hence OFF by default.
+        self.fuse_adagn_sums = os.environ.get("SDM_B200_FUSE_ADAGN_SUMS", "0") == "1"
+        self.fuse_adagn_min_c = int(os.environ.get("SDM_B200_FUSE_ADAGN_MIN_C", "0"))
         self.post_backward = None          # optional callable(layout), runs when every gradient is complete
         self.on_grads_ready = None         # optional callable(layout, lo, hi): flat range [lo, hi) is final (DP buckets)
 
@@ -463,7 +467,8 @@ class UNetTrainEngine(UNetEngine):
         """Can the GEMM that produces this layer's `dout` also emit its pass-1 sums?  bf16, whole 32-channel chunks, and every
         warp of 32 tile rows inside one image (the epilogue reduces over a warp)."""
         n, hh, ww, c = z.shape
-        return self.fuse_adagn_sums and z.dtype == torch.bfloat16 and c % 32 == 0 and hh * ww >= 32 and (hh * ww) % 32 == 0
+        return self.fuse_adagn_sums and z.dtype == torch.bfloat16 and c % 32 == 0 and hh * ww >= 32 and (hh * ww) % 32 == 0 \
+            and c >= self.fuse_adagn_min_c
 
     def _bwd_gn_conv(self, rec, dout, ctx, residual=None, need_dx=True, sums=None, next_sums=None):
         """sums: this layer's [2][N][C] pass-1 sums, already accumulated by the GEMM that produced `dout` (raw form).
