@@ -62,3 +62,20 @@ def test_unet_backward_matches_reference(name, precision):
     assert total < TOL[precision][0]
     bad = [(n, e) for e, n in errs if e >= TOL[precision][1]]
     assert not bad, bad[:20]
+
+
+def test_fused_adagn_sums_backward_equals_the_two_pass_backward():
+    """Opt-in mode (SDM_B200_FUSE_ADAGN_SUMS=1): the data-gradient GEMMs emit the next AdaGN backward's pass-1 sums from their
+    epilogues and the reduce pass is skipped -- same gradients as the default two-pass backward (bf16 mode, rounding only)."""
+    fx = load_golden("unet_gpu_cond.pt")
+    cond = fx["cond"].cuda()
+    grads = []
+    for fused in (False, True):
+        net = _build(fx, "bf16")
+        net.engine().fuse_adagn_sums = fused
+        out = net(fx["x"].cuda(), fx["t"].cuda(), cond)
+        F.mse_loss(out, fx["target"].cuda()).backward()
+        grads.append(net.engine().layout.flat.clone())
+    err = rel_l2(grads[1], grads[0])
+    print("fused vs two-pass gradient rel-L2:", err)
+    assert err < 2e-2
