@@ -2,6 +2,8 @@
 // query-axis softmax, batched transpose, sinusoidal embedding, small fp32 linear.  All are vectorised
 // (16-byte accesses where the layout allows) and sized in multiples of the SM count.
 #include "host_util.h"
+#include <cstring>
+#include <cstdlib>
 #include "ptx.cuh"
 #include "stream.cuh"
 #include "sdm_b200.h"
@@ -434,8 +436,28 @@ extern "C" int b2_adagn_apply(const void* y, long long ldy, const float* stats, 
     if (cv > 1024) return set_error("b2_adagn_apply: C too large");
     const int sms = device_sm_count();
     int k = 256 / cv; if (k < 1) k = 1;
-    int slabs = (8 * sms + N - 1) / N;
     const int max_slabs = (HW + 4 * k - 1) / (4 * k);
+    // grid = the fewest slabs per image whose waves of (SMs x 3 resident CTAs: 80 registers, 256 threads) are >= 92 % full, up to
+    // ~4 waves (same rule as the backward passes, csrc/backward.cu: a ragged last wave idles a third of the machine);
+    // SDM_B200_APPLY_GRID=legacy restores ceil(8 * SMs / N)
+    static const bool legacy_grid = [] { const char* e = getenv("SDM_B200_APPLY_GRID"); return e && !strcmp(e, "legacy"); }();
+    int slabs = 1;
+    if (legacy_grid) {
+        slabs = (8 * sms + N - 1) / N;
+    } else {
+        const int slots = sms * 3;
+        int hi = (4 * slots) / N + 1;
+        if (hi > max_slabs) hi = max_slabs;
+        if (hi < 1) hi = 1;
+        double best = -1.0;
+        for (int cand = 1; cand <= hi; ++cand) {
+            const long long total = (long long)N * cand;
+            const long long waves = (total + slots - 1) / slots;
+            const double eff = (double)total / (double)(waves * slots);
+            if (eff > best + 1e-9) { best = eff; slabs = cand; }
+            if (eff >= 0.92) { slabs = cand; break; }
+        }
+    }
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
     if (dtype == 0)
