@@ -51,6 +51,10 @@ int b2_set_workspace(void* ws, long long bytes);
  * mode 3: data gradient of mode 1: x = dz [N][H][W][Cin=fwd Cout], y = dx [N][2H][2W][Cout=fwd Cin], weights kind 5
  * mode 4: data gradient of mode 2: x = parity planes of dz [2][2][N][H][W][fwd Cout], y = dx [N][H][W], weights kind 6
  *         (data gradient of mode 0 is mode 0 itself with weights of kind 1)
+ * mode 5: data gradient of mode 0 straight from the FORWARD weights (bf16 only): x = dz [N][H][W][Cin = fwd Cout],
+ *         wpacked = the forward kernel layout [fwd Cout][9][fwd Cin] (kind 0 / the optimiser's bf16 copy of a channels-last
+ *         stored weight), Cout = fwd Cin; both channel counts multiples of 64.  The weights are consumed MN-major with the
+ *         taps mirrored, so no transposed copy (kind 1) is made (autograd of custom_layers.py:224).
  * wpacked: weights in kernel layout from b2_pack_conv_weight. act: 0 none, 1 Swish (custom_layers.py:18-20), 2 tanh,
  * 3 = store the pre-activation but accumulate the GroupNorm statistics of Swish(value) (training forward).
  * residual (optional, mode 0/1): added after the activation. gn_stats (optional): [N][gn_groups][2] fp32,

@@ -86,6 +86,11 @@ class GraphedTrainStep:
                        "cond_img": clone(cond_img), "target": clone(target), "loss": torch.zeros((), dtype=torch.float32, device=dev)}
         n, _, h, w = x0.shape
         _auto_pdl(n, h, w)
+        import os
+        if os.environ.get("SDM_B200_OVERLAP_WGRAD") not in ("0", "1"):
+            # small workloads are bound by the length of ~1.3 k short dependent kernels: weight gradients (off the critical path)
+            # go to a second stream (measured at 64x64 batch 8 together with PDL: -5.6 %; neutral or worse at 128x128 batch 32)
+            self.net.engine().overlap_wgrad = n * h * w <= PDL_MAX_PIXELS
         out_ch = self.net.out_layers[1].conv_layer[0].weight.shape[0]
         self.static["dpred"] = torch.empty((n, out_ch, h, w), dtype=torch.float32, device=dev)
         lay = self.net.engine().grad_layout(dev)

@@ -65,9 +65,9 @@ class GradLayout:
         self.offsets, off = {}, 0
         for p in self.params:
             self.offsets[id(p)] = off
-            off += (p.numel() + 7) // 8 * 8          # keep every fp32 view 32-byte and every bf16 shadow view 16-byte aligned (TMA base)
+            off += self._span(p)
         self.total = off
-        self.front_end = sum((p.numel() + 7) // 8 * 8 for p in ys_w + ys_b)
+        self.front_end = sum(self._span(p) for p in ys_w + ys_b)
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
         self.views = {id(p): self._shaped(self.flat, p) for p in self.params}
         self.params_flat = None
@@ -79,8 +79,19 @@ class GradLayout:
             p._b2_layout = self
         self.adagn_w_numel = sum(p.numel() for p in ys_w)
         self.adagn_b_numel = sum(p.numel() for p in ys_b)
-        # y_scale weights have numel % 4 == 0 whenever C % 4 == 0, so the concatenated views are dense
-        self.dense_adagn = all(p.numel() % 8 == 0 for p in ys_w + ys_b)
+        # the concatenated y_scale views are dense when no tensor needs padding up to the next ALIGN boundary
+        self.dense_adagn = all(p.numel() % self.ALIGN == 0 for p in ys_w + ys_b)
+
+    # Every tensor starts on a 128-element boundary: 256 bytes in the bf16 copy the tensor-core kernels read through TMA, 512 bytes
+    # in the fp32 buffers.  With the 8-element (16-byte) granularity of round 1 everything behind the 3-element bias of the last
+    # conv sat 16 bytes off: each 128-byte TMA row of a weight tile then straddled two L2 lines.  MEASURED (round 2, 128x128 batch
+    # 32): data gradients reading the forward weights in place were 3.5 ms per step slower than through freshly allocated
+    # (aligned) transposed copies although the kernels are equally fast on aligned buffers.
+    ALIGN = 128
+
+    @classmethod
+    def _span(cls, p):
+        return (p.numel() + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
 
     def _shaped(self, flat, p):
         """The slice of `flat` that belongs to p, shaped like p (a permuted view for channels-last stored weights)."""
@@ -134,7 +145,7 @@ class GradLayout:
     def module_range(self, module):
         """Flat range covered by a module's live parameters, AdaGN scale Linears excluded (they live in the front
         region).  Contiguous by construction of the bucket order."""
-        offs = [(self.offsets[id(p)], self.offsets[id(p)] + (p.numel() + 7) // 8 * 8) for p in module.parameters()
+        offs = [(self.offsets[id(p)], self.offsets[id(p)] + self._span(p)) for p in module.parameters()
                 if id(p) in self.offsets and self.offsets[id(p)] >= self.front_end]
         if not offs:
             return 0, 0
@@ -195,6 +206,8 @@ class UNetTrainEngine(UNetEngine):
         # lengthen the GEMM epilogues by more than the 2 ms of memory-bound reduce passes they remove.  Hence OFF by default.
         self.fuse_adagn_sums = os.environ.get("SDM_B200_FUSE_ADAGN_SUMS", "0") == "1"
         self.fuse_adagn_min_c = int(os.environ.get("SDM_B200_FUSE_ADAGN_MIN_C", "0"))
+        # data gradients of the 3x3 stride-1 convs read the forward weights MN-major (SDM_B200_DGRAD_FROM_FWD=0: transposed copies)
+        self.dgrad_from_fwd = os.environ.get("SDM_B200_DGRAD_FROM_FWD", "1") == "1"
         self.post_backward = None          # optional callable(layout), runs when every gradient is complete
         self.on_grads_ready = None         # optional callable(layout, lo, hi): flat range [lo, hi) is final (DP buckets)
 
@@ -460,6 +473,12 @@ class UNetTrainEngine(UNetEngine):
     def _dgrad_s1(self, conv, dz, residual=None, out=None, colsum=None):
         code = ops.code_of(dz)
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        lay = self.layout
+        if self.dgrad_from_fwd and code == ops.BF16 and lay is not None and lay.shadow is not None and lay.is_cl(conv.weight) \
+                and dz.shape[3] == cout and cout % 64 == 0 and cin % 64 == 0:
+            # the optimiser's bf16 copy [Cout][3][3][Cin] is consumed MN-major with mirrored taps (b2_conv2d_nhwc mode 5): no
+            # transposed weight copy, no per-step transpose launch
+            return ops.conv2d(5, dz, lay.shadow_slice(conv.weight), None, cin, act=0, residual=residual, out=out, colsum=colsum)
         w = self.cache.get(conv.weight, 1, code, cout, cin, dz.shape[3])
         return ops.conv2d(0, dz, w, None, cin, act=0, residual=residual, out=out, colsum=colsum)
 

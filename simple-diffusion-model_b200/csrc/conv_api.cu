@@ -147,7 +147,7 @@ extern "C" int b2_conv2d_nhwc_colsum(int mode, const void* x, int N, int H, int 
                                      const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
                                      const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
                                      int dtype, void* stream, const void* cs_z, long long cs_ldz, float* cs_s1, float* cs_s2) {
-    if (mode != 0 || dtype != 0 || out_mode != 0) return set_error("b2_conv2d_nhwc_colsum: plain bf16 3x3 stride-1 convolutions only");
+    if ((mode != 0 && mode != 5) || dtype != 0 || out_mode != 0) return set_error("b2_conv2d_nhwc_colsum: plain bf16 3x3 stride-1 convolutions only");
     if (!cs_z || !cs_s1 || !cs_s2 || Cout % 32 || (cs_ldz % 8) || ((uintptr_t)cs_z % 16)) return set_error("b2_conv2d_nhwc_colsum: bad column-sum arguments");
     ColSum cs = {cs_z, cs_ldz, cs_s1, cs_s2};
     return conv2d_impl(mode, x, N, H, W, Cin, ldx, wpacked, bias, Cout, y, ldy, act, residual, ldr, gn_stats, gn_groups, out_mode,
@@ -162,9 +162,17 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
     const int bk = 128 / eb;
     if (Cin % bk != 0) return set_error("b2_conv2d_nhwc: Cin=%d must be a multiple of %d", Cin, bk);
     if (out_mode != 0 && (mode != 0 || residual)) return set_error("b2_conv2d_nhwc: NCHW fp32 output only for the plain 3x3 conv");
-    if (mode < 0 || mode > 4) return set_error("b2_conv2d_nhwc: bad mode %d", mode);
+    if (mode < 0 || mode > 5) return set_error("b2_conv2d_nhwc: bad mode %d", mode);
+    // mode 5 = data gradient of the 3x3/s1 conv straight from the FORWARD weights (igemm.h: b_mn): x = dz [N][H][W][Cin = Cout_f],
+    // wpacked = the bf16 forward weights [Cout_f][9][Cin_f], Cout = Cin_f.  Everything else is mode 0.
+    const bool b_mn = mode == 5;
+    if (b_mn) {
+        if (dtype != 0 || out_mode != 0 || Cout % 64 || Cin % 64) return set_error("b2_conv2d_nhwc mode 5: bf16, whole 64-channel slabs only");
+        mode = 0;
+    }
     IgemmParams p;
     memset(&p, 0, sizeof(p));
+    p.b_mn = b_mn ? 1 : 0;
     p.W = W; p.H = H; p.N = N;
     pick_box(W, H, N, &p.wb, &p.hb, &p.nb);
     p.tiles_w = (W + p.wb - 1) / p.wb;
@@ -269,7 +277,7 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
     bool swapped = false;
     {
         const int swap_env = option("swap_ab", 0);
-        if (swap_env && !cs && mode == 0 && dtype == 0 && out_mode == 0 && Cout <= 128 && Cout >= 64 && p.cpg != 1 && !separate_stats && W <= 256) {
+        if (swap_env && !cs && !b_mn && mode == 0 && dtype == 0 && out_mode == 0 && Cout <= 128 && Cout >= 64 && p.cpg != 1 && !separate_stats && W <= 256) {
             int wb2, hb2, nb2;
             pick_box(W, H, N, &wb2, &hb2, &nb2, 256);
             const long long tiles2 = (long long)((W + wb2 - 1) / wb2) * ((H + hb2 - 1) / hb2) * ((N + nb2 - 1) / nb2);
@@ -328,6 +336,7 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
     p.b_mode = 0;
     p.splits = splits; p.ws = workspace(0).ws; p.ws_counters = workspace(0).counters;
     p.cluster = swapped ? 1 : pick_cluster(dtype, bn, splits, m_tiles * p.groups * p.n_tiles, m_tiles);
+    if (b_mn && p.cluster > bn / 64) p.cluster = bn / 64;
 
     CUtensorMap ta, tb;
     {
@@ -335,12 +344,22 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
         uint64_t str[3] = {(uint64_t)ldx * eb, (uint64_t)W * ldx * eb, (uint64_t)H * W * ldx * eb};
         if (make_tmap_4d(&ta, x, eb, dims, str, a_box)) return 1;
     }
-    {
+    if (b_mn) {
+        // (64 Cin_f of one slab | Cout_f rows | Cin_f slabs | tap) over [Cout_f][9][Cin_f]; box = 64 K rows x (bn/64)/CL slabs
+        uint64_t dims[4] = {64, (uint64_t)Cin, (uint64_t)Cout / 64, 9};
+        uint64_t str[3] = {(uint64_t)9 * Cout * eb, 128, (uint64_t)Cout * eb};
+        uint32_t box[4] = {64, 64, (uint32_t)(bn / 64 / p.cluster), 1};
+        if (make_tmap_4d(&tb, wpacked, eb, dims, str, box)) return 1;
+    } else {
         const uint64_t ktot = (uint64_t)p.taps * Cin;
         uint64_t dims[4] = {ktot, (uint64_t)Cout, (uint64_t)p.groups, 1};
         uint64_t str[3] = {ktot * eb, ktot * Cout * eb, ktot * Cout * p.groups * eb};
         uint32_t box[4] = {(uint32_t)bk, (uint32_t)(swapped ? 128 : bn / p.cluster), 1, 1};      // cluster mode: each CTA fetches 1/CL of the B tile
         if (make_tmap_4d(&tb, wpacked, eb, dims, str, box)) return 1;
+    }
+    {   // weights of >= 1 MiB are prefetched into L2 by the kernel itself (igemm.h: pf_ptr); "l2_prefetch" 0 disables it
+        const long long wbytes = (b_mn ? 9LL * Cin * Cout : (long long)p.taps * Cin * Cout * p.groups) * eb;
+        if (option("l2_prefetch", 1) && wbytes >= (1 << 20) && ((uintptr_t)wpacked % 16) == 0) { p.pf_ptr = wpacked; p.pf_bytes = wbytes & ~15LL; }
     }
     if (launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;
     if (separate_stats) return launch_gn_stats(y, ldy, gn_stats, N, H * W, Cout, gn_groups, act == 3 ? 1 : 0, dtype, (cudaStream_t)stream, det);
@@ -604,12 +623,17 @@ extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int
         const long long items = (long long)p.splits * p.m_tiles * p.n_tiles * p.taps;
         p.cluster = (tn_cl == 2 && dtype == 0 && p.m_tiles % 2 == 0 && bn >= 128 && items >= device_sm_count()) ? 2 : 1;
     }
+    // slab maps (one TMA instruction per operand box instead of one per 128-byte slab) need whole slabs of channels
+    p.box5 = (option("tn_box5", 1) && Cin % slab == 0 && Cout % slab == 0) ? 1 : 0;
+    const int a_slabs = 128 / slab, b_slabs = bn / slab;
+    const uint32_t spb_b = (uint32_t)tn_spb_b(b_slabs, a_slabs, p.cluster);
     CUtensorMap ta, tb;
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)b_images};
         uint64_t str[3] = {(uint64_t)ldx * eb, (uint64_t)W * ldx * eb, (uint64_t)H * W * ldx * eb};
         uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
-        if (make_tmap_4d(&tb, x, eb, dims, str, box, dtype == 1)) return 1;
+        if (p.box5 ? make_tmap_5d_slabs(&tb, x, eb, dims, str, box, spb_b, dtype == 1)
+                   : make_tmap_4d(&tb, x, eb, dims, str, box, dtype == 1)) return 1;
     }
     for (int g = 0; g < n_groups; ++g) {
         const char* dz_base = (const char*)dz;
@@ -630,7 +654,8 @@ extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int
             pg.out = grad_packed + (long long)g * Cout * 4 * Cin;
         }
         uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
-        if (make_tmap_4d(&ta, dz_base, eb, dims, str, box, dtype == 1)) return 1;
+        if (p.box5 ? make_tmap_5d_slabs(&ta, dz_base, eb, dims, str, box, (uint32_t)a_slabs, dtype == 1)
+                   : make_tmap_4d(&ta, dz_base, eb, dims, str, box, dtype == 1)) return 1;
         if (launch_gemm_tn(dtype, ta, tb, pg, bn, (cudaStream_t)stream)) return 1;
     }
     return 0;
@@ -660,20 +685,23 @@ extern "C" int b2_gemm_tn(const void* A, long long lda, long long a_s1, long lon
     p.out_mode = out_mode; p.alpha = alpha;
     tn_pick_splits(&p, batch1 * batch2, bn);
     const int slab = 128 / eb;
+    p.box5 = (option("tn_box5", 1) && M % slab == 0 && Ncols % slab == 0) ? 1 : 0;
     CUtensorMap ta, tb;
     {
         uint64_t dims[4] = {(uint64_t)M, (uint64_t)K, (uint64_t)batch1, (uint64_t)batch2};
         uint64_t str[3] = {(uint64_t)lda * eb, (uint64_t)(batch1 > 1 ? a_s1 : lda * K) * eb,
                            (uint64_t)(batch2 > 1 ? a_s2 : lda * K * batch1) * eb};
         uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, 1, 1};
-        if (make_tmap_4d(&ta, A, eb, dims, str, box, dtype == 1)) return 1;
+        if (p.box5 ? make_tmap_5d_slabs(&ta, A, eb, dims, str, box, (uint32_t)(128 / slab), dtype == 1)
+                   : make_tmap_4d(&ta, A, eb, dims, str, box, dtype == 1)) return 1;
     }
     {
         uint64_t dims[4] = {(uint64_t)Ncols, (uint64_t)K, (uint64_t)batch1, (uint64_t)batch2};
         uint64_t str[3] = {(uint64_t)ldb * eb, (uint64_t)(batch1 > 1 ? b_s1 : ldb * K) * eb,
                            (uint64_t)(batch2 > 1 ? b_s2 : ldb * K * batch1) * eb};
         uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, 1, 1};
-        if (make_tmap_4d(&tb, B, eb, dims, str, box, dtype == 1)) return 1;
+        if (p.box5 ? make_tmap_5d_slabs(&tb, B, eb, dims, str, box, (uint32_t)tn_spb_b(bn / slab, 128 / slab, 1), dtype == 1)
+                   : make_tmap_4d(&tb, B, eb, dims, str, box, dtype == 1)) return 1;
     }
     return launch_gemm_tn(dtype, ta, tb, p, bn, (cudaStream_t)stream);
 }

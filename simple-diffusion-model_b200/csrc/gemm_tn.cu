@@ -61,6 +61,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int UMMA_K = 32 / sizeof(T);                // 16 (bf16) / 8 (tf32)
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+    // slab-map mode (p.box5): slabs per B box / number of B boxes (igemm.h: tn_spb_b, shared with the host)
+    constexpr int SPB_B = tn_spb_b(B_SLABS, A_SLABS, CL);
+    constexpr int NB_B = B_SLABS / SPB_B;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,6 +116,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     const int k_boxes = p.kt_w * p.kt_h * p.kt_n;
     const uint32_t box_rows = static_cast<uint32_t>(p.wb * p.hb * p.nb);
+    const uint32_t slab_stride = p.box5 ? box_rows * 128u : static_cast<uint32_t>(SLAB_BYTES);     // bytes between MN slabs in smem
 
     if (warp == 0 || warp >= 2 + kTnEpiWarps) {
         // TMA producer warps (lane 0 of each): a stage is 2 + BLOCK_N/64 slab loads (one 128-byte-wide box each: the
@@ -142,6 +146,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
                     if (elect_one()) {
                     if (prod == 0) mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
+                    if (p.box5) {
+                        // slab maps: the whole A operand of the stage is one box (producer 0), B is NB_B boxes of SPB_B slabs
+                        // (producers 1, 2, ...): at most one TMA instruction per producer warp and stage
+                        if (prod == 0) tma_load_5d(a_dst, &tmA, &full[s], 0, w0, h0, n0, wk.mt * A_SLABS);
+#pragma unroll
+                        for (int j = 0; j < NB_B; ++j) {
+                            if (((1 + j) % n_prod) != prod) continue;
+                            uint8_t* dst = b_dst + j * SPB_B * slab_stride;
+                            const int sl0 = wk.nt_in_tap * B_SLABS + j * SPB_B;
+                            if constexpr (CL > 1) {
+                                if ((j % CL) != crank) continue;
+                                tma_load_5d_mc(dst, &tmB, &full[s], 0, bw, bh, bn, sl0, kMask);
+                            } else {
+                                tma_load_5d(dst, &tmB, &full[s], 0, bw, bh, bn, sl0);
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int sl = 0; sl < A_SLABS + B_SLABS; ++sl) {
                         if ((sl % n_prod) != prod) continue;
@@ -159,6 +180,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     }
+                    }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -169,8 +191,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // warp-uniform issue loop (ptx.cuh: elect_one): all lanes wait and compute the descriptors, one elected lane issues
             constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 1, 1);
             // bf16: 8-row atoms (1024 B) of 16-byte chunks; tf32: 4-row atoms (512 B) of 32-byte chunks
-            const uint64_t desc0 = umma_desc_sw128(0, SLAB_BYTES, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
-            const uint32_t smem0 = smem_u32(smem);
+            const uint64_t desc0 = umma_desc_sw128(0, slab_stride, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
+            const uint32_t smem0 = smem_u32(smem) & 0x3FFFFu;      // CTA-local offset (see ptx.cuh: umma_desc_sw128)
             constexpr uint32_t K_STEP = (UMMA_K * 128) >> 4;                 // descriptor units (16 B) per MMA K step
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;

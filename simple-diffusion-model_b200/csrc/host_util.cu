@@ -73,6 +73,29 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
     return 0;
 }
 
+int make_tmap_5d_slabs(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4],
+                       const uint64_t strides_bytes[3], const uint32_t box[4], uint32_t slabs_per_box, bool atom32) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("TMA base pointer not 16-byte aligned");
+    const uint64_t slab = 128 / elem_bytes;
+    if (dims[0] % slab) return set_error("TMA slab map: %llu channels are not whole 128-byte slabs", (unsigned long long)dims[0]);
+    cuuint64_t gd[5] = {slab, dims[1], dims[2], dims[3], dims[0] / slab};
+    cuuint64_t gs[4] = {strides_bytes[0], strides_bytes[1], strides_bytes[2], 128};
+    cuuint32_t bx[5] = {(cuuint32_t)slab, box[1], box[2], box[3], slabs_per_box};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 3; ++i)
+        if (gs[i] % 16 != 0) return set_error("TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(out, dt, 5, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error("cuTensorMapEncodeTiled (5-D slabs) failed (%d): dims %llu %llu %llu %llu box %u %u %u x %u slabs", (int)r,
+                         (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                         (unsigned long long)dims[3], box[1], box[2], box[3], slabs_per_box);
+    return 0;
+}
+
 static int g_pdl = -1;
 bool pdl_enabled() {
     if (g_pdl < 0) {
@@ -93,7 +116,8 @@ bool deterministic_mode() {
 void set_deterministic_mode(int on) { g_det = on ? 1 : 0; }
 
 struct Opt { const char* name; const char* env; int value; bool set; };
-static Opt g_opts[] = {{"halo", "SDM_B200_HALO", 0, false}, {"swap_ab", "SDM_B200_SWAP_AB", 0, false}};
+static Opt g_opts[] = {{"halo", "SDM_B200_HALO", 0, false}, {"swap_ab", "SDM_B200_SWAP_AB", 0, false},
+                       {"tn_box5", "SDM_B200_TN_BOX5", 0, false}, {"l2_prefetch", "SDM_B200_L2_PREFETCH", 0, false}};
 int option(const char* name, int default_value) {
     for (auto& o : g_opts) {
         if (strcmp(o.name, name)) continue;

@@ -16,6 +16,12 @@ int device_sm_count();
 int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4],
                  const uint64_t strides_bytes[3], const uint32_t box[4], bool atom32 = false);
 
+// 5-D variant for MN-major operands (gemm_tn.cu): dims = (elements of one 128-byte slab | d1 | d2 | d3 | slab index), the slab
+// dimension having a stride of 128 bytes, so that a box of `box[4]` slabs lands in shared memory as consecutive
+// [rows][128 B] slabs -- the layout the MN-major UMMA descriptor walks with its leading-byte offset -- from ONE TMA instruction.
+int make_tmap_5d_slabs(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4],
+                       const uint64_t strides_bytes[3], const uint32_t box[4], uint32_t slabs_per_box, bool atom32 = false);
+
 // Programmatic dependent launch (PDL): every kernel of this library begins with griddepcontrol.launch_dependents and
 // executes griddepcontrol.wait before it touches global memory, so the next kernel's CTAs may be scheduled -- and run their
 // prologue (barrier init, TMEM allocation, descriptor prefetch) -- while the previous grid drains, instead of paying the

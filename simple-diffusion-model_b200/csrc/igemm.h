@@ -66,6 +66,18 @@ struct IgemmParams {
     // layer then runs the 128x256 MMA shape of the wide layers (measured 86-91 % tensor pipe) instead of 128x128 (40-48 %), and
     // the epilogue thread owns one channel: bias is a scalar, GroupNorm sums are in-thread over pixels.  n_tiles = ceil(Cout / 128).
     int swap_ab;
+    // b_mn (b2_conv2d_nhwc mode 5: data gradient of the 3x3 stride-1 conv): B is the FORWARD weight tensor [Cout_f][tap][Cin_f]
+    // (channels-last storage = the optimiser's bf16 copy) consumed MN-major: a K block is 64 rows (Cout_f) of the mirrored tap,
+    // the N tile BLOCK_N/64 slabs of 64 contiguous Cin_f -- one 4-D TMA box (ci | co | ci slab | tap).  No transposed weight copy
+    // exists and no per-step transpose kernel runs (104-164 launches of a train step before).
+    int b_mn;
+    // L2 prefetch of the weight matrix at kernel start (cp.async.bulk.prefetch.L2 over [pf_ptr, pf_ptr + pf_bytes), spread over the
+    // CTAs): the K loop touches the matrix in 128-byte pieces that are rows apart (a K block of every output channel), a DRAM-
+    // unfriendly pattern when the weights are cold -- and they always are: 1.2 GB of weights pass between two uses of a layer.
+    // MEASURED: the just-in-time transposed copies of the data-gradient weights acted as exactly such a prefetch (dropping them
+    // without one cost 3.5 ms per 128x128 batch-32 step although the kernels are equally fast in isolation).
+    const void* pf_ptr;
+    long long pf_bytes;
     int halo;                    // 0 off, 1 flattened, 2 row-aligned
     int halo_P;                  // flattened pitch W + 1 (halo 1)
     int halo_msub;               // 128-row sub-tiles per work item (2: both share every weights stage; BLOCK_N = 128 only)
@@ -99,6 +111,20 @@ struct GemmTnParams {
     // order and stores the tile.  ws == NULL -> fp32 vector atomics straight into the output (order-dependent rounding).
     float* ws;
     int* ws_counters;
+    // box5: the operand maps are 5-D slab maps (host_util.h: make_tmap_5d_slabs): ONE TMA instruction fetches all slabs of the
+    // A operand of a stage and one (or two, BLOCK_N = 256) all slabs of B, instead of one instruction per 128-byte-wide slab.
+    // Slabs are then box_rows * 128 bytes apart in shared memory (the descriptor's leading-byte offset follows).
+    int box5;
 };
+
+// Slab-map mode of the TN kernel: a B box carries as many slabs as the A box (16 KB) unless a CTA pair has to split the B tile.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int tn_spb_b(int b_slabs, int a_slabs, int cl) {
+    int s = b_slabs / cl;
+    if (s > a_slabs) s = a_slabs;
+    return s < 1 ? 1 : s;
+}
 
 }  // namespace b2

@@ -185,6 +185,15 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_holder;
     pdl_wait();                            // everything above overlapped the previous kernel's tail; global memory from here on
 
+    if (warp == 2 && p.pf_bytes > 0) {
+        // weights -> L2, 16 KB per instruction, consecutive chunks on different CTAs (igemm.h: pf_ptr); the epilogue warps idle now
+        const long long chunks = (p.pf_bytes + 16383) >> 14;
+        for (long long c = (long long)lane * gridDim.x + blockIdx.x; c < chunks; c += 32LL * gridDim.x) {
+            const long long off = c << 14;
+            const long long left = p.pf_bytes - off;
+            l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(p.pf_ptr) + off, static_cast<uint32_t>(left < 16384 ? left : 16384));
+        }
+    }
     const int splits = p.splits;
     const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
@@ -255,7 +264,16 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             uint8_t* b_dst = b_ring + s * S::B_BYTES;
                             if (elect_one()) {
                                 mbar_arrive_expect_tx(&full[s], S::B_BYTES);
-                                if constexpr (CL > 1) {
+                                if (p.b_mn) {             // forward-layout weights, MN-major (IgemmParams::b_mn): (ci | co | ci slab | tap)
+                                    if constexpr (CL > 1) {
+                                        constexpr int PIECE = BLOCK_N / CL;
+                                        if constexpr (PIECE >= 64)
+                                            tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], 0, cb * 64,
+                                                           tc.nt * (BLOCK_N / 64) + crank * (PIECE / 64), 8 - t, kMask);
+                                    } else {
+                                        tma_load_4d(b_dst, &tmB, &full[s], 0, cb * 64, tc.nt * (BLOCK_N / 64), 8 - t);
+                                    }
+                                } else if constexpr (CL > 1) {
                                     constexpr int PIECE = BLOCK_N / CL;
                                     tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], it * 64, tc.nt * BLOCK_N + crank * PIECE, 0, 0, kMask);
                                 } else {
@@ -295,6 +313,18 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         } else if (load_a) {
                             mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
                             tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
+                        } else if (p.b_mn) {
+                            // data gradient straight from the FORWARD weights [Cout][tap][Cin] (IgemmParams::b_mn): the K block is 64
+                            // output channels (rows) of the mirrored tap, the N tile BLOCK_N/64 slabs of 64 input channels
+                            const int wt = p.taps - 1 - t;
+                            if constexpr (CL > 1) {
+                                constexpr int PIECE = BLOCK_N / CL;
+                                if constexpr (PIECE >= 64)
+                                    tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], 0, kb * 64,
+                                                   tc.nt * (BLOCK_N / 64) + crank * (PIECE / 64), wt, kMask);
+                            } else {
+                                tma_load_4d(b_dst, &tmB, &full[s], 0, kb * 64, tc.nt * (BLOCK_N / 64), wt);
+                            }
                         } else if constexpr (CL > 1) {
                             constexpr int PIECE = BLOCK_N / CL;         // rows of the B tile this CTA fetches for the whole cluster
                             tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], it * BK_ELEMS, tc.nt * BLOCK_N + crank * PIECE,
@@ -312,10 +342,13 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ------------------------------------------------------------ MMA issuer (one thread)
         if constexpr (HALO) {
             {
-                constexpr uint32_t idesc = umma_idesc(1u, 128, BLOCK_N, 0, 0);
+                // b_mn: the weights stage is BLOCK_N/64 MN-major slabs of [64 k rows][128 B] (8 KB apart); a 16-row K step is 2 KB
+                const uint32_t idesc = umma_idesc(1u, 128, BLOCK_N, 0, p.b_mn ? 1u : 0u);
                 const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);          // descriptor without its address field
-                const uint32_t smem0 = smem_u32(smem);
-                const uint32_t ring0 = smem_u32(b_ring);
+                const uint64_t bdesc0 = p.b_mn ? umma_desc_sw128(0, 64 * 128, 1024) : desc0;
+                const uint32_t bk_step = p.b_mn ? 128u : 2u;
+                const uint32_t smem0 = smem_u32(smem) & 0x3FFFFu;      // CTA-local offset (see ptx.cuh: umma_desc_sw128)
+                const uint32_t ring0 = smem_u32(b_ring) & 0x3FFFFu;
                 int s = 0; uint32_t ph = 0;
                 int slot = 0; uint32_t aph = 0;
                 int acc = 0; uint32_t acc_ph = 0;
@@ -342,12 +375,12 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             mbar_wait(&full[s], ph);
                             tc_fence_after();
                             const uint64_t ad0 = desc0 + ((a_base + static_cast<uint32_t>(row0 + dh * p.halo_BW + dw) * 128u) >> 4);
-                            const uint64_t bd0 = desc0 + ((ring0 + s * S::B_BYTES) >> 4);
+                            const uint64_t bd0 = bdesc0 + ((ring0 + s * S::B_BYTES) >> 4);
                             if (elect_one()) {
                                 for (int sub = 0; sub < msub; ++sub) {            // the sub-tiles share this weights stage (interleaving their MMAs k-outer measured 12 % slower)
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        umma_ss<false>(d_tmem + sub * BLOCK_N, ad0 + sub * (sub_rows * 8u) + 2 * k, bd0 + 2 * k, idesc,
+                                        umma_ss<false>(d_tmem + sub * BLOCK_N, ad0 + sub * (sub_rows * 8u) + 2 * k, bd0 + bk_step * k, idesc,
                                                        (cb > 0 || t > 0 || k != 0) ? 1u : 0u);
                                 }
                                 if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
@@ -367,9 +400,11 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else
         {
             // warp-uniform issue loop (see elect_one): all lanes wait and compute, one elected lane issues
-            constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, 0);
+            const uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, p.b_mn ? 1u : 0u);
             const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);              // descriptor without its address field
-            const uint32_t smem0 = smem_u32(smem);
+            const uint64_t bdesc0 = p.b_mn ? umma_desc_sw128(0, 64 * 128, 1024) : desc0;     // b_mn: MN-major slabs (see the halo branch)
+            const uint32_t bk_step = p.b_mn ? 128u : 2u;
+            const uint32_t smem0 = smem_u32(smem) & 0x3FFFFu;      // CTA-local offset (see ptx.cuh: umma_desc_sw128)
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             for (int item = item0; item < total_tiles; item += item_step) {
@@ -382,11 +417,11 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint64_t ad0 = desc0 + ((smem0 + s * S::STAGE_BYTES) >> 4);
-                    const uint64_t bd0 = ad0 + (S::A_BYTES >> 4);
+                    const uint64_t bd0 = bdesc0 + ((smem0 + s * S::STAGE_BYTES + S::A_BYTES) >> 4);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_ss<kTF32>(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (it > it0 || k != 0) ? 1u : 0u);
+                            umma_ss<kTF32>(d_tmem, ad0 + 2 * k, bd0 + bk_step * k, idesc, (it > it0 || k != 0) ? 1u : 0u);
                         if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask); else umma_commit(&empty[s]);
                     }
                     __syncwarp();
@@ -891,6 +926,8 @@ int launch_igemm_nt(int dtype /*0 bf16, 1 fp32(tf32)*/, const CUtensorMap& a, co
     if (cl > 1 && (p.splits != 1 || p.b_mode || p.act == 4)) return set_error("igemm_nt: cluster multicast needs an unsplit, unbatched GEMM");
     if (p.swap_ab && (dtype != 0 || block_n != 256 || cl != 1 || p.splits != 1 || p.halo || p.out_fp32))
         return set_error("igemm_nt: swapped-operand mode needs the bf16 256-column kernel without cluster / split-K");
+    if (p.b_mn && (dtype != 0 || p.b_mode || p.swap_ab || block_n / 64 < cl || p.Cout % 64))
+        return set_error("igemm_nt: MN-major weights need the bf16 kernel, whole 64-channel slabs and cluster <= block_n / 64");
     if (p.halo) {
         if (dtype != 0 || p.splits != 1 || p.b_mode || p.taps != 9) return set_error("igemm_nt (halo): bf16 3x3 stride-1 convolutions only");
         if (cl == 1 && block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 1, true>(a, b, p, sms, st);

@@ -83,6 +83,29 @@ __device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap
           "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// Sequential prefetch of a global range into L2 (no shared-memory destination, no completion tracking); bytes % 16 == 0.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+
+// 5-D forms (gemm_tn.cu): the fifth coordinate walks 128-byte channel slabs, so ONE instruction fetches several MN-major slabs.
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                               int c0, int c1, int c2, int c3, int c4, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%4, %5, %6, %7, %8}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(cta_mask),
+          "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 // ---------------------------------------------------------------- thread-block clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -151,6 +174,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //  MN-major: 64-element (128 B) runs along MN, k rows 128 B apart, 8-k atoms SBO apart, next 64-wide MN slab LBO apart.
 //  layout: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row atoms; the only
 //  MN-major form accepted for 32-bit (tf32) operands -- TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+//  The address field holds the CTA-LOCAL offset (18 bits >> 4).  In a cluster launch a CTA's shared::cta window sits at a rank-
+//  dependent offset of the shared::cluster window, so smem_u32() of rank >= 1 has bits above 2^18 set: kernels that ADD an address
+//  to a prebuilt descriptor must mask it first (& 0x3FFFF), or the carry lands in the leading-byte-offset field -- harmless for
+//  K-major operands (LBO ignored under SWIZZLE_128B), garbage for MN-major ones (found with the MN-major weights of
+//  b2_conv2d_nhwc mode 5 under TMA multicast: rank 1 read every slab but the first from the wrong place).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);

@@ -385,3 +385,57 @@ def test_conv_epilogue_emits_the_consumers_adagn_backward_sums(shape):
         outs.append((dz.float(), ds, dgamma, dbeta, dbias))
     for a, b in zip(outs[0], outs[1]):
         assert rel_l2(a, b) < 1e-2
+
+
+# shapes: deep level with split-K (batch 2, 4x4), unsplit single-CTA tiles, cluster multicast (many tiles, 512 -> 256 channels),
+# halo mode (dz with 128 / 256 channels -> 128 input channels), unequal channel counts in both directions
+@pytest.mark.parametrize("cfg", [(2, 512, 512, 4, 4), (3, 128, 256, 8, 8), (40, 256, 512, 32, 32), (10, 128, 128, 64, 64),
+                                 (6, 128, 256, 48, 40), (2, 1024, 512, 8, 8), (1, 64, 192, 16, 16)])
+def test_dgrad_from_forward_weights_matches_transposed_copy(cfg):
+    """b2_conv2d_nhwc mode 5 (forward weights [Cout][9][Cin] consumed MN-major, mirrored taps) == mode 0 on the transposed /
+    flipped kind-1 copy, and both match autograd (data gradient of custom_layers.py:224)."""
+    from b200 import ops
+    code, dt, tol = DT["bf16"]
+    n, cin, cout, h, w = cfg
+    g = torch.Generator(device="cuda").manual_seed(7)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * (1.0 / (cout * 9) ** 0.5)
+    dy = torch.randn((n, cout, h, w), device="cuda", generator=g)
+    res = torch.randn((n, cin, h, w), device="cuda", generator=g)
+    dyq, resq = _nhwc(dy, dt), _nhwc(res, dt)
+    w_fwd = ops.pack_weight(0, wt, cout, cin, cin, code)                 # [Cout][9][Cin] = the channels-last bf16 copy
+    w_tr = ops.pack_weight(1, wt, cout, cin, cout, code)
+    for residual in (None, resq):
+        want = ops.conv2d(0, dyq, w_tr, None, cin, act=0, residual=residual)
+        got = ops.conv2d(5, dyq, w_fwd, None, cin, act=0, residual=residual)
+        assert torch.isfinite(got.float()).all()
+        assert rel_l2(got.float(), want.float()) < 1e-6, "same products in the same order: the two layouts must agree"
+    ref = F.conv_transpose2d(_nchw(dyq), wt.to(dt).float(), padding=1)       # dL/dx of conv2d(x, w, padding=1)
+    assert rel_l2(_nchw(ops.conv2d(5, dyq, w_fwd, None, cin, act=0)), ref) < tol
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("cfg", [(0, 2, 128, 128, 16, 16), (0, 8, 1024, 512, 2, 2), (1, 2, 128, 256, 16, 16), (2, 2, 256, 128, 8, 8),
+                                 (0, 3, 256, 192, 12, 20)])
+def test_wgrad_slab_maps_match_per_slab_loads(prec, cfg):
+    """The weight-gradient GEMM with 5-D slab maps (one TMA instruction per operand box) == the per-slab 4-D loads."""
+    import b200
+    from b200 import ops
+    code, dt, tol = DT[prec]
+    mode, n, cin, cout, h, w = cfg
+    g = torch.Generator(device="cuda").manual_seed(3)
+    oh, ow = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+    x = _nhwc(torch.randn((n, cin, h, w), device="cuda", generator=g), dt)
+    dz = _nhwc(torch.randn((n, cout, oh, ow), device="cuda", generator=g), dt)
+    xin = ops.space_to_depth2(x) if mode == 1 else x
+    numel = (16 if mode == 2 else 9) * cin * cout
+    outs = []
+    try:
+        for box5 in (0, 1):
+            b200.set_option("tn_box5", box5)
+            packed = torch.zeros(numel, device="cuda")
+            ops.conv2d_wgrad(mode, xin, dz, cout, packed)
+            outs.append(packed)
+    finally:
+        b200.set_option("tn_box5", 1)
+    assert torch.isfinite(outs[1]).all() and float(outs[1].abs().max()) > 0
+    assert rel_l2(outs[1], outs[0]) < 1e-5          # split-K sums are fp32 atomics: order-dependent rounding only

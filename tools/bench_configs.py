@@ -63,7 +63,12 @@ def train_case(name, net_kw, size, n, kind, precision, steps, cosine=False, sr=F
     from models.U_Net import U_Net
     torch.manual_seed(0)
     net = U_Net(**net_kw).to(DEV).train().set_precision(precision)
-    opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), capturable=True)
+    # same set-up as the trainer (b200/trainer.py): flat parameters + bucket-wise Adam on a second stream under the backward pass
+    from b200.parallel import DataParallel
+    dp = DataParallel(net, device=DEV)
+    opt = FusedAdam(net.parameters(), lr=2e-5, betas=(0.5, 0.999), grad_scale=dp.grad_scale, capturable=True)
+    if os.environ.get("SDM_B200_BENCH_ADAM_OVERLAP", "1") == "1":
+        dp.attach_optimizer(opt)
     deg = CosineNoiseDegradation(1000) if cosine else NoiseDegradation(5e-3, 9e-3, 1000, device=DEV)
     step = GraphedTrainStep(net, deg, opt, kind=kind)
     g = torch.Generator(device=DEV).manual_seed(1234)
@@ -135,6 +140,10 @@ def main():
     if "C1" in want:
         for prec in ("bf16", "tf32"):
             guarded(train_case, "C1 default 64x64 linear eps", {}, 64, 8, "eps", prec, args.steps)
+    if "C1bf16" in want:          # A/B runs: one precision / one batch size
+        guarded(train_case, "C1 default 64x64 linear eps", {}, 64, 8, "eps", "bf16", args.steps)
+    if "C3b32" in want:
+        guarded(train_case, "C3 default cond10 128x128", dict(cond_dim=10), 128, 32, "eps", "bf16", args.steps, labels_dim=10)
     if "C3" in want:
         for n in (8, 16, 32):
             guarded(train_case, "C3 default cond10 128x128", dict(cond_dim=10), 128, n, "eps", "bf16", args.steps, labels_dim=10)

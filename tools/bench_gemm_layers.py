@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--fwd-only", action="store_true")
     ap.add_argument("--wgrad-only", action="store_true")
     ap.add_argument("--scale", type=int, default=1, help="spatial scale (2 = 128x128 input)")
+    ap.add_argument("--dgrad-only", action="store_true")
+    ap.add_argument("--dgrad-mode", type=int, default=0, help="0: transposed weight copy (K-major B); 5: forward weights consumed MN-major")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
     n, dev = args.batch, "cuda"
@@ -61,18 +63,19 @@ def main():
 
         sets = [mk() for _ in range(reps)]
         res = {"C": c, "hw": hw, "count": count, "gflop": flops / 1e9}
-        if not args.wgrad_only:
+        if not args.wgrad_only and not args.dgrad_only:
             t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d(0, x, w, b, c, act=1, out=y, gn_stats=st, groups=32), sets)
             res["fwd_us"], res["fwd_tflops"] = t * 1e3, flops / t / 1e9
             tot["fwd"] += t * count
         if not args.fwd_only:
             if not args.wgrad_only:
-                t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d(0, dz, w, None, c, act=0, out=y), sets)
+                t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d(args.dgrad_mode, dz, w, None, c, act=0, out=y), sets)
                 res["dgrad_us"], res["dgrad_tflops"] = t * 1e3, flops / t / 1e9
                 tot["dgrad"] += t * count
-            t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d_wgrad(0, x, dz, c, gw), sets)
-            res["wgrad_us"], res["wgrad_tflops"] = t * 1e3, flops / t / 1e9
-            tot["wgrad"] += t * count
+            if not args.dgrad_only:
+                t = timeit(lambda x, dz, w, y, gw, b, st: ops.conv2d_wgrad(0, x, dz, c, gw), sets)
+                res["wgrad_us"], res["wgrad_tflops"] = t * 1e3, flops / t / 1e9
+                tot["wgrad"] += t * count
         flops_tot += flops * count
         rows.append(res)
         print("  ".join(f"{k}={v:.1f}" if isinstance(v, float) else f"{k}={v}" for k, v in res.items()), flush=True)
