@@ -107,6 +107,13 @@ int b2_rowdot(const void* a, long long lda, const void* b, long long ldb, long l
  * (mode 2: [N][2H][2W][Cout]); (H, W) as in b2_conv2d_nhwc. */
 int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* dz, int Cout,
                     long long lddz, float* grad_packed, int dtype, void* stream);
+/* n_jobs weight gradients in as few launches as possible: desc = n_jobs rows of 11 values {mode, x, N, H, W, Cin, ldx, dz, Cout,
+ * lddz, grad_packed} (pointers as integers; meaning as in b2_conv2d_wgrad; host memory, consumed before the call returns).  Weight
+ * gradients feed nothing but the optimiser (the reference's autograd computes them wherever it likes, train_diffusion.py:358), so
+ * the host may defer a module's worth and run them as ONE persistent kernel whose work items carry a job index -- at small
+ * batches a step is bound by the number of ~16 us dependent launches, not by their arithmetic.  Equals n_jobs calls of
+ * b2_conv2d_wgrad up to the order of fp32 atomic adds; layers the grouped kernel cannot take are launched one by one. */
+int b2_conv2d_wgrad_batch(int n_jobs, const long long* desc, int dtype, void* stream);
 /* C (+)= alpha * A^T . B with A [K][M], B [K][Ncols] (rows = contraction index), optionally batched.
  * out_mode 0: fp32 result added into a ZEROED C (Linear weight grads; atomics only under split-K);
  * out_mode 1: store in `dtype` (attention products). */
@@ -280,6 +287,13 @@ int b2_conv2d_nhwc_colsum(int mode, const void* x, int N, int H, int W, int Cin,
                           const float* bias, int Cout, void* y, long long ldy, int act, const void* residual, long long ldr,
                           float* gn_stats, int gn_groups, int out_mode, int dtype, void* stream, const void* cs_z,
                           long long cs_ldz, float* cs_s1, float* cs_s2);
+/* b2_conv2d_nhwc (modes 0..2, act 0, no statistics / residual) with a SECOND output y_act = Swish(y) (NHWC, per-pixel stride
+ * ldy_act, same dtype): the training forward of the un-normalised convs (custom_layers.py:224-245 with use_norm False, :174-201)
+ * keeps the pre-activation y for autograd and hands Swish(y) on -- no separate activation pass.  y_act equals b2_act(mode 0) of
+ * the stored y bit for bit. */
+int b2_conv2d_nhwc_dual(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* wpacked,
+                        const float* bias, int Cout, void* y, long long ldy, void* y_act, long long ldy_act, int dtype,
+                        void* stream);
 /* b2_adagn_bwd with sums_ready != 0: `work` = [2][N][C] already holds (sum_p dout, sum_p dout * swish(z)) from
  * b2_conv2d_nhwc_colsum; the reduce pass is skipped (one pass of 6 bytes per element instead of 10). */
 int b2_adagn_bwd_fused(const void* dout, long long ldd, const void* z, long long ldz, const float* stats, const float* gamma,

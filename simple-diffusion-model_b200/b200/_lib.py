@@ -23,6 +23,7 @@ SIGNATURES = {
     "b2_set_option": [_P, _I],
     "b2_conv2d_nhwc": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P],
     "b2_conv2d_nhwc_colsum": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _P, _P, _L, _P, _P],
+    "b2_conv2d_nhwc_dual": [_I, _P, _I, _I, _I, _I, _L, _P, _P, _I, _P, _L, _P, _L, _I, _P],
     "b2_adagn_bwd_fused": [_P, _L, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _P],
     "b2_conv3x3_first": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_conv3x3_last": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -31,6 +32,7 @@ SIGNATURES = {
     "b2_attn_scores_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _L, _I, _I, _I, _I, _F, _I, _P],
     "b2_rowdot": [_P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P],
     "b2_conv2d_wgrad": [_I, _P, _I, _I, _I, _I, _L, _P, _I, _L, _P, _I, _P],
+    "b2_conv2d_wgrad_batch": [_I, _P, _I, _P],
     "b2_gemm_tn": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "b2_nchw_to_nhwc_pad": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b2_nhwc_to_nchw": [_P, _L, _P, _I, _I, _I, _I, _I, _P],
@@ -108,7 +110,7 @@ def set_launch_hook(hook):
 
 _WORKSPACE = {}       # device index -> zeroed split-K workspace registered with the library (b2_set_workspace)
 WORKSPACE_BYTES = 128 << 20
-_WORKSPACE_USERS = ("b2_conv2d_nhwc", "b2_conv2d_nhwc_colsum", "b2_gemm_nt", "b2_conv2d_wgrad", "b2_gemm_tn")
+_WORKSPACE_USERS = ("b2_conv2d_nhwc", "b2_conv2d_nhwc_colsum", "b2_conv2d_nhwc_dual", "b2_gemm_nt", "b2_conv2d_wgrad", "b2_conv2d_wgrad_batch", "b2_gemm_tn")
 
 
 def _ensure_workspace():

@@ -91,6 +91,10 @@ class GraphedTrainStep:
             # small workloads are bound by the length of ~1.3 k short dependent kernels: weight gradients (off the critical path)
             # go to a second stream (measured at 64x64 batch 8 together with PDL: -5.6 %; neutral or worse at 128x128 batch 32)
             self.net.engine().overlap_wgrad = n * h * w <= PDL_MAX_PIXELS
+        # Deferring a module's weight gradients into ONE grouped launch (b2_conv2d_wgrad_batch, SDM_B200_GROUP_WGRAD=1) was measured
+        # at 64x64 batch 8 (profiles/r02z6_grouped_wgrad_ab.log): 17.97 ms grouped vs 18.76 ms per layer on one stream, but 18.26 ms
+        # vs 17.50 ms when the weight gradients run on the side stream -- fine-grained interleaving beats fewer launches -- so it
+        # stays opt-in.
         out_ch = self.net.out_layers[1].conv_layer[0].weight.shape[0]
         self.static["dpred"] = torch.empty((n, out_ch, h, w), dtype=torch.float32, device=dev)
         lay = self.net.engine().grad_layout(dev)

@@ -61,6 +61,22 @@ def conv2d(mode, x, wpacked, bias, cout, act=0, out=None, residual=None, gn_stat
     return y
 
 
+def conv2d_dual(mode, x, wpacked, bias, cout, out_act):
+    """Forward conv (modes 0..2) + bias that stores the pre-activation z AND Swish(z) (into `out_act`, which may be a channel slice
+    of a concat buffer) from one epilogue.  Returns z."""
+    code = code_of(x)
+    n, h, w, cin, ldx = _nhwc(x)
+    if mode == 1:
+        n //= 4
+    oh, ow = (2 * h, 2 * w) if mode == 2 else (h, w)
+    z = new_act(n, oh, ow, cout, code, x.device)
+    if tuple(out_act.shape) != (n, oh, ow, cout) or out_act.dtype != z.dtype:
+        raise B200Error(f"conv2d_dual: out_act {tuple(out_act.shape)} does not match the conv output {(n, oh, ow, cout)}")
+    call("b2_conv2d_nhwc_dual", mode, ptr(x), n, h, w, cin, ldx, ptr(wpacked), ptr(bias), cout, ptr(z), _nhwc(z)[4],
+         ptr(out_act), _nhwc(out_act)[4], code, stream())
+    return z
+
+
 def gemm_nt(a, b, m, ncols, k, lda, ldb, out, ldc, bias=None, alpha=1.0, act=0, residual=None, ldr=0, out_fp32=False,
             batch=(1, 1), a_strides=(0, 0), b_strides=(0, 0), c_strides=(0, 0), code=None):
     code = code_of(a) if code is None else code
@@ -125,6 +141,24 @@ def conv2d_wgrad(mode, x, dz, cout, grad_packed):
         n //= 4
     lddz = _nhwc(dz)[4]
     call("b2_conv2d_wgrad", mode, ptr(x), n, h, w, cin, ldx, ptr(dz), cout, lddz, ptr(grad_packed), code, stream())
+
+
+def conv2d_wgrad_batch(jobs):
+    """jobs: list of (mode, x, dz, cout, grad_packed) as for conv2d_wgrad; one grouped launch per N-tile width (b2_conv2d_wgrad_batch)."""
+    if not jobs:
+        return
+    import ctypes
+    code = code_of(jobs[0][1])
+    rows = []
+    for mode, x, dz, cout, grad in jobs:
+        if code_of(x) != code:
+            raise B200Error("conv2d_wgrad_batch: mixed activation dtypes")
+        n, h, w, cin, ldx = _nhwc(x)
+        if mode == 1:
+            n //= 4
+        rows += [mode, x.data_ptr(), n, h, w, cin, ldx, dz.data_ptr(), cout, _nhwc(dz)[4], grad.data_ptr()]
+    desc = (ctypes.c_longlong * len(rows))(*rows)
+    call("b2_conv2d_wgrad_batch", len(jobs), ctypes.cast(desc, ctypes.c_void_p), code, stream())
 
 
 def gemm_tn(a, b, m, ncols, k, lda, ldb, out, ldc, alpha=1.0, out_mode=0, batch=(1, 1), a_strides=(0, 0), b_strides=(0, 0),

@@ -208,6 +208,13 @@ class UNetTrainEngine(UNetEngine):
         self.fuse_adagn_min_c = int(os.environ.get("SDM_B200_FUSE_ADAGN_MIN_C", "0"))
         # data gradients of the 3x3 stride-1 convs read the forward weights MN-major (SDM_B200_DGRAD_FROM_FWD=0: transposed copies)
         self.dgrad_from_fwd = os.environ.get("SDM_B200_DGRAD_FROM_FWD", "1") == "1"
+        # SDM_B200_GROUP_WGRAD=1 (auto for small workloads under GraphedTrainStep): weight gradients of the channels-last stored convs
+        # are deferred and run as ONE grouped launch per module (b2_conv2d_wgrad_batch) -- they feed nothing but the optimiser,
+        # and at small batches the step is bound by the number of ~16 us dependent launches
+        self.group_wgrad = os.environ.get("SDM_B200_GROUP_WGRAD", "0") == "1"
+        self._wgrad_jobs = []
+        # un-normalised convs store z and Swish(z) from one epilogue (b2_conv2d_nhwc_dual); SDM_B200_FUSE_FWD_ACT=0: separate pass
+        self.fuse_fwd_act = os.environ.get("SDM_B200_FUSE_FWD_ACT", "1") == "1"
         self.post_backward = None          # optional callable(layout), runs when every gradient is complete
         self.on_grads_ready = None         # optional callable(layout, lo, hi): flat range [lo, hi) is final (DP buckets)
 
@@ -350,11 +357,14 @@ class UNetTrainEngine(UNetEngine):
         code = ops.code_of(x)
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
         w = self.cache.get(conv.weight, 0, code, cout, cin, x.shape[3])
-        z = ops.conv2d(0, x, w, conv.bias, cout, act=0)
-        n, hh, ww, _ = z.shape
+        n, hh, ww, _ = x.shape
         if out is None:
             out = ops.new_act(n, hh, ww, cout, code, x.device)
-        ops.act(0, None, z, out, None, n * hh * ww, cout, 0, z.stride(2), out.stride(2), code)
+        if self.fuse_fwd_act:
+            z = ops.conv2d_dual(0, x, w, conv.bias, cout, out)          # z and Swish(z) from one epilogue
+        else:
+            z = ops.conv2d(0, x, w, conv.bias, cout, act=0)
+            ops.act(0, None, z, out, None, n * hh * ww, cout, 0, z.stride(2), out.stride(2), code)
         ctx["tape"].append(("plain", blk, x, z, need_dx))
         return out
 
@@ -390,17 +400,23 @@ class UNetTrainEngine(UNetEngine):
         if isinstance(blk.out_layer, UpsampleBlock):
             cin, cout = conv.weight.shape[0], conv.weight.shape[1]
             w = self.cache.get(conv.weight, 2, code, cout, cin, cin)
-            z = ops.conv2d(2, x, w, conv.bias, cout, act=0)
             if out is None:
                 out = ops.new_act(n, 2 * hh, 2 * ww, cout, code, x.device)
-            ops.act(0, None, z, out, None, n * 4 * hh * ww, cout, 0, z.stride(2), out.stride(2), code)
+            if self.fuse_fwd_act:
+                z = ops.conv2d_dual(2, x, w, conv.bias, cout, out)
+            else:
+                z = ops.conv2d(2, x, w, conv.bias, cout, act=0)
+                ops.act(0, None, z, out, None, n * 4 * hh * ww, cout, 0, z.stride(2), out.stride(2), code)
             tape.append(("up", blk.out_layer, x, z))
             return out
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
         w = self.cache.get(conv.weight, 0, code, cout, cin, cin)
         planes = ops.space_to_depth2(x)
-        z = ops.conv2d(1, planes, w, conv.bias, cout, act=0)
-        ops.act(0, None, z, out, None, n * (hh // 2) * (ww // 2), cout, 0, z.stride(2), out.stride(2), code)
+        if self.fuse_fwd_act:
+            z = ops.conv2d_dual(1, planes, w, conv.bias, cout, out)
+        else:
+            z = ops.conv2d(1, planes, w, conv.bias, cout, act=0)
+            ops.act(0, None, z, out, None, n * (hh // 2) * (ww // 2), cout, 0, z.stride(2), out.stride(2), code)
         tape.append(("down", blk.out_layer, planes, z, (n, hh, ww, cin)))
         return out
 
@@ -436,22 +452,40 @@ class UNetTrainEngine(UNetEngine):
         if self.layout.is_cl(conv.weight) and cin_pad == cin:
             # channels-last stored weight: the flat gradient slice IS the kernel layout (zeroed at the start of backward)
             grad = self.layout.raw_grad(conv.weight)
-            if not self.overlap_wgrad:
-                ops.conv2d_wgrad(mode, x, dz, cout, grad)
+            if self.group_wgrad:
+                self._wgrad_jobs.append((mode, x, dz, cout, grad))       # launched by _flush_wgrad (keeps x and dz alive until then)
                 return
-            main = torch.cuda.current_stream(x.device)
-            if self._side_stream is None or self._side_stream.device != x.device:
-                self._side_stream = torch.cuda.Stream(device=x.device)
-            side = self._side_stream
-            side.wait_stream(main)                      # dz (and the zeroed gradient buffer) are ready
-            with torch.cuda.stream(side):
-                ops.conv2d_wgrad(mode, x, dz, cout, grad)
-            self._side_busy = True
-            self._side_keep.append((x, dz))
+            self._launch_wgrads([(mode, x, dz, cout, grad)])
             return
         packed = self._scratch(cout * 9 * cin_pad, x.device)
         ops.conv2d_wgrad(mode, x, dz, cout, packed)
         call("b2_unpack_weight_grad", 0, ptr(packed), ptr(self.layout.view(conv.weight)), cout, cin, cin_pad, 0, stream())
+
+    def _launch_wgrads(self, jobs):
+        """One weight gradient directly, several as a grouped launch; on the side stream when weight gradients overlap."""
+        def run():
+            if len(jobs) == 1:
+                ops.conv2d_wgrad(*jobs[0])
+            else:
+                ops.conv2d_wgrad_batch(jobs)
+        if not self.overlap_wgrad:
+            run()
+            return
+        dev = jobs[0][1].device
+        main = torch.cuda.current_stream(dev)
+        if self._side_stream is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        side = self._side_stream
+        side.wait_stream(main)                      # dz (and the zeroed gradient buffer) are ready
+        with torch.cuda.stream(side):
+            run()
+        self._side_busy = True
+        self._side_keep.append(jobs)
+
+    def _flush_wgrad(self):
+        if self._wgrad_jobs:
+            jobs, self._wgrad_jobs = self._wgrad_jobs, []
+            self._launch_wgrads(jobs)
 
     def _join_side(self):
         """Main stream waits for the weight-gradient stream (before gradients are consumed: all-reduce, optimiser)."""
@@ -612,11 +646,14 @@ class UNetTrainEngine(UNetEngine):
                 d = self._bwd_attention(blk, x_in, saved, d)
             elif kind == "emb":
                 self._bwd_embedding(entry[1], ctx)
-            elif kind == "mark" and self.on_grads_ready is not None:
-                lo, hi = lay.module_range(entry[1])
-                if hi > lo:
-                    self._join_side()
-                    self.on_grads_ready(lay, lo, hi)
+            elif kind == "mark":
+                self._flush_wgrad()              # the module's deferred weight gradients, one grouped launch
+                if self.on_grads_ready is not None:
+                    lo, hi = lay.module_range(entry[1])
+                    if hi > lo:
+                        self._join_side()
+                        self.on_grads_ready(lay, lo, hi)
+        self._flush_wgrad()
         self._join_side()
         for p in lay.params:
             v = lay.view(p)

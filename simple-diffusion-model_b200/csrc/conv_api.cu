@@ -130,7 +130,7 @@ struct ColSum { const void* z; long long ldz; float* s1; float* s2; };
 static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
                        const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
                        const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
-                       int dtype, void* stream, const ColSum* cs);
+                       int dtype, void* stream, const ColSum* cs, void* y2 = nullptr, long long ldy2 = 0);
 
 extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
                               const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
@@ -138,6 +138,16 @@ extern "C" int b2_conv2d_nhwc(int mode, const void* x, int N, int H, int W, int 
                               int dtype, void* stream) {
     return conv2d_impl(mode, x, N, H, W, Cin, ldx, wpacked, bias, Cout, y, ldy, act, residual, ldr, gn_stats, gn_groups, out_mode,
                        dtype, stream, nullptr);
+}
+
+// b2_conv2d_nhwc (act 0) with a second output y2 = Swish(y): training forward of the convs without normalisation.
+extern "C" int b2_conv2d_nhwc_dual(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
+                                   const void* wpacked, const float* bias, int Cout, void* y, long long ldy,
+                                   void* y_act, long long ldy_act, int dtype, void* stream) {
+    if (!y_act) return set_error("b2_conv2d_nhwc_dual: y_act is NULL");
+    if (mode < 0 || mode > 2) return set_error("b2_conv2d_nhwc_dual: forward modes 0..2 only");
+    return conv2d_impl(mode, x, N, H, W, Cin, ldx, wpacked, bias, Cout, y, ldy, 0, nullptr, 0, nullptr, 0, 0, dtype, stream, nullptr,
+                       y_act, ldy_act);
 }
 
 // b2_conv2d_nhwc (mode 0, bf16) whose epilogue ALSO accumulates, per (image, output channel), cs_s1 += sum_p y and
@@ -157,7 +167,7 @@ extern "C" int b2_conv2d_nhwc_colsum(int mode, const void* x, int N, int H, int 
 static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, long long ldx,
                        const void* wpacked, const float* bias, int Cout, void* y, long long ldy, int act,
                        const void* residual, long long ldr, float* gn_stats, int gn_groups, int out_mode,
-                       int dtype, void* stream, const ColSum* cs) {
+                       int dtype, void* stream, const ColSum* cs, void* y2, long long ldy2) {
     const int eb = dtype == 0 ? 2 : 4;
     const int bk = 128 / eb;
     if (Cin % bk != 0) return set_error("b2_conv2d_nhwc: Cin=%d must be a multiple of %d", Cin, bk);
@@ -262,6 +272,20 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
         (void)oeb;
         p.vec_ok = ok ? 1 : 0;
     }
+    if (y2) {                 // second output = Swish(y), NHWC with its own per-pixel stride (igemm.h: out2)
+        if (out_mode != 0 || act != 0 || gn_stats || residual) return set_error("b2_conv2d_nhwc_dual: plain conv + bias only (act 0, no statistics / residual)");
+        const int ov = dtype == 1 ? 4 : 8;
+        const bool parity = (p.groups == 4);        // modes 2 / 3: output at 2H x 2W, group = output parity
+        p.out2 = y2;
+        if (parity) {
+            p.o2N = (long long)4 * H * W * ldy2; p.o2H = (long long)2 * (2 * W) * ldy2; p.o2W = 2 * ldy2;
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) p.goff2[a * 2 + b] = ((long long)a * (2 * W) + b) * ldy2;
+        } else {
+            p.o2N = (long long)H * W * ldy2; p.o2H = (long long)W * ldy2; p.o2W = ldy2;
+        }
+        bool ok2 = (ldy2 % ov == 0) && ((uintptr_t)y2 % 16 == 0);
+        p.vec2_ok = ok2 ? 1 : 0;
+    }
     if (cs) {
         p.cs_z = cs->z; p.cs_s1 = cs->s1; p.cs_s2 = cs->s2;
         p.cs_zN = (long long)H * W * cs->ldz; p.cs_zH = (long long)W * cs->ldz; p.cs_zW = cs->ldz;
@@ -357,9 +381,9 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
         uint32_t box[4] = {(uint32_t)bk, (uint32_t)(swapped ? 128 : bn / p.cluster), 1, 1};      // cluster mode: each CTA fetches 1/CL of the B tile
         if (make_tmap_4d(&tb, wpacked, eb, dims, str, box)) return 1;
     }
-    {   // weights of >= 1 MiB are prefetched into L2 by the kernel itself (igemm.h: pf_ptr); "l2_prefetch" 0 disables it
+    {   // weights of >= 1 MiB are prefetched into L2 by the kernel itself (igemm.h: pf_ptr); measured neutral on B200 (profiles/r02z4_step_ab_alignment.log), so opt-in: "l2_prefetch" 1 / SDM_B200_L2_PREFETCH=1
         const long long wbytes = (b_mn ? 9LL * Cin * Cout : (long long)p.taps * Cin * Cout * p.groups) * eb;
-        if (option("l2_prefetch", 1) && wbytes >= (1 << 20) && ((uintptr_t)wpacked % 16) == 0) { p.pf_ptr = wpacked; p.pf_bytes = wbytes & ~15LL; }
+        if (option("l2_prefetch", 0) && wbytes >= (1 << 20) && ((uintptr_t)wpacked % 16) == 0) { p.pf_ptr = wpacked; p.pf_bytes = wbytes & ~15LL; }
     }
     if (launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;
     if (separate_stats) return launch_gn_stats(y, ldy, gn_stats, N, H * W, Cout, gn_groups, act == 3 ? 1 : 0, dtype, (cudaStream_t)stream, det);
@@ -576,12 +600,9 @@ static void tn_pick_splits(GemmTnParams* p, int batches, int bn) {
     }
 }
 
-// Weight gradient of the three convolution flavours, accumulated (fp32 atomics) into a zero-initialised buffer in
-// KERNEL layout: mode 0/1 -> [Cout][9][Cin], mode 2 -> [4 parities][Cout][4][Cin]  (b2_unpack_weight_grad maps
-// it back to the parameter's layout).  x: the forward input (mode 1: its parity planes), dz: gradient w.r.t. the
-// conv's pre-activation output.  (H, W): forward A-operand extents, as in b2_conv2d_nhwc.
-extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* dz,
-                               int Cout, long long lddz, float* grad_packed, int dtype, void* stream) {
+// Plans group g (mode 2: output parity, else 0) of a weight gradient: shapes, tiling, split-K and both operand maps.
+static int wgrad_setup(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* dz, int Cout, long long lddz,
+                       float* grad_packed, int dtype, int g, GemmTnParams* out, CUtensorMap* ta, CUtensorMap* tb, int* bn_out) {
     const int eb = dtype == 0 ? 2 : 4;
     const int kmult = dtype == 0 ? 16 : 8;
     if (mode < 0 || mode > 2) return set_error("b2_conv2d_wgrad: bad mode %d", mode);
@@ -600,7 +621,6 @@ extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int
     p.tap_stride = Cin;
     const int slab = 128 / eb;
     int b_images = N;
-    const int n_groups = mode == 2 ? 4 : 1;
     if (mode == 0 || mode == 1) {
         p.taps = 9; p.ldc = 9LL * Cin;
         for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
@@ -627,37 +647,105 @@ extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int
     p.box5 = (option("tn_box5", 1) && Cin % slab == 0 && Cout % slab == 0) ? 1 : 0;
     const int a_slabs = 128 / slab, b_slabs = bn / slab;
     const uint32_t spb_b = (uint32_t)tn_spb_b(b_slabs, a_slabs, p.cluster);
-    CUtensorMap ta, tb;
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)b_images};
         uint64_t str[3] = {(uint64_t)ldx * eb, (uint64_t)W * ldx * eb, (uint64_t)H * W * ldx * eb};
         uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
-        if (p.box5 ? make_tmap_5d_slabs(&tb, x, eb, dims, str, box, spb_b, dtype == 1)
-                   : make_tmap_4d(&tb, x, eb, dims, str, box, dtype == 1)) return 1;
+        if (p.box5 ? make_tmap_5d_slabs(tb, x, eb, dims, str, box, spb_b, dtype == 1)
+                   : make_tmap_4d(tb, x, eb, dims, str, box, dtype == 1)) return 1;
     }
-    for (int g = 0; g < n_groups; ++g) {
+    {
         const char* dz_base = (const char*)dz;
         uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         uint64_t str[3] = {(uint64_t)lddz * eb, (uint64_t)W * lddz * eb, (uint64_t)H * W * lddz * eb};
-        GemmTnParams pg = p;
-        pg.out = grad_packed;
+        p.out = grad_packed;
         if (mode == 2) {       // dz is [N][2H][2W][Cout]; parity (a, b) is the strided view dz[:, a::2, b::2, :]
             const int a = g >> 1, b = g & 1;
             dz_base += ((long long)a * (2 * W) + b) * lddz * eb;
             str[0] = (uint64_t)2 * lddz * eb; str[1] = (uint64_t)2 * (2 * W) * lddz * eb; str[2] = (uint64_t)4 * H * W * lddz * eb;
             for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
                 const int t = i * 2 + j;
-                pg.tap_dh[t] = (i == 0) ? 0 : (a == 0 ? -1 : 1);
-                pg.tap_dw[t] = (j == 0) ? 0 : (b == 0 ? -1 : 1);
-                pg.tap_dn[t] = 0;
+                p.tap_dh[t] = (i == 0) ? 0 : (a == 0 ? -1 : 1);
+                p.tap_dw[t] = (j == 0) ? 0 : (b == 0 ? -1 : 1);
+                p.tap_dn[t] = 0;
             }
-            pg.out = grad_packed + (long long)g * Cout * 4 * Cin;
+            p.out = grad_packed + (long long)g * Cout * 4 * Cin;
         }
         uint32_t box[4] = {(uint32_t)slab, (uint32_t)p.wb, (uint32_t)p.hb, (uint32_t)p.nb};
-        if (p.box5 ? make_tmap_5d_slabs(&ta, dz_base, eb, dims, str, box, (uint32_t)a_slabs, dtype == 1)
-                   : make_tmap_4d(&ta, dz_base, eb, dims, str, box, dtype == 1)) return 1;
-        if (launch_gemm_tn(dtype, ta, tb, pg, bn, (cudaStream_t)stream)) return 1;
+        if (p.box5 ? make_tmap_5d_slabs(ta, dz_base, eb, dims, str, box, (uint32_t)a_slabs, dtype == 1)
+                   : make_tmap_4d(ta, dz_base, eb, dims, str, box, dtype == 1)) return 1;
     }
+    *out = p;
+    *bn_out = bn;
+    return 0;
+}
+
+// Weight gradient of the three convolution flavours, accumulated (fp32 atomics) into a zero-initialised buffer in
+// KERNEL layout: mode 0/1 -> [Cout][9][Cin], mode 2 -> [4 parities][Cout][4][Cin]  (b2_unpack_weight_grad maps
+// it back to the parameter's layout).  x: the forward input (mode 1: its parity planes), dz: gradient w.r.t. the
+// conv's pre-activation output.  (H, W): forward A-operand extents, as in b2_conv2d_nhwc.
+extern "C" int b2_conv2d_wgrad(int mode, const void* x, int N, int H, int W, int Cin, long long ldx, const void* dz,
+                               int Cout, long long lddz, float* grad_packed, int dtype, void* stream) {
+    const int n_groups = mode == 2 ? 4 : 1;
+    for (int g = 0; g < n_groups; ++g) {
+        GemmTnParams p;
+        CUtensorMap ta, tb;
+        int bn;
+        if (wgrad_setup(mode, x, N, H, W, Cin, ldx, dz, Cout, lddz, grad_packed, dtype, g, &p, &ta, &tb, &bn)) return 1;
+        if (launch_gemm_tn(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;
+    }
+    return 0;
+}
+
+// Several weight gradients in as few launches as possible (igemm.h: TnJobTable).  desc: n_jobs rows of 11 values
+// {mode, x, N, H, W, Cin, ldx, dz, Cout, lddz, grad_packed} (pointers as integers), same meaning as b2_conv2d_wgrad.  Layers the
+// grouped kernel cannot take (transposed conv, TF32, channel counts that are not whole 64-channel slabs, ordered split-K, CTA
+// pairs) are launched one by one.  The result equals n_jobs calls of b2_conv2d_wgrad (up to the order of fp32 atomic adds).
+namespace b2 { int launch_gemm_tn_grouped(const TnJobTable& tab, int block_n, cudaStream_t st); }
+extern "C" int b2_conv2d_wgrad_batch(int n_jobs, const long long* desc, int dtype, void* stream) {
+    if (n_jobs < 0 || (n_jobs > 0 && !desc)) return set_error("b2_conv2d_wgrad_batch: bad job list");
+    static thread_local TnJobTable tabs[3];          // one table per N-tile width (256 / 128 / 64), filled and flushed in turn
+    const int widths[3] = {256, 128, 64};
+    for (int t = 0; t < 3; ++t) { tabs[t].n_jobs = 0; tabs[t].total_items = 0; }
+    auto flush = [&](int t) -> int {
+        if (tabs[t].n_jobs == 0) return 0;
+        const int rc = launch_gemm_tn_grouped(tabs[t], widths[t], (cudaStream_t)stream);
+        tabs[t].n_jobs = 0; tabs[t].total_items = 0;
+        return rc;
+    };
+    for (int i = 0; i < n_jobs; ++i) {
+        const long long* d = desc + 11LL * i;
+        const int mode = (int)d[0], N = (int)d[2], H = (int)d[3], W = (int)d[4], Cin = (int)d[5], Cout = (int)d[8];
+        const void* x = reinterpret_cast<const void*>(d[1]);
+        const void* dz = reinterpret_cast<const void*>(d[7]);
+        float* grad = reinterpret_cast<float*>(d[10]);
+        const long long ldx = d[6], lddz = d[9];
+        const int n_groups = mode == 2 ? 4 : 1;
+        for (int g = 0; g < n_groups; ++g) {
+            GemmTnParams p;
+            CUtensorMap ta, tb;
+            int bn;
+            if (wgrad_setup(mode, x, N, H, W, Cin, ldx, dz, Cout, lddz, grad, dtype, g, &p, &ta, &tb, &bn)) return 1;
+            const bool groupable = dtype == 0 && mode != 2 && p.box5 && p.cluster == 1 && p.ws == nullptr && p.taps <= 9 &&
+                                   Cin % 64 == 0 && ((uintptr_t)p.out % 16) == 0;
+            if (!groupable) {
+                if (launch_gemm_tn(dtype, ta, tb, p, bn, (cudaStream_t)stream)) return 1;
+                continue;
+            }
+            const int t = bn == 256 ? 0 : (bn == 128 ? 1 : 2);
+            if (tabs[t].n_jobs == kTnMaxJobs && flush(t)) return 1;
+            TnJob& J = tabs[t].jobs[tabs[t].n_jobs++];
+            J.tmA = ta; J.tmB = tb;
+            J.out = reinterpret_cast<float*>(p.out); J.ldc = p.ldc; J.tap_stride = p.tap_stride;
+            J.wb = p.wb; J.hb = p.hb; J.nb = p.nb; J.kt_w = p.kt_w; J.kt_h = p.kt_h; J.kt_n = p.kt_n;
+            J.m_tiles = p.m_tiles; J.n_tiles = p.n_tiles; J.taps = p.taps; J.splits = p.splits; J.M = p.M; J.Ncols = p.Ncols;
+            J.alpha = p.alpha;
+            for (int k = 0; k < 9; ++k) { J.tap_dw[k] = p.tap_dw[k]; J.tap_dh[k] = p.tap_dh[k]; J.tap_dn[k] = p.tap_dn[k]; }
+            J.item_begin = tabs[t].total_items;
+            tabs[t].total_items += p.splits * p.m_tiles * p.n_tiles * p.taps;
+        }
+    }
+    for (int t = 0; t < 3; ++t) if (flush(t)) return 1;
     return 0;
 }
 

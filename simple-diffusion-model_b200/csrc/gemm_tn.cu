@@ -379,6 +379,231 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ grouped weight gradients
+// Same pipeline as gemm_tn_kernel (bf16, no cluster, atomic split-K, slab maps), but a work item carries a JOB index: the
+// operand maps and shapes of up to kTnMaxJobs layers live in the kernel's parameter space (igemm.h: TnJobTable).  CTA i takes
+// items i, i + grid, ...; the three roles walk the same item sequence and look the job up with a running index.
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kTnThreads, 1)
+gemm_tn_grouped_kernel(const __grid_constant__ TnJobTable tab) {
+    constexpr int SLAB = 64, A_SLABS = 2, B_SLABS = BLOCK_N / SLAB;
+    constexpr int SLAB_BYTES = kTnBK * 128;
+    constexpr int A_BYTES = A_SLABS * SLAB_BYTES, B_BYTES = B_SLABS * SLAB_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int UMMA_K = 16;
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+    constexpr int SPB_B = tn_spb_b(B_SLABS, A_SLABS, 1);
+    constexpr int NB_B = B_SLABS / SPB_B;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kTnEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();
+
+    const int total_items = tab.total_items;
+    const int n_jobs = tab.n_jobs;
+    struct Work { int mt, nt, tap, kb0, kb1; };
+    auto advance = [&](int item, int& j) { while (j + 1 < n_jobs && item >= tab.jobs[j + 1].item_begin) ++j; };
+    auto decode = [&](const TnJob& J, int item) -> Work {
+        Work w;
+        int local = item - J.item_begin;
+        const int split = local % J.splits;  local /= J.splits;
+        w.mt = local % J.m_tiles;            local /= J.m_tiles;
+        w.nt = local % J.n_tiles;            local /= J.n_tiles;
+        w.tap = local;
+        const int k_boxes = J.kt_w * J.kt_h * J.kt_n;
+        w.kb0 = (int)(((long long)k_boxes * split) / J.splits);
+        w.kb1 = (int)(((long long)k_boxes * (split + 1)) / J.splits);
+        return w;
+    };
+
+    if (warp == 0 || warp >= 2 + kTnEpiWarps) {
+        constexpr int n_prod = kTnMaxProducers;
+        const int prod = warp == 0 ? 0 : warp - (2 + kTnEpiWarps) + 1;
+        if (prod < n_prod) {
+            int s = 0; uint32_t ph = 0;
+            int j = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                advance(item, j);
+                const TnJob& J = tab.jobs[j];
+                const Work wk = decode(J, item);
+                const uint32_t box_rows = static_cast<uint32_t>(J.wb * J.hb * J.nb);
+                const uint32_t slab_stride = box_rows * 128u;
+                const int dw = J.tap_dw[wk.tap], dh = J.tap_dh[wk.tap], dn = J.tap_dn[wk.tap];
+                for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+                    int r = kb;
+                    const int w0 = (r % J.kt_w) * J.wb;  r /= J.kt_w;
+                    const int h0 = (r % J.kt_h) * J.hb;  r /= J.kt_h;
+                    const int n0 = r * J.nb;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + A_BYTES;
+                    if (elect_one()) {
+                        if (prod == 0) {
+                            mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
+                            tma_load_5d(a_dst, &J.tmA, &full[s], 0, w0, h0, n0, wk.mt * A_SLABS);
+                        }
+#pragma unroll
+                        for (int b = 0; b < NB_B; ++b) {
+                            if (((1 + b) % n_prod) != prod) continue;
+                            tma_load_5d(b_dst + b * SPB_B * slab_stride, &J.tmB, &full[s], 0, w0 + dw, h0 + dh, n0 + dn,
+                                        wk.nt * B_SLABS + b * SPB_B);
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc(1u, 128, BLOCK_N, 1, 1);
+        const uint32_t smem0 = smem_u32(smem) & 0x3FFFFu;
+        constexpr uint32_t K_STEP = (UMMA_K * 128) >> 4;
+        int s = 0; uint32_t ph = 0;
+        int acc = 0; uint32_t acc_ph = 0;
+        int j = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            advance(item, j);
+            const TnJob& J = tab.jobs[j];
+            const Work wk = decode(J, item);
+            const uint32_t box_rows = static_cast<uint32_t>(J.wb * J.hb * J.nb);
+            const int k_steps = (int)(box_rows + UMMA_K - 1) / UMMA_K;
+            const uint64_t desc0 = umma_desc_sw128(0, box_rows * 128u, 1024, 2);
+            mbar_wait(&tempty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t ad0 = desc0 + ((smem0 + s * STAGE_BYTES) >> 4);
+                const uint64_t bd0 = ad0 + (A_BYTES >> 4);
+                if (elect_one()) {
+                    constexpr int MAX_K = kTnBK / UMMA_K;
+#pragma unroll
+                    for (int k = 0; k < MAX_K; ++k)
+                        if (k < k_steps) umma_ss<false>(d_tmem, ad0 + k * K_STEP, bd0 + k * K_STEP, idesc, (kb > wk.kb0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            if (elect_one()) umma_commit(&tfull[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int acc = 0; uint32_t acc_ph = 0;
+        int j = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            advance(item, j);
+            const TnJob& J = tab.jobs[j];
+            const Work wk = decode(J, item);
+            const int m = wk.mt * 128 + q * 32 + lane;
+            const bool valid = m < J.M;
+            const long long off = (long long)m * J.ldc + (long long)wk.tap * J.tap_stride;
+            const float alpha = J.alpha;
+            const bool atomic = J.splits > 1;
+            mbar_wait(&tfull[acc], acc_ph);
+            tc_fence_after();
+            if (wk.kb1 > wk.kb0) {
+#pragma unroll 1
+                for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
+                    const int col0 = wk.nt * BLOCK_N + ch * 32;
+                    if (col0 >= J.Ncols) break;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + ch * 32, r);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+                    float* o = J.out + off + col0;              // Ncols is a multiple of 64 and every slice 16-byte aligned (host check)
+                    if (!atomic) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            reinterpret_cast<float4*>(o)[i] =
+                                make_float4(__uint_as_float(r[4 * i]) * alpha, __uint_as_float(r[4 * i + 1]) * alpha,
+                                            __uint_as_float(r[4 * i + 2]) * alpha, __uint_as_float(r[4 * i + 3]) * alpha);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            atomicAdd(reinterpret_cast<float4*>(o) + i,
+                                      make_float4(__uint_as_float(r[4 * i]) * alpha, __uint_as_float(r[4 * i + 1]) * alpha,
+                                                  __uint_as_float(r[4 * i + 2]) * alpha, __uint_as_float(r[4 * i + 3]) * alpha));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_tn_grouped_cfg(const TnJobTable& tab, int num_sms, cudaStream_t st) {
+    constexpr int stage_bytes = (2 + BLOCK_N / 64) * kTnBK * 128;
+    constexpr int total = STAGES * stage_bytes + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static_assert(total <= 227 * 1024, "shared memory budget");
+    auto kern = gemm_tn_grouped_kernel<BLOCK_N, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+        if (e != cudaSuccess) return set_error("gemm_tn (grouped): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kTnThreads);
+    cfg.dynamicSmemBytes = total;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    int na = 0;
+    if (pdl_enabled()) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    cfg.gridDim = dim3(tab.total_items < num_sms ? tab.total_items : num_sms);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tab);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return set_error("gemm_tn (grouped) launch: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int launch_gemm_tn_grouped(const TnJobTable& tab, int block_n, cudaStream_t st) {
+    const int sms = device_sm_count();
+    if (tab.n_jobs < 1 || tab.n_jobs > kTnMaxJobs || tab.total_items < 1) return set_error("gemm_tn (grouped): empty or oversized job table");
+    if (block_n == 256) return launch_tn_grouped_cfg<256, 4>(tab, sms, st);
+    if (block_n == 128) return launch_tn_grouped_cfg<128, 6>(tab, sms, st);
+    if (block_n == 64)  return launch_tn_grouped_cfg<64, 8>(tab, sms, st);
+    return set_error("gemm_tn (grouped): unsupported block_n %d", block_n);
+}
+
 template <typename T, int BLOCK_N, int STAGES, int CL, bool ORDERED = false>
 static int launch_tn_cfg(const CUtensorMap& a, const CUtensorMap& b, const GemmTnParams& p, int num_sms, cudaStream_t st) {
     constexpr int SLAB = 128 / sizeof(T);

@@ -1,6 +1,7 @@
 // Parameter blocks shared by the tcgen05 implicit-GEMM kernels and their host launchers.
 #pragma once
 #include <stdint.h>
+#include <cuda.h>
 
 namespace b2 {
 
@@ -78,6 +79,13 @@ struct IgemmParams {
     // without one cost 3.5 ms per 128x128 batch-32 step although the kernels are equally fast in isolation).
     const void* pf_ptr;
     long long pf_bytes;
+    // Second output (b2_conv2d_nhwc_dual, act 0): out2 = Swish(value stored to out), same dtype, its own per-pixel stride / group
+    // offsets.  Training forward of the un-normalised convs keeps the pre-activation z for backward AND feeds Swish(z) on; the
+    // separate Swish pass (read z, write a: 4 bytes per element and one launch per conv) disappears.
+    void* out2;
+    long long o2N, o2H, o2W;
+    long long goff2[kMaxGroups];
+    int vec2_ok;
     int halo;                    // 0 off, 1 flattened, 2 row-aligned
     int halo_P;                  // flattened pitch W + 1 (halo 1)
     int halo_msub;               // 128-row sub-tiles per work item (2: both share every weights stage; BLOCK_N = 128 only)
@@ -116,6 +124,30 @@ struct GemmTnParams {
     // Slabs are then box_rows * 128 bytes apart in shared memory (the descriptor's leading-byte offset follows).
     int box5;
 };
+
+// ---- grouped weight gradients (gemm_tn.cu: gemm_tn_grouped_kernel) ------------------------------------------------------------
+// At small per-GPU batches the deep U-Net levels turn every weight gradient into a ~16 us launch whose K loop is 3 us: the step is
+// bound by the NUMBER of dependent launches.  Weight gradients feed nothing but the optimiser, so the host may defer them and hand
+// a whole module's worth to ONE persistent launch: a work item is (job, tile, split), the job table (operand maps + shapes) rides
+// in the kernel's parameter space (CUDA 12.1+: up to 32 KB), so nothing has to be uploaded and a captured graph carries it.
+constexpr int kTnMaxJobs = 48;
+struct alignas(64) TnJob {
+    CUtensorMap tmA, tmB;        // 5-D slab maps of dz (A) and x (B)
+    float* out;                  // flat gradient slice of the layer, kernel layout [Cout][taps][Cin]
+    long long ldc, tap_stride;
+    int wb, hb, nb;              // K box (pixels)
+    int kt_w, kt_h, kt_n;        // K boxes per dim
+    int m_tiles, n_tiles, taps, splits;
+    int M, Ncols;
+    int item_begin;              // first work item of this job within the launch
+    float alpha;
+    int tap_dw[9], tap_dh[9], tap_dn[9];
+};
+struct TnJobTable {
+    TnJob jobs[kTnMaxJobs];
+    int n_jobs, total_items;
+};
+static_assert(sizeof(TnJobTable) <= 32000, "the job table must fit the kernel parameter space (32 764 bytes)");
 
 // Slab-map mode of the TN kernel: a B box carries as many slabs as the A box (16 KB) unless a CTA pair has to split the B tile.
 #ifdef __CUDACC__

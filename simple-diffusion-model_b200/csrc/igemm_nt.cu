@@ -135,8 +135,16 @@ __device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
 // through row-shifted descriptors; B (weights) streams through a ring of p.b_stages stages, one stage per (channel block, tap).
 constexpr int kMaxASlots = 4;
 
+// B2_NT_MAXREG: cap the registers per thread (all 11 warps get the epilogue warps' allocation: 168 x 352 = 59 136 of the SM's 65 536
+// registers, so no other kernel's CTA -- the bucket-wise Adam on its own stream, a side-stream weight gradient's helper kernels --
+// can become resident next to a GEMM CTA).
+#ifdef B2_NT_MAXREG
+#define B2_NT_BOUNDS __maxnreg__(B2_NT_MAXREG)
+#else
+#define B2_NT_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <typename T, int BLOCK_N, int STAGES, int CL, bool HALO = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void B2_NT_BOUNDS
 igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ IgemmParams p) {
     using S = IgemmSmem<BLOCK_N, STAGES>;
@@ -802,6 +810,43 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         } else {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) if (i < ncols) o[i * p.oC] = __float2bfloat16(v[i]);
+                        }
+                    }
+                }
+                if (p.out2 && valid) {
+                    // second output: Swish of the value just stored (rounded to the storage type first, so that the result equals
+                    // the separate Swish pass over the stored pre-activation bit for bit)
+                    const long long o2_off = n * p.o2N + h * p.o2H + w * p.o2W + p.goff2[tc.g] + col0;
+                    const bool vec2 = p.vec2_ok && ncols == 32;
+                    if (f32out) {
+                        float* o2 = reinterpret_cast<float*>(p.out2) + o2_off;
+                        float a[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { const float sw = swish_t<!kTF32>(v[i]); a[i] = (kTF32 && !p.out_fp32) ? round_tf32(sw) : sw; }
+                        if (vec2) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(o2)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o2[i] = a[i];
+                        }
+                    } else {
+                        __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + o2_off;
+                        float a[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) a[i] = swish_t<true>(__bfloat162float(__float2bfloat16(v[i])));
+                        if (vec2) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 x;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(a[8 * i + 2 * j], a[8 * i + 2 * j + 1]);
+                                reinterpret_cast<uint4*>(o2)[i] = x;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (i < ncols) o2[i] = __float2bfloat16(a[i]);
                         }
                     }
                 }

@@ -439,3 +439,58 @@ def test_wgrad_slab_maps_match_per_slab_loads(prec, cfg):
         b200.set_option("tn_box5", 1)
     assert torch.isfinite(outs[1]).all() and float(outs[1].abs().max()) > 0
     assert rel_l2(outs[1], outs[0]) < 1e-5          # split-K sums are fp32 atomics: order-dependent rounding only
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("cfg", [(0, 2, 128, 128, 16, 16), (0, 3, 64, 256, 4, 4), (1, 2, 128, 256, 16, 16), (2, 2, 256, 128, 8, 8),
+                                 (0, 9, 128, 192, 10, 6)])
+def test_dual_output_conv_equals_conv_plus_swish_pass(prec, cfg):
+    """b2_conv2d_nhwc_dual: the pre-activation z AND Swish(z) from one epilogue == b2_conv2d_nhwc followed by b2_act(mode 0), bit for
+    bit, also when Swish(z) lands in a channel slice of a wider (concat) buffer."""
+    from b200 import ops
+    code, dt, tol = DT[prec]
+    mode, n, cin, cout, h, w = cfg
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = _nhwc(torch.randn((n, cin, h, w), device="cuda", generator=g), dt)
+    wshape = (cin, cout, 4, 4) if mode == 2 else (cout, cin, 3, 3)
+    wt = torch.randn(wshape, device="cuda", generator=g) * (1.0 / (cin * 9) ** 0.5)
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    wp = ops.pack_weight(2 if mode == 2 else 0, wt, cout, cin, cin, code)
+    xin = ops.space_to_depth2(x) if mode == 1 else x
+    z_ref = ops.conv2d(mode, xin, wp, bias, cout, act=0)
+    nn_, oh, ow, _ = z_ref.shape
+    a_ref = torch.empty_like(z_ref)
+    ops.act(0, None, z_ref, a_ref, None, nn_ * oh * ow, cout, 0, z_ref.stride(2), a_ref.stride(2), code)
+    wide = torch.zeros((nn_, oh, ow, 2 * cout), dtype=dt, device="cuda")
+    z = ops.conv2d_dual(mode, xin, wp, bias, cout, wide[..., cout:])
+    assert torch.equal(z, z_ref)
+    assert torch.equal(wide[..., cout:], a_ref)
+    assert float(wide[..., :cout].abs().max()) == 0.0          # the other half of the concat buffer is untouched
+
+
+def test_grouped_weight_gradients_match_individual_launches():
+    """b2_conv2d_wgrad_batch (one persistent kernel per N-tile width, job table in the kernel parameters) == one b2_conv2d_wgrad per
+    layer, for a mix of shapes: deep levels with split-K, 32-row K boxes, stride-2 parity planes, a partial M tile (Cout = 192), three
+    N-tile widths, a transposed conv and a narrow layer that fall back to single launches, and more jobs than one table holds."""
+    from b200 import ops
+    dt = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapes = [(0, 8, 512, 512, 4, 4), (0, 8, 1024, 1024, 2, 2), (0, 4, 256, 128, 16, 16), (1, 4, 128, 256, 16, 16), (0, 2, 64, 192, 8, 8),
+              (0, 8, 1024, 512, 8, 8), (2, 2, 256, 128, 4, 4), (0, 3, 32, 96, 8, 8), (0, 16, 128, 128, 32, 32)]
+    shapes = shapes + [(0, 8, 256, 256, 4, 4)] * 50                      # > kTnMaxJobs jobs of one width: the table is flushed in between
+    jobs, refs = [], []
+    for mode, n, cin, cout, h, w in shapes:
+        oh, ow = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+        x = _nhwc(torch.randn((n, cin, h, w), device="cuda", generator=g), dt)
+        dz = _nhwc(torch.randn((n, cout, oh, ow), device="cuda", generator=g), dt)
+        xin = ops.space_to_depth2(x) if mode == 1 else x
+        numel = (16 if mode == 2 else 9) * cin * cout
+        ref = torch.zeros(numel, device="cuda")
+        ops.conv2d_wgrad(mode, xin, dz, cout, ref)
+        refs.append(ref)
+        jobs.append((mode, xin, dz, cout, torch.zeros(numel, device="cuda")))
+    ops.conv2d_wgrad_batch(jobs)
+    torch.cuda.synchronize()
+    for (mode, _, _, _, got), ref, shp in zip(jobs, refs, shapes):
+        assert torch.isfinite(got).all() and float(ref.abs().max()) > 0
+        assert rel_l2(got, ref) < 1e-5, shp          # split-K sums are fp32 atomics: order-dependent rounding only
