@@ -92,7 +92,12 @@ def lib():
         handle.b2_last_error.restype = ctypes.c_char_p
         handle.b2_version.restype = _I
         for name, args in SIGNATURES.items():
-            fn = getattr(handle, name)
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                if os.environ.get("SDM_B200_LIB"):       # an older A/B build (tools/): entry points added since are simply absent
+                    continue
+                raise B200Error(f"{LIB_PATH} does not export {name}: rebuild the extension (`make`)")
             fn.argtypes = args
             fn.restype = _I
         _lib = handle

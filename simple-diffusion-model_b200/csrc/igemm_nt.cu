@@ -143,7 +143,10 @@ constexpr int kMaxASlots = 4;
 #else
 #define B2_NT_BOUNDS __launch_bounds__(kThreads, 1)
 #endif
-template <typename T, int BLOCK_N, int STAGES, int CL, bool HALO = false>
+// B_MN: IgemmParams::b_mn as a COMPILE-TIME switch.  As a run-time one it put the B descriptor, its K step and the instruction
+// descriptor into per-thread registers, and the issue loop paid ten R2UR moves per K step (tensor pipe of the wide convs 82 -> 74 %
+// under ncu); as a template parameter the descriptors are immediates on the uniform datapath again.
+template <typename T, int BLOCK_N, int STAGES, int CL, bool HALO = false, bool B_MN = false>
 __global__ void B2_NT_BOUNDS
 igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ IgemmParams p) {
@@ -272,7 +275,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             uint8_t* b_dst = b_ring + s * S::B_BYTES;
                             if (elect_one()) {
                                 mbar_arrive_expect_tx(&full[s], S::B_BYTES);
-                                if (p.b_mn) {             // forward-layout weights, MN-major (IgemmParams::b_mn): (ci | co | ci slab | tap)
+                                if constexpr (B_MN) {     // forward-layout weights, MN-major (IgemmParams::b_mn): (ci | co | ci slab | tap)
                                     if constexpr (CL > 1) {
                                         constexpr int PIECE = BLOCK_N / CL;
                                         if constexpr (PIECE >= 64)
@@ -321,7 +324,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         } else if (load_a) {
                             mbar_arrive_expect_tx(&full[s], a_bytes + S::B_BYTES);
                             tma_load_4d(a_dst, &tmA, &full[s], kb * BK_ELEMS, aw, ah, an);
-                        } else if (p.b_mn) {
+                        } else if constexpr (B_MN) {
                             // data gradient straight from the FORWARD weights [Cout][tap][Cin] (IgemmParams::b_mn): the K block is 64
                             // output channels (rows) of the mirrored tap, the N tile BLOCK_N/64 slabs of 64 input channels
                             const int wt = p.taps - 1 - t;
@@ -351,10 +354,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (HALO) {
             {
                 // b_mn: the weights stage is BLOCK_N/64 MN-major slabs of [64 k rows][128 B] (8 KB apart); a 16-row K step is 2 KB
-                const uint32_t idesc = umma_idesc(1u, 128, BLOCK_N, 0, p.b_mn ? 1u : 0u);
+                constexpr uint32_t idesc = umma_idesc(1u, 128, BLOCK_N, 0, B_MN ? 1u : 0u);
                 const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);          // descriptor without its address field
-                const uint64_t bdesc0 = p.b_mn ? umma_desc_sw128(0, 64 * 128, 1024) : desc0;
-                const uint32_t bk_step = p.b_mn ? 128u : 2u;
+                const uint64_t bdesc0 = B_MN ? umma_desc_sw128(0, 64 * 128, 1024) : desc0;
+                constexpr uint32_t bk_step = B_MN ? 128u : 2u;
                 const uint32_t smem0 = smem_u32(smem) & 0x3FFFFu;      // CTA-local offset (see ptx.cuh: umma_desc_sw128)
                 const uint32_t ring0 = smem_u32(b_ring) & 0x3FFFFu;
                 int s = 0; uint32_t ph = 0;
@@ -408,10 +411,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else
         {
             // warp-uniform issue loop (see elect_one): all lanes wait and compute, one elected lane issues
-            const uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, p.b_mn ? 1u : 0u);
+            constexpr uint32_t idesc = umma_idesc(kTF32 ? 2u : 1u, 128, BLOCK_N, 0, B_MN ? 1u : 0u);
             const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);              // descriptor without its address field
-            const uint64_t bdesc0 = p.b_mn ? umma_desc_sw128(0, 64 * 128, 1024) : desc0;     // b_mn: MN-major slabs (see the halo branch)
-            const uint32_t bk_step = p.b_mn ? 128u : 2u;
+            const uint64_t bdesc0 = B_MN ? umma_desc_sw128(0, 64 * 128, 1024) : desc0;       // b_mn: MN-major slabs (see the halo branch)
+            constexpr uint32_t bk_step = B_MN ? 128u : 2u;
             const uint32_t smem0 = smem_u32(smem) & 0x3FFFFu;      // CTA-local offset (see ptx.cuh: umma_desc_sw128)
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
@@ -425,7 +428,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint64_t ad0 = desc0 + ((smem0 + s * S::STAGE_BYTES) >> 4);
-                    const uint64_t bd0 = bdesc0 + ((smem0 + s * S::STAGE_BYTES + S::A_BYTES) >> 4);
+                    const uint64_t bd0 = B_MN ? bdesc0 + ((smem0 + s * S::STAGE_BYTES + S::A_BYTES) >> 4) : ad0 + (S::A_BYTES >> 4);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -906,10 +909,10 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <typename T, int BLOCK_N, int STAGES, int CL, bool HALO = false>
+template <typename T, int BLOCK_N, int STAGES, int CL, bool HALO = false, bool B_MN = false>
 static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const IgemmParams& p, int num_sms, cudaStream_t st) {
     using S = IgemmSmem<BLOCK_N, STAGES>;
-    auto kern = igemm_nt_kernel<T, BLOCK_N, STAGES, CL, HALO>;
+    auto kern = igemm_nt_kernel<T, BLOCK_N, STAGES, CL, HALO, B_MN>;
     static bool attr_set = false;
     static int max_clusters = 0;
     constexpr int kHaloMax = 227 * 1024;               // halo mode sizes its buffers per layer: opt in to the maximum once
@@ -973,6 +976,23 @@ int launch_igemm_nt(int dtype /*0 bf16, 1 fp32(tf32)*/, const CUtensorMap& a, co
         return set_error("igemm_nt: swapped-operand mode needs the bf16 256-column kernel without cluster / split-K");
     if (p.b_mn && (dtype != 0 || p.b_mode || p.swap_ab || block_n / 64 < cl || p.Cout % 64))
         return set_error("igemm_nt: MN-major weights need the bf16 kernel, whole 64-channel slabs and cluster <= block_n / 64");
+    if (p.b_mn) {           // MN-major forward weights: separate instantiations (see igemm_nt_kernel: B_MN)
+        if (p.halo) {
+            if (p.splits != 1 || p.taps != 9) return set_error("igemm_nt (halo): bf16 3x3 stride-1 convolutions only");
+            if (cl == 1 && block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 1, true, true>(a, b, p, sms, st);
+            if (cl == 2 && block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 2, true, true>(a, b, p, sms, st);
+            return set_error("igemm_nt (halo, MN-major weights): unsupported block_n %d / cluster %d", block_n, cl);
+        }
+        if (cl == 1) {
+            if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 1, false, true>(a, b, p, sms, st);
+            if (block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 1, false, true>(a, b, p, sms, st);
+            if (block_n == 64)  return launch_cfg<__nv_bfloat16, 64, 8, 1, false, true>(a, b, p, sms, st);
+        } else if (cl == 2) {
+            if (block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 2, false, true>(a, b, p, sms, st);
+            if (block_n == 128) return launch_cfg<__nv_bfloat16, 128, 6, 2, false, true>(a, b, p, sms, st);
+        }
+        return set_error("igemm_nt (MN-major weights): unsupported block_n %d / cluster %d", block_n, cl);
+    }
     if (p.halo) {
         if (dtype != 0 || p.splits != 1 || p.b_mode || p.taps != 9) return set_error("igemm_nt (halo): bf16 3x3 stride-1 convolutions only");
         if (cl == 1 && block_n == 256) return launch_cfg<__nv_bfloat16, 256, 4, 1, true>(a, b, p, sms, st);

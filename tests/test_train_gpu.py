@@ -84,12 +84,14 @@ def test_fused_adagn_sums_backward_equals_the_two_pass_backward():
 @pytest.mark.parametrize("side_stream", [False, True])
 def test_deferred_grouped_weight_gradients_equal_per_layer_launches(side_stream):
     """Small-workload mode of the backward pass: the weight gradients of a module are deferred and run as one grouped launch
-    (b2_conv2d_wgrad_batch), optionally on the side stream -- same gradients as one launch per conv (fp32 atomics order only).
-    Also: data gradients from the forward weights (mode 5) and the dual-output forward convs against their unfused forms."""
+    (b2_conv2d_wgrad_batch), optionally on the side stream -- same gradients as one launch per conv.  Also: the unfused forms of the
+    dual-output forward convs and of the data gradients from the forward weights.  The default mode is not bitwise repeatable
+    (GroupNorm statistics and split-K sums are fp32 atomics, and one flipped bf16 rounding of an activation is 4e-3 of that
+    element), so every variant is held against the run-to-run noise of two identical runs; the op-level tests are exact."""
     fx = load_golden("unet_gpu_cond.pt")
     cond = fx["cond"].cuda()
-    grads, outs = [], []
-    for variant in ("reference", "grouped", "unfused"):
+    grads, outs = {}, {}
+    for variant in ("reference", "again", "grouped", "unfused"):
         net = _build(fx, "bf16")
         eng = net.engine()
         eng.group_wgrad = variant == "grouped"
@@ -100,10 +102,14 @@ def test_deferred_grouped_weight_gradients_equal_per_layer_launches(side_stream)
         out = net(fx["x"].cuda(), fx["t"].cuda(), cond)
         F.mse_loss(out, fx["target"].cuda()).backward()
         torch.cuda.synchronize()
-        outs.append(out.detach().clone())
-        grads.append(eng.layout.flat.clone())
-    # run-to-run noise of the default mode (GroupNorm statistics and split-K sums are fp32 atomics; one flipped bf16 rounding of an
-    # activation is 4e-3 of that element) bounds these from below; the op-level tests in test_kernels_gpu.py are exact
-    e_out, e_grp, e_unf = rel_l2(outs[2], outs[0]), rel_l2(grads[1], grads[0]), rel_l2(grads[2], grads[0])
-    print(f"forward unfused vs fused {e_out:.2e}; gradients grouped {e_grp:.2e}, unfused {e_unf:.2e}")
-    assert e_out < 1e-3 and e_grp < 5e-3 and e_unf < 5e-3
+        outs[variant] = out.detach().clone()
+        grads[variant] = eng.layout.flat.clone()
+    floor_out = rel_l2(outs["again"], outs["reference"])
+    floor_grad = rel_l2(grads["again"], grads["reference"])
+    e_out = rel_l2(outs["unfused"], outs["reference"])
+    e_grp, e_unf = rel_l2(grads["grouped"], grads["reference"]), rel_l2(grads["unfused"], grads["reference"])
+    print(f"noise floor: forward {floor_out:.2e}, gradients {floor_grad:.2e}; forward unfused {e_out:.2e}; "
+          f"gradients grouped {e_grp:.2e}, unfused {e_unf:.2e}")
+    tol_out, tol_grad = max(4 * floor_out, 5e-3), max(4 * floor_grad, 5e-3)     # a wrong kernel is off by O(1), not by rounding
+    assert e_out <= tol_out
+    assert e_grp <= tol_grad and e_unf <= tol_grad
