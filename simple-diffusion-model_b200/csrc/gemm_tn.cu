@@ -132,18 +132,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const TnWork wk = decode(item);
                 const int kb0 = (int)(((long long)k_boxes * wk.split) / p.splits);
                 const int kb1 = (int)(((long long)k_boxes * (wk.split + 1)) / p.splits);
+                // K-box coordinates advance incrementally: the divisions by kt_w / kt_h that decode kb cost ~8 % of this kernel's
+                // issue slots when they sat inside the loop (ncu source page, round 2) -- in the warps whose pace feeds the MMAs
+                int iw = kb0 % p.kt_w, ih = (kb0 / p.kt_w) % p.kt_h, in_ = kb0 / (p.kt_w * p.kt_h);
+                const int kt_w = p.kt_w, kt_h = p.kt_h, wb = p.wb, hb = p.hb, nb = p.nb;
+                const bool batched = p.batch_mode != 0;
+                const int dw = p.tap_dw[wk.tap], dh = batched ? 0 : p.tap_dh[wk.tap], dn = batched ? 0 : p.tap_dn[wk.tap];
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    int r = kb;
-                    const int w0 = (r % p.kt_w) * p.wb;  r /= p.kt_w;
-                    int h0 = (r % p.kt_h) * p.hb;  r /= p.kt_h;
-                    int n0 = r * p.nb;
-                    if (p.batch_mode) { h0 = wk.bh; n0 = wk.bn; }
+                    const int w0 = iw * wb;
+                    const int h0 = batched ? wk.bh : ih * hb;
+                    const int n0 = batched ? wk.bn : in_ * nb;
+                    if (++iw == kt_w) { iw = 0; if (++ih == kt_h) { ih = 0; ++in_; } }
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
                     uint8_t* b_dst = a_dst + A_BYTES;
-                    const int bw = w0 + p.tap_dw[wk.tap];
-                    const int bh = p.batch_mode ? h0 : h0 + p.tap_dh[wk.tap];
-                    const int bn = p.batch_mode ? n0 : n0 + p.tap_dn[wk.tap];
+                    const int bw = w0 + dw, bh = h0 + dh, bn = n0 + dn;
                     if (elect_one()) {
                     if (prod == 0) mbar_arrive_expect_tx(&full[s], (A_SLABS + B_SLABS) * box_rows * 128u);
                     if (p.box5) {
@@ -447,11 +450,11 @@ gemm_tn_grouped_kernel(const __grid_constant__ TnJobTable tab) {
                 const uint32_t box_rows = static_cast<uint32_t>(J.wb * J.hb * J.nb);
                 const uint32_t slab_stride = box_rows * 128u;
                 const int dw = J.tap_dw[wk.tap], dh = J.tap_dh[wk.tap], dn = J.tap_dn[wk.tap];
+                int iw = wk.kb0 % J.kt_w, ih = (wk.kb0 / J.kt_w) % J.kt_h, in_ = wk.kb0 / (J.kt_w * J.kt_h);
+                const int kt_w = J.kt_w, kt_h = J.kt_h, wb = J.wb, hb = J.hb, nb = J.nb;
                 for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
-                    int r = kb;
-                    const int w0 = (r % J.kt_w) * J.wb;  r /= J.kt_w;
-                    const int h0 = (r % J.kt_h) * J.hb;  r /= J.kt_h;
-                    const int n0 = r * J.nb;
+                    const int w0 = iw * wb, h0 = ih * hb, n0 = in_ * nb;
+                    if (++iw == kt_w) { iw = 0; if (++ih == kt_h) { ih = 0; ++in_; } }
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * STAGE_BYTES;
                     uint8_t* b_dst = a_dst + A_BYTES;

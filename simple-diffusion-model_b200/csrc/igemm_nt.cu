@@ -305,8 +305,8 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int bb2 = p.b_mode ? tc.h0 : tc.g;
                 const int bb3 = p.b_mode ? tc.n0 : 0;
                 const int it0 = (int)(((long long)k_iters * split) / splits), it1 = (int)(((long long)k_iters * (split + 1)) / splits);
+                int t = it0 / p.kb_per_tap, kb = it0 - t * p.kb_per_tap;       // (tap, K block) advance without a division per K step
                 for (int it = it0; it < it1; ++it) {
-                    const int t = it / p.kb_per_tap, kb = it - t * p.kb_per_tap;
                     const int ti = tc.g * p.taps + t;
                     const int aw = tc.w0 + p.tap_dw[ti], ah = tc.h0 + p.tap_dh[ti], an = tc.n0 + p.tap_dn[ti];
                     mbar_wait(&empty[s], ph ^ 1);
@@ -346,6 +346,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (++kb == p.kb_per_tap) { kb = 0; ++t; }
                 }
             }
         }
