@@ -360,6 +360,7 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
     p.b_mode = 0;
     p.splits = splits; p.ws = workspace(0).ws; p.ws_counters = workspace(0).counters;
     p.cluster = swapped ? 1 : pick_cluster(dtype, bn, splits, m_tiles * p.groups * p.n_tiles, m_tiles);
+    if (p.halo && p.cluster > 2) p.cluster = 2;               // halo kernels are instantiated for clusters of 1 and 2
     if (b_mn && p.cluster > 2) p.cluster = 2;                 // MN-major weights: instantiated for clusters of 1 and 2
     if (b_mn && p.cluster > bn / 64) p.cluster = bn / 64;
 
