@@ -86,6 +86,8 @@ class GraphedTrainStep:
                        "cond_img": clone(cond_img), "target": clone(target), "loss": torch.zeros((), dtype=torch.float32, device=dev)}
         n, _, h, w = x0.shape
         _auto_pdl(n, h, w)
+        # (the 128-channel conv variants are auto-tuned for inference graphs only -- GraphedUNet._capture: in the train step the
+        # swapped form won the micro-benchmark but not the step: 83.3 vs 82.9 ms, profiles/r02z13_autotune_ab.log)
         import os
         if os.environ.get("SDM_B200_OVERLAP_WGRAD") not in ("0", "1"):
             # small workloads are bound by the length of ~1.3 k short dependent kernels: weight gradients (off the critical path)
@@ -233,6 +235,8 @@ class GraphedUNet:
         dev = x.device
         eng = self.net.engine()
         _auto_pdl(x.shape[0], x.shape[2], x.shape[3])
+        from .autotune import tune_conv128
+        tune_conv128(self.net, x.shape[0], x.shape[2], x.shape[3], dev)
         st = {"x": x.detach().clone().contiguous().float(), "t": None if t is None else t.detach().clone().to(torch.int64),
               "cond": None if cond is None else cond.detach().clone().float(), "wkey": wkey}
         side = torch.cuda.Stream(device=dev)

@@ -301,7 +301,7 @@ static int conv2d_impl(int mode, const void* x, int N, int H, int W, int Cin, lo
     bool swapped = false;
     {
         const int swap_env = option("swap_ab", 0);
-        if (swap_env && !cs && !b_mn && mode == 0 && dtype == 0 && out_mode == 0 && Cout <= 128 && Cout >= 64 && p.cpg != 1 && !separate_stats && W <= 256) {
+        if (swap_env && !cs && !b_mn && !y2 && mode == 0 && dtype == 0 && out_mode == 0 && Cout <= 128 && Cout >= 64 && p.cpg != 1 && !separate_stats && W <= 256) {
             int wb2, hb2, nb2;
             pick_box(W, H, N, &wb2, &hb2, &nb2, 256);
             const long long tiles2 = (long long)((W + wb2 - 1) / wb2) * ((H + hb2 - 1) / hb2) * ((N + nb2 - 1) / nb2);
