@@ -105,6 +105,7 @@ class WeightCache:
         of the channels-last shadow; fp32 -> kernel-layout packs) instead of ~180 few-microsecond launches per train step."""
         tr, packs = [], {}
         pending = []
+        stale = []
         for key, (param, kind, code, cout, cin, cin_pad, family) in self._log.items():
             lay = getattr(param, "_b2_layout", None)
             if lay is None:
@@ -128,12 +129,22 @@ class WeightCache:
                     continue                      # channels-last stored parameter read through a permuted view: stays lazy
                 if self._from_shadow(param, lay, kind, code, cout, cin, cin_pad):
                     continue                      # made just in time from the bf16 copy (get)
+                if code == ops.BF16 and lay.shadow is not None and cin_pad == cin and id(param) in lay.offsets and \
+                        ((kind == 0 and lay.is_cl(param)) or kind == 3):
+                    # get() serves this layout straight from the optimiser's bf16 copy; the key was logged by the very first
+                    # forward, before that copy existed.  Re-packing it here cost one 0.48 ms launch per train step (all attention
+                    # Linear weights, round 2b) for buffers nobody read.
+                    stale.append(key)
+                    continue
                 shape = {0: (cout, 9 * cin_pad), 1: (cin, 9 * cin_pad), 2: (4 * cout, 4 * cin), 3: (cout, cin_pad), 4: (cin, cin_pad),
                          5: (4 * cin, 4 * cout), 6: (cin, 16 * cout)}[kind]
                 out = hit[1] if hit is not None and tuple(hit[1].shape) == shape else \
                     torch.empty(shape, dtype=ops.TORCH_DTYPE[code], device=param.device)
                 packs.setdefault(code, []).append((param.data_ptr(), out.data_ptr(), kind, cout, cin, cin_pad, out.numel()))
                 pending.append((key, ver, out))
+        for key in stale:
+            self._log.pop(key, None)
+            self._packed.pop(key, None)
         if not pending:
             return
         dev = pending[0][2].device
@@ -148,6 +159,10 @@ class WeightCache:
                 ok = False
             else:
                 call("b2_transpose_weight_cl_multi", ptr(table), len(rows), start, stream())
+        import os
+        if os.environ.get("SDM_B200_DEBUG_PACKS") and packs:
+            for code, jobs in packs.items():
+                print("[b200] bulk weight packs:", [(kind, cout, cin, numel) for _, _, kind, cout, cin, _, numel in jobs], flush=True)
         for code, jobs in packs.items():
             rows, start = [], 0
             for w, out, kind, cout, cin, k_pad, numel in jobs:
