@@ -28,6 +28,7 @@ SIGNATURES = {
     "b2_conv3x3_first": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_conv3x3_last": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_gemm_nt": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P, _F, _I, _P, _L, _I, _I, _P],
+    "b2_gemm_nt_bmn": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _I, _P],
     "b2_attn_scores_softmax": [_P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P],
     "b2_attn_scores_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _L, _I, _I, _I, _I, _F, _I, _P],
     "b2_rowdot": [_P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P],
@@ -115,7 +116,7 @@ def set_launch_hook(hook):
 
 _WORKSPACE = {}       # device index -> zeroed split-K workspace registered with the library (b2_set_workspace)
 WORKSPACE_BYTES = 128 << 20
-_WORKSPACE_USERS = ("b2_conv2d_nhwc", "b2_conv2d_nhwc_colsum", "b2_conv2d_nhwc_dual", "b2_gemm_nt", "b2_conv2d_wgrad", "b2_conv2d_wgrad_batch", "b2_gemm_tn")
+_WORKSPACE_USERS = ("b2_conv2d_nhwc", "b2_conv2d_nhwc_colsum", "b2_conv2d_nhwc_dual", "b2_gemm_nt", "b2_gemm_nt_bmn", "b2_conv2d_wgrad", "b2_conv2d_wgrad_batch", "b2_gemm_tn")
 
 
 def _ensure_workspace():

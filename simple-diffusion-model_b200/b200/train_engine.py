@@ -213,6 +213,7 @@ class UNetTrainEngine(UNetEngine):
         # and at small batches the step is bound by the number of ~16 us dependent launches
         self.group_wgrad = os.environ.get("SDM_B200_GROUP_WGRAD", "0") == "1"
         self._wgrad_jobs = []
+        self.attn_bmn = os.environ.get("SDM_B200_ATTN_BMN", "1") == "1"      # attention backward reads dO / Q in place (see _bwd_attention)
         # un-normalised convs store z and Swish(z) from one epilogue (b2_conv2d_nhwc_dual); SDM_B200_FUSE_FWD_ACT=0: separate pass
         self.fuse_fwd_act = os.environ.get("SDM_B200_FUSE_FWD_ACT", "1") == "1"
         self.post_backward = None          # optional callable(layout), runs when every gradient is complete
@@ -698,9 +699,15 @@ class UNetTrainEngine(UNetEngine):
                  p_len, d, heads, n, code, stream())
             return out_t
 
+        # bf16: dO and Q are consumed in place, MN-major (b2_gemm_nt_bmn) -- no transposed copies (60 launches per step before)
+        bmn = self.attn_bmn and code == ops.BF16 and d % 64 == 0
         # dV[j][c] = sum_i P^T[j][i] dO[i][c]
-        ops.gemm_nt(pt, transposed(d_o, hd, (d, p_len * hd)), p_len, d, p_len, ldp, ldp, dqkv[:, 2 * d:], ldq, batch=(heads, n),
-                    a_strides=pt_s, b_strides=t_s, c_strides=qkv_s, code=code)
+        if bmn:
+            ops.gemm_nt_bmn(pt, d_o, p_len, d, p_len, ldp, hd, dqkv[:, 2 * d:], ldq, batch=(heads, n), a_strides=pt_s,
+                            b_strides=(d, p_len * hd), c_strides=qkv_s)
+        else:
+            ops.gemm_nt(pt, transposed(d_o, hd, (d, p_len * hd)), p_len, d, p_len, ldp, ldp, dqkv[:, 2 * d:], ldq, batch=(heads, n),
+                        a_strides=pt_s, b_strides=t_s, c_strides=qkv_s, code=code)
         # softmax backward needs sum_i P^T dP^T per key, which equals sum_c V[j][c] dV[j][c]: a row dot product
         dot = torch.empty((rows, heads), dtype=torch.float32, device=dev)
         call("b2_rowdot", ptr(qkv[:, 2 * d:]), ldq, ptr(dqkv[:, 2 * d:]), ldq, 3 * d, ptr(dot), rows, heads, d, code, stream())
@@ -712,8 +719,12 @@ class UNetTrainEngine(UNetEngine):
         ops.gemm_tn(dst, qkv[:, d:], p_len, d, p_len, ldp, ldq, dqkv, ldq, out_mode=1, batch=(heads, n),
                     a_strides=pt_s, b_strides=qkv_s, c_strides=qkv_s, code=code)
         # dK[j][c] = sum_i dS^T[j][i] Q[i][c]
-        ops.gemm_nt(dst, transposed(qkv, ldq, qkv_s), p_len, d, p_len, ldp, ldp, dqkv[:, d:], ldq, batch=(heads, n),
-                    a_strides=pt_s, b_strides=t_s, c_strides=qkv_s, code=code)
+        if bmn:
+            ops.gemm_nt_bmn(dst, qkv, p_len, d, p_len, ldp, ldq, dqkv[:, d:], ldq, batch=(heads, n), a_strides=pt_s,
+                            b_strides=qkv_s, c_strides=qkv_s)
+        else:
+            ops.gemm_nt(dst, transposed(qkv, ldq, qkv_s), p_len, d, p_len, ldp, ldp, dqkv[:, d:], ldq, batch=(heads, n),
+                        a_strides=pt_s, b_strides=t_s, c_strides=qkv_s, code=code)
         # input projection: qkv = x Wp^T + bp
         ops.act(2, dqkv, None, None, lay.view(blk.projection.bias), rows, ldq, ldq, 0, 0, code)
         ops.gemm_tn(dqkv, x, ldq, c, rows, ldq, ldx, lay.view(blk.projection.weight), c, code=code)

@@ -445,6 +445,51 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
 
 // ================================================================================================ attention scores
 namespace b2 {
+// b2_gemm_nt with B given UN-transposed, [b2][b1][k][n] (row stride ldb): C = alpha * A . B.  The NT kernel consumes it MN-major
+// (igemm.h: b_mn), so the attention backward products dV = P^T dO and dK = dS^T Q (autograd of custom_layers.py:144-150) need no
+// transposed copies of dO / Q.  bf16 only; Ncols a multiple of 64; always batched addressing (batch1 = batch2 = 1 is fine).
+extern "C" int b2_gemm_nt_bmn(const void* A, long long lda, long long a_s1, long long a_s2, const void* B, long long ldb,
+                              long long b_s1, long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2,
+                              int M, int Ncols, int K, int batch1, int batch2, float alpha, int dtype, void* stream) {
+    if (dtype != 0) return set_error("b2_gemm_nt_bmn: bf16 only");
+    const int eb = 2, bk = 64;
+    if (Ncols % 64) return set_error("b2_gemm_nt_bmn: Ncols must be a multiple of 64");
+    if ((lda * eb) % 16 || (ldb * eb) % 16 || (b_s1 * eb) % 16 || (b_s2 * eb) % 16) return set_error("b2_gemm_nt_bmn: strides must be 16-byte multiples");
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.W = M; p.H = batch1; p.N = batch2;
+    p.wb = 128; p.hb = 1; p.nb = 1;
+    p.tiles_w = (M + 127) / 128; p.tiles_h = batch1; p.tiles_n = batch2;
+    p.groups = 1; p.taps = 1; p.kb_per_tap = (K + bk - 1) / bk;   // K tail is zero-filled by TMA (both operands)
+    p.Cout = Ncols;
+    p.out = C; p.oN = c_s2; p.oH = c_s1; p.oW = ldc; p.oC = 1;
+    p.vec_ok = ((ldc % 8 == 0) && (c_s1 % 8 == 0) && (c_s2 % 8 == 0) && ((uintptr_t)C % 16 == 0)) ? 1 : 0;
+    p.alpha = alpha;
+    p.b_mode = 1;
+    p.b_mn = 1;
+    int bn, splits;
+    pick_tiling(Ncols, (long long)p.tiles_w * batch1 * batch2, 1, p.kb_per_tap, false, &bn, &splits);
+    p.n_tiles = (Ncols + bn - 1) / bn;
+    p.splits = 1; p.ws = workspace(0).ws; p.ws_counters = workspace(0).counters;
+    p.cluster = 1;
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch1, (uint64_t)batch2};
+        uint64_t str[3] = {(uint64_t)lda * eb, (uint64_t)(batch1 > 1 ? a_s1 : lda * M) * eb,
+                           (uint64_t)(batch2 > 1 ? a_s2 : lda * M * batch1) * eb};
+        uint32_t box[4] = {(uint32_t)bk, 128, 1, 1};
+        if (make_tmap_4d(&ta, A, eb, dims, str, box)) return 1;
+    }
+    {
+        uint64_t dims[5] = {64, (uint64_t)K, (uint64_t)Ncols / 64, (uint64_t)batch1, (uint64_t)batch2};
+        uint64_t str[4] = {(uint64_t)ldb * eb, 128, (uint64_t)(batch1 > 1 ? b_s1 : ldb * K) * eb,
+                           (uint64_t)(batch2 > 1 ? b_s2 : ldb * K * batch1) * eb};
+        uint32_t box[5] = {64, 64, (uint32_t)(bn / 64), 1, 1};
+        if (make_tmap_nd(&tb, B, eb, 5, dims, str, box)) return 1;
+    }
+    return launch_igemm_nt(dtype, ta, tb, p, bn, (cudaStream_t)stream);
+}
+
 int launch_softmax_fixup(void* pt, long long ldp, const float* stats, long long rows, int P, int n_tiles, int tile_cols, int dtype,
                          cudaStream_t st);
 }

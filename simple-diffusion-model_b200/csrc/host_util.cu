@@ -96,6 +96,27 @@ int make_tmap_5d_slabs(CUtensorMap* out, const void* base, int elem_bytes, const
     return 0;
 }
 
+int make_tmap_nd(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    if (rank < 3 || rank > 5) return set_error("make_tmap_nd: rank %d", rank);
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("TMA base pointer not 16-byte aligned");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gs[i] = strides_bytes[i];
+        if (gs[i] % 16 != 0) return set_error("TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+    }
+    if (box[0] * elem_bytes != 128) return set_error("TMA inner box must be 128 bytes");
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(out, dt, rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r);
+    return 0;
+}
+
 static int g_pdl = -1;
 bool pdl_enabled() {
     if (g_pdl < 0) {

@@ -22,6 +22,10 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
 int make_tmap_5d_slabs(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4],
                        const uint64_t strides_bytes[3], const uint32_t box[4], uint32_t slabs_per_box, bool atom32 = false);
 
+// Generic tiled map of rank 3..5 (SWIZZLE_128B, inner box = 128 bytes): dims / box have `rank` entries, strides rank - 1.
+int make_tmap_nd(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box);
+
 // Programmatic dependent launch (PDL): every kernel of this library begins with griddepcontrol.launch_dependents and
 // executes griddepcontrol.wait before it touches global memory, so the next kernel's CTAs may be scheduled -- and run their
 // prologue (barrier init, TMEM allocation, descriptor prefetch) -- while the previous grid drains, instead of paying the

@@ -333,6 +333,9 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 if constexpr (PIECE >= 64)
                                     tma_load_4d_mc(b_dst + crank * PIECE * 128, &tmB, &full[s], 0, kb * 64,
                                                    tc.nt * (BLOCK_N / 64) + crank * (PIECE / 64), wt, kMask);
+                            } else if (p.b_mode) {
+                                // batched GEMM with B given as [K][Ncols] (b2_gemm_nt_bmn): (n | k | n slab | batch 1 | batch 2)
+                                tma_load_5d(b_dst, &tmB, &full[s], 0, kb * 64, tc.nt * (BLOCK_N / 64), bb2, bb3);
                             } else {
                                 tma_load_4d(b_dst, &tmB, &full[s], 0, kb * 64, tc.nt * (BLOCK_N / 64), wt);
                             }
@@ -975,7 +978,7 @@ int launch_igemm_nt(int dtype /*0 bf16, 1 fp32(tf32)*/, const CUtensorMap& a, co
     if (cl > 1 && (p.splits != 1 || p.b_mode || p.act == 4)) return set_error("igemm_nt: cluster multicast needs an unsplit, unbatched GEMM");
     if (p.swap_ab && (dtype != 0 || block_n != 256 || cl != 1 || p.splits != 1 || p.halo || p.out_fp32))
         return set_error("igemm_nt: swapped-operand mode needs the bf16 256-column kernel without cluster / split-K");
-    if (p.b_mn && (dtype != 0 || p.b_mode || p.swap_ab || block_n / 64 < cl || p.Cout % 64))
+    if (p.b_mn && (dtype != 0 || (p.b_mode && cl != 1) || p.swap_ab || block_n / 64 < cl || p.Cout % 64))
         return set_error("igemm_nt: MN-major weights need the bf16 kernel, whole 64-channel slabs and cluster <= block_n / 64");
     if (p.b_mn) {           // MN-major forward weights: separate instantiations (see igemm_nt_kernel: B_MN)
         if (p.halo) {

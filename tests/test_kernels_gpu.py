@@ -494,3 +494,32 @@ def test_grouped_weight_gradients_match_individual_launches():
     for (mode, _, _, _, got), ref, shp in zip(jobs, refs, shapes):
         assert torch.isfinite(got).all() and float(ref.abs().max()) > 0
         assert rel_l2(got, ref) < 1e-5, shp          # split-K sums are fp32 atomics: order-dependent rounding only
+
+
+@pytest.mark.parametrize("cfg", [(64, 128, 1, 2), (256, 512, 2, 3), (324, 64, 4, 1), (1024, 256, 1, 2)])
+def test_batched_gemm_with_untransposed_b_matches_transposed_copy(cfg):
+    """b2_gemm_nt_bmn (B = [K][Ncols] consumed MN-major) == b2_gemm_nt on an explicit transposed copy of B, per (head, image) batch
+    entry, with the strided layouts of the attention backward (dV = P^T dO, dK = dS^T Q; autograd of custom_layers.py:144-150)."""
+    from b200 import ops
+    p_len, d, heads, n = cfg
+    dt = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(9)
+    ldp = (p_len + 7) // 8 * 8
+    pt = torch.zeros((n, heads, p_len, ldp), dtype=dt, device="cuda")
+    pt[..., :p_len] = (torch.randn((n, heads, p_len, p_len), device="cuda", generator=g) * 0.1).to(dt)
+    ldq = 3 * heads * d
+    qkv = (torch.randn((n * p_len, ldq), device="cuda", generator=g) * 0.5).to(dt)          # B = Q: columns [h*3d, h*3d + d)
+    pt_s, qkv_s = (p_len * ldp, heads * p_len * ldp), (3 * d, p_len * ldq)
+    got = torch.zeros((n * p_len, ldq), dtype=dt, device="cuda")
+    ops.gemm_nt_bmn(pt, qkv, p_len, d, p_len, ldp, ldq, got[:, d:], ldq, batch=(heads, n), a_strides=pt_s, b_strides=qkv_s,
+                    c_strides=qkv_s)
+    want = torch.zeros_like(got)
+    qt = torch.zeros((n, heads, d, ldp), dtype=dt, device="cuda")
+    q4 = qkv.view(n, p_len, heads, 3 * d)[..., :d]                                           # [n][i][h][c]
+    qt[..., :p_len] = q4.permute(0, 2, 3, 1)
+    ops.gemm_nt(pt, qt, p_len, d, p_len, ldp, ldp, want[:, d:], ldq, batch=(heads, n), a_strides=pt_s,
+                b_strides=(d * ldp, heads * d * ldp), c_strides=qkv_s, code=0)
+    torch.cuda.synchronize()
+    ref = torch.einsum("nhji,nihc->njhc", pt[..., :p_len].float(), q4.float())
+    assert torch.equal(got, want), "same products in the same order"
+    assert rel_l2(got.view(n, p_len, heads, 3 * d)[..., d:2 * d].float(), ref) < 1e-2
