@@ -84,10 +84,11 @@ int b2_gemm_nt(const void* A, long long lda, long long a_s1, long long a_s2, con
                const void* residual, long long ldr, int out_fp32, int dtype, void* stream);
 /* b2_gemm_nt with B given UN-transposed, [batch2][batch1][K][Ncols] (row stride ldb): C = alpha * A . B, bf16, Ncols % 64 == 0.
  * The attention backward products dV = P^T dO and dK = dS^T Q (autograd of custom_layers.py:144-150) read dO / Q in place --
- * the tensor-core kernel consumes B MN-major -- instead of through transposed copies. */
+ * the tensor-core kernel consumes B MN-major -- instead of through transposed copies; likewise the Linear data gradients
+ * dX = dY W (+ residual, unbatched) read the forward weight [out][in] in place. */
 int b2_gemm_nt_bmn(const void* A, long long lda, long long a_s1, long long a_s2, const void* B, long long ldb, long long b_s1,
                    long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2, int M, int Ncols, int K, int batch1,
-                   int batch2, float alpha, int dtype, void* stream);
+                   int batch2, float alpha, const void* residual, long long ldr, int dtype, void* stream);
 
 /* Fused attention scores (custom_layers.py:144-147): P^T[n][h][j][i] = softmax over the QUERY index i of
  * scale * q_i . k_j, computed as S^T = K Q^T on the tensor cores with the softmax in the epilogue (one thread owns one

@@ -28,7 +28,7 @@ SIGNATURES = {
     "b2_conv3x3_first": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_conv3x3_last": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2_gemm_nt": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _P, _F, _I, _P, _L, _I, _I, _P],
-    "b2_gemm_nt_bmn": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b2_gemm_nt_bmn": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _P, _L, _I, _P],
     "b2_attn_scores_softmax": [_P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P],
     "b2_attn_scores_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _L, _I, _I, _I, _I, _F, _I, _P],
     "b2_rowdot": [_P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P],

@@ -87,10 +87,11 @@ def gemm_nt(a, b, m, ncols, k, lda, ldb, out, ldc, bias=None, alpha=1.0, act=0, 
 
 
 def gemm_nt_bmn(a, b, m, ncols, k, lda, ldb, out, ldc, alpha=1.0, batch=(1, 1), a_strides=(0, 0), b_strides=(0, 0),
-                c_strides=(0, 0)):
-    """out = alpha * a @ b with b given un-transposed ([k][ncols] rows of stride ldb per batch entry): bf16, ncols % 64 == 0."""
+                c_strides=(0, 0), residual=None, ldr=0):
+    """out = alpha * a @ b (+ residual) with b given un-transposed ([k][ncols] rows of stride ldb per batch entry): bf16,
+    ncols % 64 == 0."""
     call("b2_gemm_nt_bmn", ptr(a), lda, a_strides[0], a_strides[1], ptr(b), ldb, b_strides[0], b_strides[1], ptr(out), ldc,
-         c_strides[0], c_strides[1], m, ncols, k, batch[0], batch[1], float(alpha), code_of(a), stream())
+         c_strides[0], c_strides[1], m, ncols, k, batch[0], batch[1], float(alpha), ptr(residual), ldr, code_of(a), stream())
     return out
 
 

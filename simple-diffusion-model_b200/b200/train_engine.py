@@ -685,9 +685,16 @@ class UNetTrainEngine(UNetEngine):
         # output projection: out = o Wo^T + bo + x
         ops.act(2, dout, None, None, lay.view(blk.output.bias), rows, c, ldd, 0, 0, code)
         ops.gemm_tn(dout, o, c, hd, rows, ldd, hd, lay.view(blk.output.weight), hd, code=code)
-        wo_t = self.cache.get(blk.output.weight, 4, code, c, hd, c)               # [hd][C]
         d_o = torch.empty((rows, hd), dtype=dt, device=dev)
-        ops.gemm_nt(dout, wo_t, rows, hd, c, ldd, c, d_o, hd)
+        # bf16 with the optimiser's copy of the weights: the Linear data gradients read W [out][in] in place (MN-major B)
+        w_o = lay.shadow_slice(blk.output.weight) if (self.attn_bmn and code == ops.BF16 and lay.shadow is not None
+                                                       and c % 64 == 0 and hd % 64 == 0 and id(blk.output.weight) in lay.offsets
+                                                       and id(blk.projection.weight) in lay.offsets) else None
+        if w_o is not None:
+            ops.gemm_nt_bmn(dout, w_o, rows, hd, c, ldd, hd, d_o, hd)
+        else:
+            wo_t = self.cache.get(blk.output.weight, 4, code, c, hd, c)               # [hd][C]
+            ops.gemm_nt(dout, wo_t, rows, hd, c, ldd, c, d_o, hd)
         dqkv = torch.empty((rows, ldq), dtype=dt, device=dev)
         pt_s, t_s = (p_len * ldp, heads * p_len * ldp), (d * ldp, heads * d * ldp)      # batch strides of P^T-shaped / transposed tensors
         qkv_s = (3 * d, p_len * ldq)
@@ -728,9 +735,12 @@ class UNetTrainEngine(UNetEngine):
         # input projection: qkv = x Wp^T + bp
         ops.act(2, dqkv, None, None, lay.view(blk.projection.bias), rows, ldq, ldq, 0, 0, code)
         ops.gemm_tn(dqkv, x, ldq, c, rows, ldq, ldx, lay.view(blk.projection.weight), c, code=code)
-        wp_t = self.cache.get(blk.projection.weight, 4, code, ldq, c, ldq)          # [C][3hd]
         dx = torch.empty((n, hh, ww, c), dtype=dt, device=dev)
-        ops.gemm_nt(dqkv, wp_t, rows, c, ldq, ldq, ldq, dx, c, residual=dout, ldr=ldd)
+        if w_o is not None:
+            ops.gemm_nt_bmn(dqkv, lay.shadow_slice(blk.projection.weight), rows, c, ldq, ldq, c, dx, c, residual=dout, ldr=ldd)
+        else:
+            wp_t = self.cache.get(blk.projection.weight, 4, code, ldq, c, ldq)          # [C][3hd]
+            ops.gemm_nt(dqkv, wp_t, rows, c, ldq, ldq, ldq, dx, c, residual=dout, ldr=ldd)
         return dx
 
     def _ones(self, n, device):

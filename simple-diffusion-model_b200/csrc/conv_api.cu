@@ -447,11 +447,14 @@ extern "C" int b2_gemm_nt(const void* A, long long lda, long long a_s1, long lon
 namespace b2 {
 // b2_gemm_nt with B given UN-transposed, [b2][b1][k][n] (row stride ldb): C = alpha * A . B.  The NT kernel consumes it MN-major
 // (igemm.h: b_mn), so the attention backward products dV = P^T dO and dK = dS^T Q (autograd of custom_layers.py:144-150) need no
-// transposed copies of dO / Q.  bf16 only; Ncols a multiple of 64; always batched addressing (batch1 = batch2 = 1 is fine).
+// transposed copies of dO / Q, and the Linear data gradients (dX = dY W, custom_layers.py:116,119) read the forward weight [out][in]
+// in place.  bf16 only; Ncols a multiple of 64; always batched addressing (batch1 = batch2 = 1 is fine); residual: unbatched only.
 extern "C" int b2_gemm_nt_bmn(const void* A, long long lda, long long a_s1, long long a_s2, const void* B, long long ldb,
                               long long b_s1, long long b_s2, void* C, long long ldc, long long c_s1, long long c_s2,
-                              int M, int Ncols, int K, int batch1, int batch2, float alpha, int dtype, void* stream) {
+                              int M, int Ncols, int K, int batch1, int batch2, float alpha, const void* residual, long long ldr,
+                              int dtype, void* stream) {
     if (dtype != 0) return set_error("b2_gemm_nt_bmn: bf16 only");
+    if (residual && (batch1 != 1 || batch2 != 1)) return set_error("b2_gemm_nt_bmn: residual only for unbatched GEMM");
     const int eb = 2, bk = 64;
     if (Ncols % 64) return set_error("b2_gemm_nt_bmn: Ncols must be a multiple of 64");
     if ((lda * eb) % 16 || (ldb * eb) % 16 || (b_s1 * eb) % 16 || (b_s2 * eb) % 16) return set_error("b2_gemm_nt_bmn: strides must be 16-byte multiples");
@@ -463,7 +466,9 @@ extern "C" int b2_gemm_nt_bmn(const void* A, long long lda, long long a_s1, long
     p.groups = 1; p.taps = 1; p.kb_per_tap = (K + bk - 1) / bk;   // K tail is zero-filled by TMA (both operands)
     p.Cout = Ncols;
     p.out = C; p.oN = c_s2; p.oH = c_s1; p.oW = ldc; p.oC = 1;
-    p.vec_ok = ((ldc % 8 == 0) && (c_s1 % 8 == 0) && (c_s2 % 8 == 0) && ((uintptr_t)C % 16 == 0)) ? 1 : 0;
+    p.vec_ok = ((ldc % 8 == 0) && (c_s1 % 8 == 0) && (c_s2 % 8 == 0) && ((uintptr_t)C % 16 == 0) &&
+                (!residual || ((ldr % 8 == 0) && ((uintptr_t)residual % 16 == 0)))) ? 1 : 0;
+    p.residual = residual; p.rN = 0; p.rH = 0; p.rW = ldr;
     p.alpha = alpha;
     p.b_mode = 1;
     p.b_mn = 1;

@@ -523,3 +523,25 @@ def test_batched_gemm_with_untransposed_b_matches_transposed_copy(cfg):
     ref = torch.einsum("nhji,nihc->njhc", pt[..., :p_len].float(), q4.float())
     assert torch.equal(got, want), "same products in the same order"
     assert rel_l2(got.view(n, p_len, heads, 3 * d)[..., d:2 * d].float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("cfg", [(4096, 512, 512), (33000, 1536, 512), (200, 128, 384)])
+def test_linear_data_gradient_reads_the_forward_weight_in_place(cfg):
+    """dX = dY W (+ residual) with W = the forward Linear weight [out][in] consumed MN-major (b2_gemm_nt_bmn, unbatched) == the NT
+    GEMM on an explicit transposed copy, bit for bit (autograd of custom_layers.py:116,119)."""
+    from b200 import ops
+    rows, n_out, n_in = cfg
+    dt = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(13)
+    dy = (torch.randn((rows, n_out), device="cuda", generator=g) * 0.5).to(dt)
+    w = (torch.randn((n_out, n_in), device="cuda", generator=g) * 0.05).to(dt)
+    res = (torch.randn((rows, n_in), device="cuda", generator=g) * 0.5).to(dt)
+    for residual in (None, res):
+        got = torch.empty((rows, n_in), dtype=dt, device="cuda")
+        want = torch.empty_like(got)
+        ops.gemm_nt_bmn(dy, w, rows, n_in, n_out, n_out, n_in, got, n_in, residual=residual, ldr=n_in)
+        ops.gemm_nt(dy, w.t().contiguous(), rows, n_in, n_out, n_out, n_out, want, n_in, residual=residual, ldr=n_in)
+        torch.cuda.synchronize()
+        ref = dy.float() @ w.float() + (residual.float() if residual is not None else 0)
+        assert rel_l2(got.float(), ref) < 1e-2
+        assert rel_l2(got.float(), want.float()) < 1e-6          # split-K / cluster choices may differ between the two entry points
