@@ -306,9 +306,15 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int bb3 = p.b_mode ? tc.n0 : 0;
                 const int it0 = (int)(((long long)k_iters * split) / splits), it1 = (int)(((long long)k_iters * (split + 1)) / splits);
                 int t = it0 / p.kb_per_tap, kb = it0 - t * p.kb_per_tap;       // (tap, K block) advance without a division per K step
-                for (int it = it0; it < it1; ++it) {
+                // the tap's box origin changes once per kb_per_tap K steps: looked up then, not per step (the indexed constant loads
+                // were a third of the A producer's samples in the ncu source page of the 1024-channel conv)
+                int aw = 0, ah = 0, an = 0;
+                auto tap_origin = [&]() {
                     const int ti = tc.g * p.taps + t;
-                    const int aw = tc.w0 + p.tap_dw[ti], ah = tc.h0 + p.tap_dh[ti], an = tc.n0 + p.tap_dn[ti];
+                    aw = tc.w0 + p.tap_dw[ti]; ah = tc.h0 + p.tap_dh[ti]; an = tc.n0 + p.tap_dn[ti];
+                };
+                if (it0 < it1) tap_origin();
+                for (int it = it0; it < it1; ++it) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * S::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + S::A_BYTES;
@@ -349,7 +355,7 @@ igemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
-                    if (++kb == p.kb_per_tap) { kb = 0; ++t; }
+                    if (++kb == p.kb_per_tap) { kb = 0; ++t; if (it + 1 < it1) tap_origin(); }
                 }
             }
         }
