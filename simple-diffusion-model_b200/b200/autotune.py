@@ -73,3 +73,12 @@ def tune_conv128(net, n, h, w, device):
     set_option("halo", halo)
     set_option("swap_ab", swap)
     return halo, swap
+
+
+def reset_conv128():
+    """Back to the library's default choice (halo tiles) unless the environment pins one: the train step keeps the default -- see
+    GraphedTrainStep._capture -- even when an inference graph captured earlier in the process selected another form."""
+    if "SDM_B200_HALO" in os.environ or "SDM_B200_SWAP_AB" in os.environ:
+        return
+    set_option("halo", 1)
+    set_option("swap_ab", 0)

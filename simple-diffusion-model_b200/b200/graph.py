@@ -88,6 +88,8 @@ class GraphedTrainStep:
         _auto_pdl(n, h, w)
         # (the 128-channel conv variants are auto-tuned for inference graphs only -- GraphedUNet._capture: in the train step the
         # swapped form won the micro-benchmark but not the step: 83.3 vs 82.9 ms, profiles/r02z13_autotune_ab.log)
+        from .autotune import reset_conv128
+        reset_conv128()
         import os
         if os.environ.get("SDM_B200_OVERLAP_WGRAD") not in ("0", "1"):
             # small workloads are bound by the length of ~1.3 k short dependent kernels: weight gradients (off the critical path)
