@@ -41,11 +41,13 @@ def tune_conv128(net, n, h, w, device):
     if os.environ.get("SDM_B200_AUTOTUNE", "1") == "0" or "SDM_B200_HALO" in os.environ or "SDM_B200_SWAP_AB" in os.environ:
         return None
     from . import is_deterministic
-    if getattr(net, "precision", "bf16") != "bf16" or torch.cuda.is_current_stream_capturing() or is_deterministic():
+    if getattr(net, "precision", "bf16") != "bf16" or is_deterministic():
         return None          # deterministic mode: one fixed kernel choice, whatever the batch size (sharded == unsharded bitwise)
     first = net.in_layer[1].conv_layer[0]
     if tuple(first.weight.shape[:2]) != (128, 128):
         return None          # only the class-default width has dedicated variants
+    if not torch.cuda.is_available() or torch.cuda.is_current_stream_capturing():
+        return None
     dev = torch.device(device)
     key = (n, h, w, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _CHOICE:
